@@ -1,0 +1,92 @@
+"""ORACLE (test infrastructure only) -- restatement of mr_gan.py's epoch loop
+(mr_gan.py:183-234) and fold preparation (mr_gan.py:86-107) on top of the step oracle.
+
+PARITY UNPINNED (see gan_oracle.py header).  The loop takes the epoch index
+arrays as INPUTS (the reference builds them with unseeded numpy permutations,
+mr_gan.py:189-202) and replays the device noise stream (oracle/philox.py), so
+that the CUDA epoch path and this loop see identical batches and noise.
+Never imported by the product path.
+"""
+import numpy as np
+
+from . import gan_oracle as O
+from . import philox
+
+
+def d_noise(key, step, rows, D, row0, tids=philox.TID_D_LAYER):
+    """The 5 GaussianNoise draws of one D application on stacked rows [row0, row0+rows)."""
+    widths = (D,) + O.D_WIDTHS[:4]
+    return [philox.normal(key, step, tids[l], rows, widths[l], row0=row0) for l in range(5)]
+
+
+def prep_fold(X_train, X_test, y_train, y_test, percentlabeled, percentunlabeled, rng, K=O.K_CLASSES):
+    """mr_gan.py:96-107: StandardScaler, shuffle, first 10*percent rows per class as labeled.
+
+    Returns scaled train/test plus ROW INDICES (into the shuffled train set) of
+    the labeled subset and (table 6) of the unlabeled subset.
+    """
+    mu = X_train.mean(axis=0)
+    sd = X_train.std(axis=0)
+    sd = np.where(sd == 0.0, 1.0, sd)               # sklearn's zero-variance guard
+    Xtr, Xte = (X_train - mu) / sd, (X_test - mu) / sd
+    perm = rng.permutation(len(Xtr))                # sklearn.utils.shuffle
+    Xtr, ytr = Xtr[perm], y_train[perm]
+    nlab = int(10 * percentlabeled)
+    lab_rows = np.concatenate([np.nonzero(ytr == j)[0][:nlab] for j in range(K)])
+    unl_rows = None
+    if percentunlabeled is not None:
+        nun = nlab + int(10 * percentunlabeled)
+        unl_rows = np.concatenate([np.nonzero(ytr == j)[0][:nun] for j in range(K)])
+    return Xtr, Xte, ytr, y_test, lab_rows, unl_rows
+
+
+def tiled_perm(rng, n_total, n_sub):
+    """mr_gan.py:189 (and :197-201): floor(N/L) permutations of L plus one of N mod L."""
+    parts = [rng.permutation(n_sub) for _ in range(n_total // n_sub)]
+    parts.append(rng.permutation(n_total % n_sub))
+    return np.concatenate(parts).astype(np.int64)
+
+
+def epoch_indices(rng, n_train, lab_rows, unl_rows=None):
+    """Row indices (into X_train) of the 3 streams used by one epoch, mr_gan.py:189-202.
+
+    The reference also draws a third unlabeled permutation that it never uses
+    (trainx_unl3, :195/:202); it is drawn here too so the generator state advances alike.
+    """
+    idx_lab = lab_rows[tiled_perm(rng, n_train, len(lab_rows))]
+    if unl_rows is None:
+        u1, u2, _ = (rng.permutation(n_train) for _ in range(3))
+    else:
+        u1, u2, _ = (unl_rows[tiled_perm(rng, n_train, len(unl_rows))] for _ in range(3))
+    return idx_lab.astype(np.int32), np.asarray(u1, np.int32), np.asarray(u2, np.int32)
+
+
+def train_epoch(model, X_train, y_train, idx_lab, idx_unl, idx_unl2, key, rng_step, B=O.BATCH_GAN):
+    """mr_gan.py:204-217 with the device noise stream.  Returns per-step stats [nb,4] and the new rng_step.
+
+    ``rng_step`` counts executed train steps (D and G steps alike); it is the
+    Philox ``step`` word.  Stacked-row convention of the device: D step rows =
+    [labeled | unlabeled | fake]; G step rows = [fake | real].
+    """
+    D = X_train.shape[1]
+    nb = X_train.shape[0] // B
+    stats = np.zeros((nb, 4))
+    for t in range(nb):
+        sl = slice(t * B, (t + 1) * B)
+        z = philox.normal(key, rng_step, philox.TID_Z, B, O.NOISE_SIZE)
+        ll, lu, te = model.disc_step(
+            X_train[idx_lab[sl]], y_train[idx_lab[sl]], X_train[idx_unl[sl]], z,
+            d_noise(key, rng_step, B, D, 0), d_noise(key, rng_step, B, D, B), d_noise(key, rng_step, B, D, 2 * B))
+        rng_step += 1
+        z = philox.normal(key, rng_step, philox.TID_Z, B, O.NOISE_SIZE)
+        lg = model.gen_step(X_train[idx_unl2[sl]], z,
+                            d_noise(key, rng_step, B, D, 0), d_noise(key, rng_step, B, D, B))
+        rng_step += 1
+        stats[t] = (ll, lu, te, lg)
+    return stats, rng_step
+
+
+def eval_batches(model, X_test, y_test, B=O.BATCH_GAN):
+    """mr_gan.py:219-223: mean of per-batch errors over the first floor(N/B) batches."""
+    nb = X_test.shape[0] // B
+    return float(np.mean([model.test_batch(X_test[t * B:(t + 1) * B], y_test[t * B:(t + 1) * B]) for t in range(nb)]))
