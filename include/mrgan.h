@@ -1,0 +1,146 @@
+/*
+ * mrgan.h -- C-ABI of the B200-native replacement for mr-gan's compiled training step.
+ *
+ * What it replaces (reference = Healthcare-Robotics/mr-gan, paths relative to it):
+ *   the three opaque callables that Keras builds with K.function at
+ *   mr_gan.py:169-171 (train_batch_disc / train_batch_gen / test_batch), the
+ *   inner epoch loop that drives them (mr_gan.py:183-230) and mr_nn's
+ *   model.fit / model.evaluate pair (mr_nn.py:114-118).  SURVEY.md section 8(b).
+ *
+ * Conventions
+ *   - plain C types only; every matrix is row-major float32, labels/indices int32;
+ *   - every entry point returns 0 on success, a negative mrgan_status otherwise;
+ *     mrgan_last_error() gives the message (reference behaviour: a Python
+ *     exception that aborts the sweep, e.g. the B==50 assumption at mr_gan.py:146);
+ *   - a handle owns ALL device memory (parameters, Adam slots, activations, fold
+ *     data, RNG counters) of a GROUP of folds that train side by side on one
+ *     GPU; host pointers are borrowed for the duration of the call only;
+ *   - a handle is bound to one CUDA device and one stream and is not thread-safe;
+ *   - there is no CPU fallback: without an sm_100 device mrgan_create fails.
+ *
+ * Parameter vectors use the reference's weight order (Keras `trainable_weights`):
+ *   discriminator (net 0): W1[D,1000] b1 W2[1000,500] b2 W3[500,250] b3
+ *                          W4[250,250] b4 W5[250,250] b5 W6[250,K] b6   (mr_gan.py:117-128)
+ *   generator     (net 1): W1[100,500] b1 gamma[500] beta[500] W2[500,500] b2
+ *                          W3[500,D] b3                                  (mr_gan.py:110-114)
+ */
+#ifndef MRGAN_H_
+#define MRGAN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mrgan_handle mrgan_handle;
+
+typedef enum {
+  MRGAN_OK = 0,
+  MRGAN_ERR_ARG = -1,      /* bad argument / shape mismatch */
+  MRGAN_ERR_CUDA = -2,     /* CUDA runtime error (message has the detail) */
+  MRGAN_ERR_NO_DEVICE = -3,/* no sm_100 device: there is no CPU fallback */
+  MRGAN_ERR_STATE = -4     /* call made in the wrong state (e.g. epoch before load_fold) */
+} mrgan_status;
+
+enum { MRGAN_NET_D = 0, MRGAN_NET_G = 1 };
+enum { MRGAN_MODEL_GAN = 0,   /* mr_gan.py: G + D, feature matching          */
+       MRGAN_MODEL_NN = 1 };  /* mr_nn.py: D as a plain classifier, MSE loss */
+enum { MRGAN_PREC_FP32 = 0,   /* FFMA kernels, fp32 operands (parity mode)                  */
+       MRGAN_PREC_TF32 = 1 }; /* tcgen05 kind::tf32 tensor-core kernels, fp32 accumulate    */
+
+/* Hyper-parameters; mrgan_default_config() fills the reference's values. */
+typedef struct {
+  int model;             /* MRGAN_MODEL_*                                     */
+  int n_folds;           /* folds trained side by side by this handle         */
+  int batch;             /* 50 (mr_gan.py:78) / 20 (mr_nn.py:117)             */
+  int n_classes;         /* 6  (mr_gan.py:80)                                 */
+  int noise_dim;         /* 100 (mr_gan.py:77)                                */
+  int precision;         /* MRGAN_PREC_*                                      */
+  int shared_t;          /* 1: D and G share Adam's step counter (mr_gan.py:165-167) */
+  int eval_each_epoch;   /* 1: batch-wise test error every epoch (mr_gan.py:219-223) */
+  int device;            /* CUDA device ordinal                               */
+  float lr, beta1, beta2, adam_eps;   /* 6e-4, .5, .999, 1e-8 (mr_gan.py:165) */
+  float bn_eps;          /* 2e-5 (mr_gan.py:112)                              */
+  float unlabeled_weight;/* 1 (mr_gan.py:79)                                  */
+  float sigma_in, sigma_hidden; /* .3, .5 (mr_gan.py:118-126)                 */
+} mrgan_config;
+
+typedef struct {
+  int D;                 /* input width of this fold (X_train.shape[1])       */
+  int n_train;           /* rows of X_train (must be equal for all folds of a handle) */
+  int n_test;            /* rows of X_test                                    */
+  uint64_t seed;         /* Philox key of this fold's noise streams           */
+} mrgan_fold_shape;
+
+/* statistics of one epoch and one fold (mr_gan.py:215-223) */
+typedef struct {
+  float loss_lab, loss_unl, train_err, loss_gen;  /* means over the epoch's batches */
+  float test_err;        /* mean batch-wise test error (-1 if eval_each_epoch == 0)  */
+} mrgan_epoch_stats;
+
+int  mrgan_default_config(int model, mrgan_config* cfg);
+
+/* Replaces model construction + K.function compilation, mr_gan.py:109-171. */
+int  mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_handle** out);
+int  mrgan_destroy(mrgan_handle* h);
+const char* mrgan_last_error(const mrgan_handle* h);   /* h may be NULL (creation errors) */
+int  mrgan_sync(mrgan_handle* h);
+
+/* Theano shared variables of the nets (mr_gan.py:131-133): read / write, reference order. */
+int64_t mrgan_num_params(const mrgan_handle* h, int fold, int net);
+int  mrgan_set_params(mrgan_handle* h, int fold, int net, const float* src, int64_t n);
+int  mrgan_get_params(mrgan_handle* h, int fold, int net, float* dst, int64_t n);
+/* Adam slots m, v (Keras optimizer weights) and the step counters, for tests / checkpoints. */
+int  mrgan_get_adam(mrgan_handle* h, int fold, int net, float* m, float* v, int64_t n);
+int  mrgan_get_counters(mrgan_handle* h, int fold, int* iterations, int* rng_step);
+
+/* Fold data made device-resident once (replaces the per-call numpy slices of
+ * mr_gan.py:207,213,222): scaled X_train/X_test, labels. */
+int  mrgan_load_fold(mrgan_handle* h, int fold,
+                     const float* x_train, const int32_t* y_train,
+                     const float* x_test, const int32_t* y_test);
+
+/* The three K.function callables, one fold at a time, HOST buffers:
+ *   train_batch_disc([1, x_lab, labels, x_unl, noise]) -> [loss_lab, loss_unl, train_err]  mr_gan.py:169
+ *   train_batch_gen ([1, x_unl, noise])               -> loss_gen                          mr_gan.py:170
+ *   test_batch      ([0, x, labels])                  -> err                               mr_gan.py:171
+ * rows = cfg.batch for the two train calls; n <= max(n_test, 3*batch) for test_batch. */
+int  mrgan_disc_step(mrgan_handle* h, int fold, const float* x_lab, const int32_t* labels,
+                     const float* x_unl, const float* z, float out[3]);
+int  mrgan_gen_step(mrgan_handle* h, int fold, const float* x_unl, const float* z, float out[1]);
+int  mrgan_test_batch(mrgan_handle* h, int fold, const float* x, const int32_t* y, int n, float* err);
+
+/* The epoch loop of mr_gan.py:183-223 for ALL folds of the handle as one CUDA
+ * graph launch: n_train/batch x (D step, G step), then the batch-wise test pass.
+ * idx_* are this epoch's row indices into X_train ([n_folds][n_train], the
+ * permutations of mr_gan.py:189-202).  stats may be NULL (asynchronous; collect
+ * with mrgan_epoch_result). */
+int  mrgan_train_epoch(mrgan_handle* h, const int32_t* idx_lab, const int32_t* idx_unl,
+                       const int32_t* idx_unl2, mrgan_epoch_stats* stats);
+int  mrgan_epoch_result(mrgan_handle* h, mrgan_epoch_stats* stats);
+/* testerror on the full resident test set in one call, mr_gan.py:230 */
+int  mrgan_eval(mrgan_handle* h, int fold, float* err);
+
+/* mr_nn.py:114-118 twins (handle created with MRGAN_MODEL_NN):
+ *   one model.fit batch: x[n,D], labels[n] -> {mse loss, accuracy}; n <= batch */
+int  mrnn_step(mrgan_handle* h, int fold, const float* x, const int32_t* labels, int n, float out[2]);
+/* one fit epoch over idx ([n_folds][n_idx] rows of X_train, n_idx % batch == 0), all folds */
+int  mrnn_train_epoch(mrgan_handle* h, const int32_t* idx, int n_idx, float* loss_acc /* [n_folds][2] or NULL */);
+/* model.evaluate(X_test, y_test) -> {mse loss, accuracy} */
+int  mrnn_evaluate(mrgan_handle* h, int fold, float out[2]);
+
+/* Utilities used by tests and bench */
+int  mrgan_fill_normal(mrgan_handle* h, int fold, int step, int tensor_id, int rows, int cols,
+                       int row0, float* dst /* host [rows, cols] */);
+int  mrgan_adam_flat(mrgan_handle* h, float* p, float* m, float* v, const float* g, int64_t n,
+                     int t /* 1-based */);              /* host buffers; fused flat Adam, SURVEY a8 */
+int64_t mrgan_kernel_launches(const mrgan_handle* h); /* kernels launched so far (graph nodes count per replay) */
+double  mrgan_last_device_ms(const mrgan_handle* h);  /* CUDA-event time of the last train_epoch */
+const char* mrgan_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRGAN_H_ */

@@ -1,0 +1,93 @@
+"""ctypes binding of libmrgan.so (include/mrgan.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc, and if
+that fails -- or if a compute entry point is called without a Blackwell GPU -- the
+call raises.  Nothing in this package ever routes through ``oracle/``.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+
+class Config(C.Structure):
+    _fields_ = [("model", C.c_int), ("n_folds", C.c_int), ("batch", C.c_int), ("n_classes", C.c_int),
+                ("noise_dim", C.c_int), ("precision", C.c_int), ("shared_t", C.c_int),
+                ("eval_each_epoch", C.c_int), ("device", C.c_int),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
+                ("bn_eps", C.c_float), ("unlabeled_weight", C.c_float),
+                ("sigma_in", C.c_float), ("sigma_hidden", C.c_float)]
+
+
+class FoldShape(C.Structure):
+    _fields_ = [("D", C.c_int), ("n_train", C.c_int), ("n_test", C.c_int), ("seed", C.c_uint64)]
+
+
+class EpochStats(C.Structure):
+    _fields_ = [("loss_lab", C.c_float), ("loss_unl", C.c_float), ("train_err", C.c_float),
+                ("loss_gen", C.c_float), ("test_err", C.c_float)]
+
+
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int32)
+_H = C.c_void_p
+
+# every symbol include/mrgan.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "mrgan_default_config": (C.c_int, [C.c_int, C.POINTER(Config)]),
+    "mrgan_create": (C.c_int, [C.POINTER(Config), C.POINTER(FoldShape), C.POINTER(_H)]),
+    "mrgan_destroy": (C.c_int, [_H]),
+    "mrgan_last_error": (C.c_char_p, [_H]),
+    "mrgan_sync": (C.c_int, [_H]),
+    "mrgan_num_params": (C.c_int64, [_H, C.c_int, C.c_int]),
+    "mrgan_set_params": (C.c_int, [_H, C.c_int, C.c_int, _fp, C.c_int64]),
+    "mrgan_get_params": (C.c_int, [_H, C.c_int, C.c_int, _fp, C.c_int64]),
+    "mrgan_get_adam": (C.c_int, [_H, C.c_int, C.c_int, _fp, _fp, C.c_int64]),
+    "mrgan_get_counters": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "mrgan_load_fold": (C.c_int, [_H, C.c_int, _fp, _ip, _fp, _ip]),
+    "mrgan_disc_step": (C.c_int, [_H, C.c_int, _fp, _ip, _fp, _fp, _fp]),
+    "mrgan_gen_step": (C.c_int, [_H, C.c_int, _fp, _fp, _fp]),
+    "mrgan_test_batch": (C.c_int, [_H, C.c_int, _fp, _ip, C.c_int, _fp]),
+    "mrgan_train_epoch": (C.c_int, [_H, _ip, _ip, _ip, C.POINTER(EpochStats)]),
+    "mrgan_epoch_result": (C.c_int, [_H, C.POINTER(EpochStats)]),
+    "mrgan_eval": (C.c_int, [_H, C.c_int, _fp]),
+    "mrnn_step": (C.c_int, [_H, C.c_int, _fp, _ip, C.c_int, _fp]),
+    "mrnn_train_epoch": (C.c_int, [_H, _ip, C.c_int, _fp]),
+    "mrnn_evaluate": (C.c_int, [_H, C.c_int, _fp]),
+    "mrgan_fill_normal": (C.c_int, [_H, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    "mrgan_adam_flat": (C.c_int, [_H, _fp, _fp, _fp, _fp, C.c_int64, C.c_int]),
+    "mrgan_kernel_launches": (C.c_int64, [_H]),
+    "mrgan_last_device_ms": (C.c_double, [_H]),
+    "mrgan_version": (C.c_char_p, []),
+}
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building if needed) libmrgan.so and declare every prototype.  Raises on failure."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if not os.path.exists(path):
+        path = _build.build()
+    lib = C.CDLL(path)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def fptr(a):
+    return a.ctypes.data_as(_fp)
+
+
+def iptr(a):
+    return a.ctypes.data_as(_ip)

@@ -1,0 +1,112 @@
+// common.cuh -- shared device structs, Philox4x32-10 noise stream, small helpers.
+//
+// Layout conventions (see DESIGN.md "Data layout in HBM"):
+//  * every matrix is row-major fp32 with a pitch rounded up to 4 floats; pad
+//    columns are zero at allocation and are NEVER written by any kernel;
+//  * a Dense layer's kernel W[in,out] and bias b[out] (mr_gan.py:111-128) are
+//    stored as ONE augmented matrix Waug[(in+1), pitch(out)] whose last row is the
+//    bias -- the reference's own weight order (W then b) already is that matrix;
+//    every activation buffer carries a constant 1.0 in column `in`, so bias add
+//    (forward) and bias gradient (backward) fall out of the GEMMs themselves.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define MRGAN_TID_Z 5   // noise stream ids 0..4 = GaussianNoise layers of D, 5 = z
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SOFTPLUS = 2 };
+enum { EPI_FWD = 0, EPI_DX = 1, EPI_STORE = 2 };
+
+// Per-fold device state.  One per fold, resident in HBM for the handle's life.
+struct FoldState {
+  uint32_t key0, key1;   // Philox key (from mrgan_fold_shape.seed)
+  int iterations;        // Keras `adam.iterations`, shared by D and G (mr_gan.py:165-167)
+  int it_net[2];         // per-net counters used when shared_t == 0
+  int rng_step;          // number of executed train steps = Philox `step` word
+  float lr_t;            // lr * sqrt(1-b2^t) / (1-b1^t) of the step in flight
+  int D, n_train, n_test;
+  int ldx;               // pitch of x_train
+  const float* x_train;  // [n_train, ldx] scaled features (device-resident fold data)
+  const int* y_train;    // [n_train]
+  const int* y_test;     // [n_test]
+  const int* idx[3];     // epoch row indices: labeled, unlabeled (D step), unlabeled (G step)
+  const float* stage_x;  // [3B, ldx] host-provided batches of the step API
+  const int* stage_y;    // [B]
+  const float* stage_z;  // [B, noise_dim]
+  float* a0; int lda0;   // stacked, noisy D input [3B, pitch(D+1)]
+  float* z;  int ldz;    // generator input [B, pitch(noise_dim+1)]
+  int* labels_cur;       // [B] labels of the labeled rows of the step in flight
+};
+
+// One GEMM of the step, for one fold: C[M,N] = op(A)[M,K] * op(B)[K,N] (+ epilogue).
+struct GemmDesc {
+  const float* A; const float* B; float* C; float* C2; const float* aux;
+  int lda, ldb, ldc, ldc2, ldaux;
+  int M, N, K;
+  int act, epi;
+  float sigma; int tid; int row0;   // noise added to C2: sigma * n(row0 + m, n)
+  int fold;
+};
+
+struct AdamHyper { float lr, b1, b2, eps; int shared_t; };
+
+__host__ __device__ inline int pitch4(int w) { return (w + 3) & ~3; }
+
+// ---------------------------------------------------------------- Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// The 4 normals of rows 4*rowgroup .. 4*rowgroup+3 at column `col`
+// (definition: oracle/philox.py module docstring).
+__device__ __forceinline__ void normal4(uint32_t k0, uint32_t k1, uint32_t rowgroup, uint32_t col,
+                                        uint32_t step, uint32_t tid, float out[4]) {
+  const uint4 x = philox4x32_10(make_uint4(rowgroup, col, step, tid), k0, k1);
+  const float s = 1.1920928955078125e-07f;   // 2^-23
+  const float u1a = ((float)(x.x >> 9) + 0.5f) * s, u2a = ((float)(x.y >> 9) + 0.5f) * s;
+  const float u1b = ((float)(x.z >> 9) + 0.5f) * s, u2b = ((float)(x.w >> 9) + 0.5f) * s;
+  const float ra = sqrtf(-2.0f * logf(u1a)), rb = sqrtf(-2.0f * logf(u1b));
+  float sa, ca, sb, cb;
+  sincospif(2.0f * u2a - 1.0f, &sa, &ca);
+  sincospif(2.0f * u2b - 1.0f, &sb, &cb);
+  out[0] = ra * ca; out[1] = ra * sa; out[2] = rb * cb; out[3] = rb * sb;
+}
+
+__device__ __forceinline__ float normal1(uint32_t k0, uint32_t k1, uint32_t row, uint32_t col,
+                                         uint32_t step, uint32_t tid) {
+  float n[4];
+  normal4(k0, k1, row >> 2, col, step, tid, n);
+  return n[row & 3];
+}
+
+__device__ __forceinline__ float softplusf(float x) {
+  // log(1+e^x), stable on both tails (K.softplus)
+  return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x)));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum, result valid in thread 0; `sh` needs 32 floats
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = (l < (int)((blockDim.x + 31) >> 5)) ? sh[l] : 0.0f;
+    v = warp_sum(v);
+  }
+  return v;
+}

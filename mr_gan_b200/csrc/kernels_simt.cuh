@@ -1,0 +1,458 @@
+// kernels_simt.cuh -- fp32 (FFMA) kernels of the training step: grouped GEMM with fused
+// epilogues, batch assembly + noise, BatchNorm, loss heads, feature matching, flat Adam.
+// All kernels are grouped over folds through blockIdx.z (or .y) and read their
+// per-fold operands from descriptor tables that live in HBM for the handle's life.
+#pragma once
+#include "common.cuh"
+
+// ------------------------------------------------------------------ grouped GEMM (fp32)
+// C[M,N] = op(A)[M,K] * op(B)[K,N]; 64x64x16 tiles, 256 threads, 4x4 micro-tiles,
+// register-prefetch double buffering.
+//   AT = false: A stored [M, lda] (K contiguous)   AT = true: A stored [K, lda] (M contiguous)
+//   BT = false: B stored [K, ldb] (N contiguous)   BT = true: B stored [N, ldb] (K contiguous)
+// forward  (mr_gan.py:111-128 Dense):   NN  act(A @ Waug)            (+ GaussianNoise for the next layer)
+// backward dX:                          NT  (dZ @ Waug[:in]^T) * act'(h)
+// backward dW,db:                       TN  A_aug^T @ dZ            (last row = bias gradient)
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+template <bool AT, bool BT>
+__global__ void __launch_bounds__(256)
+k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ folds, int rows_override) {
+  const GemmDesc d = descs[blockIdx.z];
+  int M = d.M, K = d.K;
+  const int N = d.N;
+  if (rows_override > 0) { if (AT) K = rows_override; else M = rows_override; }
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  if (m0 >= M || n0 >= N) return;
+
+  __shared__ __align__(16) float As[2][16][68];
+  __shared__ __align__(16) float Bs[2][16][68];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  auto load_a = [&](int k0) -> float4 {
+    if (AT) {
+      const int k = k0 + (tid >> 4), m = m0 + (tid & 15) * 4;
+      return (k < K && m < d.lda) ? ldg4(d.A + (size_t)k * d.lda + m) : zero4;
+    } else {
+      const int m = m0 + (tid >> 2), k = k0 + (tid & 3) * 4;
+      return (m < M && k < d.lda) ? ldg4(d.A + (size_t)m * d.lda + k) : zero4;
+    }
+  };
+  auto load_b = [&](int k0) -> float4 {
+    if (!BT) {
+      const int k = k0 + (tid >> 4), n = n0 + (tid & 15) * 4;
+      return (k < K && n < d.ldb) ? ldg4(d.B + (size_t)k * d.ldb + n) : zero4;
+    } else {
+      const int n = n0 + (tid >> 2), k = k0 + (tid & 3) * 4;
+      return (n < N && k < d.ldb) ? ldg4(d.B + (size_t)n * d.ldb + k) : zero4;
+    }
+  };
+  auto store_a = [&](int buf, float4 v) {
+    if (AT) {
+      *reinterpret_cast<float4*>(&As[buf][tid >> 4][(tid & 15) * 4]) = v;
+    } else {
+      const int kk = (tid & 3) * 4, mm = tid >> 2;
+      As[buf][kk + 0][mm] = v.x; As[buf][kk + 1][mm] = v.y; As[buf][kk + 2][mm] = v.z; As[buf][kk + 3][mm] = v.w;
+    }
+  };
+  auto store_b = [&](int buf, float4 v) {
+    if (!BT) {
+      *reinterpret_cast<float4*>(&Bs[buf][tid >> 4][(tid & 15) * 4]) = v;
+    } else {
+      const int kk = (tid & 3) * 4, nn = tid >> 2;
+      Bs[buf][kk + 0][nn] = v.x; Bs[buf][kk + 1][nn] = v.y; Bs[buf][kk + 2][nn] = v.z; Bs[buf][kk + 3][nn] = v.w;
+    }
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nk = (K + 15) >> 4;
+  float4 ra = load_a(0), rb = load_b(0);
+  store_a(0, ra); store_b(0, rb);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    const bool more = (kt + 1 < nk);
+    if (more) { ra = load_a((kt + 1) << 4); rb = load_b((kt + 1) << 4); }
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) { store_a(buf ^ 1, ra); store_b(buf ^ 1, rb); }
+    __syncthreads();
+  }
+
+  // ---- epilogue ----
+  const int mb = m0 + ty * 4, nb = n0 + tx * 4;
+  if (d.epi == EPI_STORE) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = mb + i;
+      if (m >= M) break;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (nb + j < N) d.C[(size_t)m * d.ldc + nb + j] = acc[i][j];
+    }
+    return;
+  }
+  if (d.epi == EPI_DX) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = mb + i;
+      if (m >= M) break;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = nb + j;
+        if (n >= N) continue;
+        float v = acc[i][j];
+        if (d.act == ACT_RELU) v = (d.aux[(size_t)m * d.ldaux + n] > 0.f) ? v : 0.f;
+        else if (d.act == ACT_SOFTPLUS) v *= 1.0f - expf(-d.aux[(size_t)m * d.ldaux + n]);
+        d.C[(size_t)m * d.ldc + n] = v;
+      }
+    }
+    return;
+  }
+  // EPI_FWD: activation, optional clean copy (C), optional noisy copy for the next layer (C2)
+  const bool noisy = (d.C2 != nullptr) && (d.sigma != 0.f);
+  uint32_t k0 = 0, k1 = 0, step = 0;
+  if (noisy) { const FoldState& fs = folds[d.fold]; k0 = fs.key0; k1 = fs.key1; step = (uint32_t)fs.rng_step; }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = nb + j;
+    if (n >= N) continue;
+    float nz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (noisy) {
+      if (((d.row0 + mb) & 3) == 0) {
+        normal4(k0, k1, (uint32_t)(d.row0 + mb) >> 2, (uint32_t)n, step, (uint32_t)d.tid, nz);
+      } else {
+        for (int i = 0; i < 4; ++i) nz[i] = normal1(k0, k1, (uint32_t)(d.row0 + mb + i), (uint32_t)n, step, (uint32_t)d.tid);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = mb + i;
+      if (m >= M) continue;
+      float v = acc[i][j];
+      if (d.act == ACT_RELU) v = fmaxf(v, 0.f);
+      else if (d.act == ACT_SOFTPLUS) v = softplusf(v);
+      if (d.C) d.C[(size_t)m * d.ldc + n] = v;
+      if (d.C2) d.C2[(size_t)m * d.ldc2 + n] = v + d.sigma * nz[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ batch assembly
+// Builds the stacked, noisy discriminator input and the generator input of one step
+// (replaces the numpy slicing + np.random.normal of mr_gan.py:206-207,212-213 and the
+// first GaussianNoise layer mr_gan.py:118) and computes Adam's lr_t for the step.
+//   mode 0 (D step): rows [0,B) labeled, [B,2B) unlabeled; rows [2B,3B) come from G
+//   mode 1 (G step): rows [B,2B) unlabeled; rows [0,B) come from G
+//   mode 2 (mr_nn step): rows [0,n) labeled
+// from_stage: rows come from the step-API staging buffers instead of the resident fold.
+__global__ void __launch_bounds__(128)
+k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, int t, int B, int nrows,
+       int noise_dim, float sigma_in, AdamHyper hp) {
+  FoldState& fs = folds[fold_base + blockIdx.z];
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int rg = blockIdx.y;
+  const uint32_t step = (uint32_t)fs.rng_step;
+  const int D = fs.D;
+
+  if (blockIdx.x == 0 && rg == 0) {
+    if (threadIdx.x == 0) {
+      const int net = (mode == 1) ? 1 : 0;
+      const int tt = (hp.shared_t ? fs.iterations : fs.it_net[net]) + 1;
+      const double b1t = pow((double)hp.b1, (double)tt), b2t = pow((double)hp.b2, (double)tt);
+      fs.lr_t = (float)((double)hp.lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+    }
+    if (mode != 1) {
+      for (int r = threadIdx.x; r < (mode == 2 ? nrows : B); r += 128)
+        fs.labels_cur[r] = from_stage ? fs.stage_y[r] : fs.y_train[fs.idx[0][(size_t)t * B + r]];
+    }
+  }
+
+  if (c < D) {
+    float nz[4];
+    normal4(fs.key0, fs.key1, (uint32_t)rg, (uint32_t)c, step, 0u, nz);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rg * 4 + i;
+      if (r >= nrows) break;
+      int stream;
+      if (mode == 0) { if (r >= 2 * B) break; stream = (r < B) ? 0 : 1; }
+      else if (mode == 1) { if (r < B) continue; if (r >= 2 * B) break; stream = 2; }
+      else stream = 0;
+      const int lr = (mode == 2) ? r : (r < B ? r : r - B);
+      const float* src = from_stage ? fs.stage_x + (size_t)r * fs.ldx
+                                    : fs.x_train + (size_t)fs.idx[stream][(size_t)t * B + lr] * fs.ldx;
+      fs.a0[(size_t)r * fs.lda0 + c] = src[c] + sigma_in * nz[i];
+    }
+  }
+  if (mode != 2 && c < noise_dim) {       // generator input z (mr_gan.py:206,212)
+    float nz[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!from_stage) normal4(fs.key0, fs.key1, (uint32_t)rg, (uint32_t)c, step, MRGAN_TID_Z, nz);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rg * 4 + i;
+      if (r >= B) break;
+      fs.z[(size_t)r * fs.ldz + c] = from_stage ? fs.stage_z[(size_t)r * noise_dim + c] : nz[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ BatchNorm (batch statistics)
+struct BnDesc {
+  const float* h1; float* xhat; float* u; float* istd;      // fwd
+  const float* gamma; const float* beta;
+  const float* du; float* dz1; float* g_gamma; float* g_beta;  // bwd
+  int ld, ldu, B, W;
+};
+
+// mr_gan.py:112 BatchNormalization(epsilon=2e-5) in training phase: biased batch variance.
+__global__ void __launch_bounds__(128) k_bn_fwd(const BnDesc* __restrict__ descs, float eps) {
+  const BnDesc d = descs[blockIdx.z];
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= d.W) return;
+  float s = 0.f;
+  for (int r = 0; r < d.B; ++r) s += d.h1[(size_t)r * d.ld + j];
+  const float mu = s / d.B;
+  float q = 0.f;
+  for (int r = 0; r < d.B; ++r) { const float x = d.h1[(size_t)r * d.ld + j] - mu; q = fmaf(x, x, q); }
+  const float istd = rsqrtf(q / d.B + eps);
+  d.istd[j] = istd;
+  const float g = d.gamma[j], b = d.beta[j];
+  for (int r = 0; r < d.B; ++r) {
+    const float xh = (d.h1[(size_t)r * d.ld + j] - mu) * istd;
+    d.xhat[(size_t)r * d.ld + j] = xh;
+    d.u[(size_t)r * d.ldu + j] = fmaf(g, xh, b);
+  }
+}
+
+// BN backward + softplus' of the layer in front of it (G layer 1): du -> dgamma, dbeta, dz1.
+__global__ void __launch_bounds__(128) k_bn_bwd(const BnDesc* __restrict__ descs) {
+  const BnDesc d = descs[blockIdx.z];
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= d.W) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int r = 0; r < d.B; ++r) {
+    const float du = d.du[(size_t)r * d.ld + j];
+    s1 += du;
+    s2 = fmaf(du, d.xhat[(size_t)r * d.ld + j], s2);
+  }
+  d.g_gamma[j] = s2;
+  d.g_beta[j] = s1;
+  const float g = d.gamma[j], istd = d.istd[j], invB = 1.0f / d.B;
+  for (int r = 0; r < d.B; ++r) {
+    const float xh = d.xhat[(size_t)r * d.ld + j];
+    const float dxh = d.du[(size_t)r * d.ld + j] * g;
+    const float dh1 = istd * (dxh - invB * g * s1 - xh * invB * g * s2);
+    d.dz1[(size_t)r * d.ld + j] = dh1 * (1.0f - expf(-d.h1[(size_t)r * d.ld + j]));
+  }
+}
+
+// ------------------------------------------------------------------ loss heads
+struct LossDesc {
+  const float* logits; float* dlogits; int ld;   // [rows, ld]
+  const int* labels;
+  const float* mid; float* dmid; int ldmid, lddmid, Wmid;   // feature matching
+};
+
+// Salimans-style supervised + unsupervised losses on the stacked logits
+// (mr_gan.py:146-149,161) and their gradients.
+__global__ void __launch_bounds__(256)
+k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total,
+            int t, int B, int K, float w_unl) {
+  __shared__ float sh[32];
+  const LossDesc d = descs[blockIdx.z];
+  float s_lab = 0.f, s_unl = 0.f, s_err = 0.f;
+  for (int r = threadIdx.x; r < 3 * B; r += blockDim.x) {
+    const float* l = d.logits + (size_t)r * d.ld;
+    float mx = l[0]; int am = 0;
+    for (int k = 1; k < K; ++k) if (l[k] > mx) { mx = l[k]; am = k; }
+    float se = 0.f;
+    for (int k = 0; k < K; ++k) se += expf(l[k] - mx);
+    const float lse = mx + logf(se), inv = 1.0f / se;
+    float* dl = d.dlogits + (size_t)r * d.ld;
+    if (r < B) {
+      const int y = d.labels[r];
+      s_lab += lse - l[y];
+      s_err += (am != y) ? 1.f : 0.f;
+      for (int k = 0; k < K; ++k) dl[k] = (expf(l[k] - mx) * inv - (k == y ? 1.f : 0.f)) / B;
+    } else {
+      const float sp = softplusf(lse), sg = 1.0f / (1.0f + expf(-lse));
+      float coef;
+      if (r < 2 * B) { s_unl += 0.5f * (sp - lse); coef = 0.5f * (sg - 1.0f); }
+      else           { s_unl += 0.5f * sp;         coef = 0.5f * sg; }
+      coef *= w_unl / B;
+      for (int k = 0; k < K; ++k) dl[k] = coef * expf(l[k] - mx) * inv;
+    }
+  }
+  s_lab = block_sum(s_lab, sh);
+  s_unl = block_sum(s_unl, sh);
+  s_err = block_sum(s_err, sh);
+  if (threadIdx.x == 0) {
+    float* st = step_stats + ((size_t)t * nf_total + fold_base + blockIdx.z) * 4;
+    st[0] = s_lab / B; st[1] = s_unl / B; st[2] = s_err / B;
+  }
+}
+
+// Feature matching (mr_gan.py:152-154): rows [0,B) = fake, [B,2B) = real mid activations.
+// Writes dZ5 (already multiplied by ReLU') for the fake rows.
+__global__ void __launch_bounds__(256)
+k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total, int t, int B) {
+  __shared__ float sh[32];
+  const LossDesc d = descs[blockIdx.z];
+  float s = 0.f;
+  for (int j = threadIdx.x; j < d.Wmid; j += blockDim.x) {
+    float mg = 0.f, mr = 0.f;
+    for (int r = 0; r < B; ++r) { mg += d.mid[(size_t)r * d.ldmid + j]; mr += d.mid[(size_t)(r + B) * d.ldmid + j]; }
+    const float diff = (mg - mr) / B;
+    s = fmaf(diff, diff, s);
+    const float g = 2.0f * diff / ((float)d.Wmid * B);
+    for (int r = 0; r < B; ++r)
+      d.dmid[(size_t)r * d.lddmid + j] = (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : 0.f;
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) step_stats[((size_t)t * nf_total + fold_base + blockIdx.z) * 4 + 3] = s / d.Wmid;
+}
+
+// mr_nn.py:114 loss='mse' vs one-hot, metrics=['accuracy'].
+__global__ void __launch_bounds__(256)
+k_loss_mse(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total,
+           int t, int n, int K) {
+  __shared__ float sh[32];
+  const LossDesc d = descs[blockIdx.z];
+  float s_loss = 0.f, s_acc = 0.f;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    const float* l = d.logits + (size_t)r * d.ld;
+    float* dl = d.dlogits + (size_t)r * d.ld;
+    const int y = d.labels[r];
+    float mx = l[0]; int am = 0;
+    for (int k = 1; k < K; ++k) if (l[k] > mx) { mx = l[k]; am = k; }
+    float q = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float diff = l[k] - (k == y ? 1.f : 0.f);
+      q = fmaf(diff, diff, q);
+      dl[k] = 2.0f * diff / ((float)n * K);
+    }
+    s_loss += q / K;
+    s_acc += (am == y) ? 1.f : 0.f;
+  }
+  s_loss = block_sum(s_loss, sh);
+  s_acc = block_sum(s_acc, sh);
+  if (threadIdx.x == 0) {
+    float* st = step_stats + ((size_t)t * nf_total + fold_base + blockIdx.z) * 4;
+    st[0] = s_loss / n; st[1] = s_acc / n;
+  }
+}
+
+// ------------------------------------------------------------------ evaluation
+struct EvalDesc { const float* logits; int ld; const int* y; int n; int n_batched; float* out; };
+
+// test_batch (mr_gan.py:162,171): mean(argmax != y); out[0] over the first n_batched rows
+// (= mean of the per-batch errors of mr_gan.py:221-223), out[1] over all rows (mr_gan.py:230),
+// out[2] = mse vs one-hot over all rows (mr_nn.py:118 evaluate()[0]).
+__global__ void __launch_bounds__(256)
+k_argmax_err(const EvalDesc* __restrict__ descs, int n_override, int K) {
+  __shared__ float sh[32];
+  const EvalDesc d = descs[blockIdx.z];
+  const int n = n_override > 0 ? n_override : d.n;
+  const int nb = n_override > 0 ? n_override : d.n_batched;
+  float e_b = 0.f, e_all = 0.f, q = 0.f;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    const float* l = d.logits + (size_t)r * d.ld;
+    const int y = d.y[r];
+    float mx = l[0]; int am = 0;
+    for (int k = 1; k < K; ++k) if (l[k] > mx) { mx = l[k]; am = k; }
+    for (int k = 0; k < K; ++k) { const float diff = l[k] - (k == y ? 1.f : 0.f); q = fmaf(diff, diff, q); }
+    const float e = (am != y) ? 1.f : 0.f;
+    e_all += e;
+    if (r < nb) e_b += e;
+  }
+  e_b = block_sum(e_b, sh);
+  e_all = block_sum(e_all, sh);
+  q = block_sum(q, sh);
+  if (threadIdx.x == 0) { d.out[0] = nb > 0 ? e_b / nb : 0.f; d.out[1] = e_all / n; d.out[2] = q / ((float)n * K); }
+}
+
+// Means over the epoch's batches (mr_gan.py:215-217) -> epoch_stats[f][0..3]; [4] = batch-wise test error.
+__global__ void k_epoch_reduce(const float* __restrict__ step_stats, const EvalDesc* __restrict__ evals,
+                               float* __restrict__ epoch_stats, int nf, int nb, int with_eval) {
+  const int f = blockIdx.x, j = threadIdx.x;
+  if (j < 4) {
+    float s = 0.f;
+    for (int t = 0; t < nb; ++t) s += step_stats[((size_t)t * nf + f) * 4 + j];
+    epoch_stats[f * 8 + j] = s / nb;
+  } else if (j == 4) {
+    epoch_stats[f * 8 + 4] = with_eval ? evals[f].out[0] : -1.f;
+  }
+}
+
+// ------------------------------------------------------------------ flat fused Adam
+// Keras-2.0.9 Adam.get_updates over one flat parameter range per fold:
+// m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr_t m / (sqrt(v) + eps).
+// The last block advances the fold's step counters (K.update_add(iterations, 1)).
+struct AdamRange { long long off; long long n; };   // n multiple of 4, off 16B aligned
+
+__global__ void __launch_bounds__(256)
+k_adam(float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ Vo, const float* __restrict__ G,
+       const AdamRange* __restrict__ ranges, FoldState* __restrict__ folds, int fold_base, int net, AdamHyper hp) {
+  const int f = fold_base + blockIdx.y;
+  const AdamRange rg = ranges[f];
+  FoldState& fs = folds[f];
+  const float lr_t = fs.lr_t;
+  const float b1 = hp.b1, b2 = hp.b2, eps = hp.eps, c1 = 1.0f - hp.b1, c2 = 1.0f - hp.b2;
+  const long long n4 = rg.n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(P + rg.off);
+  float4* m4 = reinterpret_cast<float4*>(Mo + rg.off);
+  float4* v4 = reinterpret_cast<float4*>(Vo + rg.off);
+  const float4* g4 = reinterpret_cast<const float4*>(G + rg.off);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 p = p4[i], m = m4[i], v = v4[i];
+    const float4 g = __ldg(g4 + i);
+#define ADAM1(c) m.c = fmaf(b1, m.c, c1 * g.c); v.c = fmaf(b2, v.c, c2 * g.c * g.c); p.c -= lr_t * m.c / (sqrtf(v.c) + eps);
+    ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+    p4[i] = p; m4[i] = m; v4[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (hp.shared_t) fs.iterations += 1; else fs.it_net[net] += 1;
+    fs.rng_step += 1;
+  }
+}
+
+// standalone flat Adam on caller-provided buffers (mrgan_adam_flat; unit tests + roofline probe)
+__global__ void __launch_bounds__(256)
+k_adam_plain(float4* __restrict__ p4, float4* __restrict__ m4, float4* __restrict__ v4, const float4* __restrict__ g4,
+             long long n4, float lr_t, float b1, float b2, float eps) {
+  const float c1 = 1.0f - b1, c2 = 1.0f - b2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 p = p4[i], m = m4[i], v = v4[i];
+    const float4 g = __ldg(g4 + i);
+#define ADAM1(c) m.c = fmaf(b1, m.c, c1 * g.c); v.c = fmaf(b2, v.c, c2 * g.c * g.c); p.c -= lr_t * m.c / (sqrtf(v.c) + eps);
+    ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
+#undef ADAM1
+    p4[i] = p; m4[i] = m; v4[i] = v;
+  }
+}
+
+// debug / test utility: materialise a block of the noise stream
+__global__ void k_fill_normal(float* __restrict__ dst, const FoldState* __restrict__ folds, int fold, int step, int tid,
+                              int rows, int cols, int row0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i % cols;
+  const FoldState& fs = folds[fold];
+  dst[i] = normal1(fs.key0, fs.key1, (uint32_t)(row0 + r), (uint32_t)c, (uint32_t)step, (uint32_t)tid);
+}

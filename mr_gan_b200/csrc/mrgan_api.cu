@@ -1,0 +1,1002 @@
+// mrgan_api.cu -- handle, memory layout, launch sequences, CUDA-graph epoch and the C-ABI
+// declared in include/mrgan.h.  Reference interface replaced: the K.function callables of
+// mr_gan.py:169-171, the epoch loop mr_gan.py:183-230 and mr_nn.py:114-118.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mrgan.h"
+#include "kernels_simt.cuh"
+#ifdef MRGAN_WITH_TC
+#include "kernels_tc.cuh"
+#endif
+
+namespace {
+
+thread_local std::string g_last_error;
+
+// ------------------------------------------------------------------ op table
+enum Op {
+  OP_G1, OP_G2, OP_G3D, OP_G3G,
+  OP_D1, OP_D2, OP_D3, OP_D4, OP_D5, OP_D6,
+  OP_DW1, OP_DW2, OP_DW3, OP_DW4, OP_DW5, OP_DW6,
+  OP_DX2, OP_DX3, OP_DX4, OP_DX5, OP_DX6,     // OP_DXl: dZ[l] -> dZ[l-1]
+  OP_DX1G,                                     // dZ[1] -> dFake (G step only)
+  OP_GW1, OP_GW2, OP_GW3, OP_GX2, OP_GX3,
+  OP_E1, OP_E1S, OP_E2, OP_E3, OP_E4, OP_E5, OP_E6,
+  NUM_OPS
+};
+
+struct OpInfo { bool at = false, bt = false, used = false; int maxM = 0, maxN = 0; };
+
+struct Arena {
+  char* base = nullptr; size_t off = 0;
+  template <typename T> T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+struct TensorLayout { int rows, cols, pitch; long long off; };   // inside a net's flat block
+
+struct NetLayout {
+  std::vector<TensorLayout> t;   // D: 6 augmented matrices; G: W1aug, gamma, beta, W2aug, W3aug
+  long long n = 0;               // padded length (multiple of 32)
+  long long n_ref = 0;           // length in the reference's packed order
+  long long off = 0;             // offset of this net in the handle's flat buffers
+};
+
+struct FoldBuffers {
+  float *a[6], *hb[6], *dz[6], *lg, *dlg, *dfake, *zb, *h1g, *xhat, *istd, *u, *h2g, *dz2g, *du, *dz1g;
+  float *stage_x, *stage_z, *ex_stage, *xte, *eh[6], *elg, *xtr, *eval_out, *eval_out_s;
+  int *stage_y, *labels_cur, *ey_stage, *ytr, *yte, *idx;
+  int lda[6], ldz[6];   // pitches of a/h (with ones column) and dz
+  bool loaded = false;
+};
+
+}  // namespace
+
+struct mrgan_handle {
+  mrgan_config cfg;
+  int nf = 0, R = 0, NE = 0, n_train = 0;
+  std::vector<mrgan_fold_shape> shapes;
+  std::vector<NetLayout> net[2];
+  std::vector<FoldBuffers> fb;
+  cudaStream_t stream = nullptr;
+  char* arena = nullptr; size_t arena_bytes = 0;
+  float *P = nullptr, *Mo = nullptr, *Vo = nullptr, *Gr = nullptr; long long n_flat = 0;
+  FoldState* d_folds = nullptr; std::vector<FoldState> h_folds;
+  GemmDesc* d_descs = nullptr; std::vector<GemmDesc> h_descs;
+  BnDesc* d_bn = nullptr; LossDesc* d_loss = nullptr; EvalDesc *d_eval = nullptr, *d_eval_s = nullptr;
+  AdamRange* d_ranges[2] = {nullptr, nullptr};
+  OpInfo ops[NUM_OPS];
+  float *d_step_stats = nullptr, *d_epoch_stats = nullptr, *h_epoch_stats = nullptr;
+  int* h_idx_pinned[2] = {nullptr, nullptr}; cudaEvent_t idx_free[2] = {nullptr, nullptr}; int idx_slot = 0;
+  float* h_scratch = nullptr;   // pinned scalars for the step API
+  std::map<int, cudaGraphExec_t> graphs;   // key: nb (GAN) or n_idx (NN)
+  std::map<int, long long> graph_nodes;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool epoch_pending = false; double last_ms = 0.0;
+  long long launches = 0;
+  std::string err;
+  AdamHyper hp;
+};
+
+namespace {
+
+int fail(mrgan_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_last_error = msg;
+  return code;
+}
+
+#define CK(expr)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail(h, MRGAN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+  } while (0)
+
+const int kDW[5] = {1000, 500, 250, 250, 250};   // mr_gan.py:119-127
+const int kGH = 500;                               // mr_gan.py:111,113
+
+long long align32(long long x) { return (x + 31) & ~31LL; }
+
+NetLayout layout_disc(int D, int K) {
+  NetLayout L;
+  int dims[7] = {D, kDW[0], kDW[1], kDW[2], kDW[3], kDW[4], K};
+  for (int l = 0; l < 6; ++l) {
+    TensorLayout t{dims[l] + 1, dims[l + 1], pitch4(dims[l + 1]), L.n};
+    L.t.push_back(t);
+    L.n = align32(L.n + (long long)t.rows * t.pitch);
+    L.n_ref += (long long)(dims[l] + 1) * dims[l + 1];
+  }
+  return L;
+}
+
+NetLayout layout_gen(int D, int nd) {
+  NetLayout L;
+  auto add = [&](int rows, int cols) {
+    TensorLayout t{rows, cols, pitch4(cols), L.n};
+    L.t.push_back(t);
+    L.n = align32(L.n + (long long)rows * t.pitch);
+    L.n_ref += (long long)rows * cols;
+  };
+  add(nd + 1, kGH);   // W1aug
+  add(1, kGH);        // gamma
+  add(1, kGH);        // beta
+  add(kGH + 1, kGH);  // W2aug
+  add(kGH + 1, D);    // W3aug
+  return L;
+}
+
+__global__ void k_set_col(float* p, int ld, int rows, int col, float v) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) p[(size_t)r * ld + col] = v;
+}
+
+// ---- buffer layout (run twice: sizing pass with base == nullptr, then for real) ----
+void layout_buffers(mrgan_handle* h, Arena& ar) {
+  const mrgan_config& c = h->cfg;
+  const int B = c.batch, R = h->R, NE = h->NE, K = c.n_classes, nd = c.noise_dim, nf = h->nf;
+  const bool gan = c.model == MRGAN_MODEL_GAN;
+  h->P = ar.take<float>(h->n_flat);
+  h->Mo = ar.take<float>(h->n_flat);
+  h->Vo = ar.take<float>(h->n_flat);
+  h->Gr = ar.take<float>(h->n_flat);
+  h->d_folds = ar.take<FoldState>(nf);
+  h->d_descs = ar.take<GemmDesc>((size_t)NUM_OPS * nf);
+  h->d_bn = ar.take<BnDesc>(nf);
+  h->d_loss = ar.take<LossDesc>(nf);
+  h->d_eval = ar.take<EvalDesc>(nf);
+  h->d_eval_s = ar.take<EvalDesc>(nf);
+  h->d_ranges[0] = ar.take<AdamRange>(nf);
+  h->d_ranges[1] = ar.take<AdamRange>(nf);
+  h->d_step_stats = ar.take<float>((size_t)(h->n_train / B + 1) * nf * 4);
+  h->d_epoch_stats = ar.take<float>((size_t)nf * 8);
+  for (int f = 0; f < nf; ++f) {
+    FoldBuffers& b = h->fb[f];
+    const int D = h->shapes[f].D, ntr = h->shapes[f].n_train, nte = h->shapes[f].n_test;
+    const int ldx = pitch4(D);
+    int win[6] = {D, kDW[0], kDW[1], kDW[2], kDW[3], kDW[4]};
+    for (int l = 0; l < 6; ++l) { b.lda[l] = pitch4(win[l] + 1); b.ldz[l] = pitch4(win[l]); }
+    b.a[0] = ar.take<float>((size_t)R * b.lda[0]);
+    b.hb[0] = nullptr; b.dz[0] = nullptr;
+    for (int l = 1; l <= 5; ++l) {
+      b.hb[l] = ar.take<float>((size_t)R * b.lda[l]);
+      b.a[l] = (l < 5) ? ar.take<float>((size_t)R * b.lda[l]) : b.hb[l];
+      b.dz[l] = ar.take<float>((size_t)R * b.ldz[l]);
+    }
+    b.lg = ar.take<float>((size_t)R * pitch4(K));
+    b.dlg = ar.take<float>((size_t)R * pitch4(K));
+    b.labels_cur = ar.take<int>(R);
+    b.stage_x = ar.take<float>((size_t)R * ldx);
+    b.stage_y = ar.take<int>(R);
+    if (gan) {
+      b.dfake = ar.take<float>((size_t)B * ldx);
+      b.zb = ar.take<float>((size_t)B * pitch4(nd + 1));
+      b.h1g = ar.take<float>((size_t)B * kGH);
+      b.xhat = ar.take<float>((size_t)B * kGH);
+      b.istd = ar.take<float>(kGH);
+      b.u = ar.take<float>((size_t)B * pitch4(kGH + 1));
+      b.h2g = ar.take<float>((size_t)B * pitch4(kGH + 1));
+      b.dz2g = ar.take<float>((size_t)B * kGH);
+      b.du = ar.take<float>((size_t)B * kGH);
+      b.dz1g = ar.take<float>((size_t)B * kGH);
+      b.stage_z = ar.take<float>((size_t)B * nd);
+    }
+    b.ex_stage = ar.take<float>((size_t)NE * b.lda[0]);
+    b.xte = ar.take<float>((size_t)nte * b.lda[0]);
+    for (int l = 1; l <= 5; ++l) b.eh[l] = ar.take<float>((size_t)NE * b.lda[l]);
+    b.elg = ar.take<float>((size_t)NE * pitch4(K));
+    b.ey_stage = ar.take<int>(NE);
+    b.eval_out = ar.take<float>(4);
+    b.eval_out_s = ar.take<float>(4);
+    b.xtr = ar.take<float>((size_t)ntr * ldx);
+    b.ytr = ar.take<int>(ntr);
+    b.yte = ar.take<int>(nte);
+    b.idx = ar.take<int>((size_t)3 * ntr);
+  }
+}
+
+GemmDesc make_desc(const float* A, int lda, const float* Bm, int ldb, float* C, int ldc, int M, int N, int K, int epi,
+                   int act, int fold) {
+  GemmDesc d;
+  memset(&d, 0, sizeof(d));
+  d.A = A; d.lda = lda; d.B = Bm; d.ldb = ldb; d.C = C; d.ldc = ldc; d.M = M; d.N = N; d.K = K;
+  d.epi = epi; d.act = act; d.fold = fold;
+  return d;
+}
+
+void build_descs(mrgan_handle* h) {
+  const mrgan_config& c = h->cfg;
+  const int B = c.batch, R = h->R, K = c.n_classes, nd = c.noise_dim, nf = h->nf;
+  const bool gan = c.model == MRGAN_MODEL_GAN;
+  h->h_descs.assign((size_t)NUM_OPS * nf, GemmDesc{});
+  h->h_folds.assign(nf, FoldState{});
+  std::vector<BnDesc> bn(nf); std::vector<LossDesc> ls(nf); std::vector<EvalDesc> ev(nf), evs(nf);
+  std::vector<AdamRange> rg0(nf), rg1(nf);
+  auto setop = [&](int op, int f, const GemmDesc& d, bool at, bool bt) {
+    h->h_descs[(size_t)op * nf + f] = d;
+    OpInfo& oi = h->ops[op];
+    oi.at = at; oi.bt = bt; oi.used = true;
+    if (d.M > oi.maxM) oi.maxM = d.M;
+    if (d.N > oi.maxN) oi.maxN = d.N;
+  };
+  for (int f = 0; f < nf; ++f) {
+    FoldBuffers& b = h->fb[f];
+    const int D = h->shapes[f].D;
+    const NetLayout& LD = h->net[0][f];
+    float* PD = h->P + LD.off; float* GD = h->Gr + LD.off;
+    int win[6] = {D, kDW[0], kDW[1], kDW[2], kDW[3], kDW[4]};
+    int wout[6] = {kDW[0], kDW[1], kDW[2], kDW[3], kDW[4], K};
+    const float sig[5] = {c.sigma_in, c.sigma_hidden, c.sigma_hidden, c.sigma_hidden, c.sigma_hidden};
+    // ---- discriminator forward (train): layer l (1-based) reads a[l-1], writes h[l] (+ noisy a[l])
+    for (int l = 1; l <= 6; ++l) {
+      const TensorLayout& W = LD.t[l - 1];
+      float* C = (l <= 5) ? b.hb[l] : b.lg;
+      const int ldc = (l <= 5) ? b.lda[l] : pitch4(K);
+      GemmDesc d = make_desc(b.a[l - 1], b.lda[l - 1], PD + W.off, W.pitch, C, ldc, R, wout[l - 1], win[l - 1] + 1,
+                             EPI_FWD, l <= 5 ? ACT_RELU : ACT_NONE, f);
+      if (l <= 4) { d.C2 = b.a[l]; d.ldc2 = b.lda[l]; d.sigma = sig[l]; d.tid = l; d.row0 = 0; }
+      setop(OP_D1 + l - 1, f, d, false, false);
+      // eval twin: no noise, reads the clean activations
+      const float* EA = (l == 1) ? b.xte : b.eh[l - 1];
+      float* EC = (l <= 5) ? b.eh[l] : b.elg;
+      GemmDesc e = make_desc(EA, b.lda[l - 1], PD + W.off, W.pitch, EC, ldc, h->shapes[f].n_test, wout[l - 1],
+                             win[l - 1] + 1, EPI_FWD, l <= 5 ? ACT_RELU : ACT_NONE, f);
+      setop(l == 1 ? OP_E1 : OP_E2 + l - 2, f, e, false, false);
+      if (l == 1) { e.A = b.ex_stage; setop(OP_E1S, f, e, false, false); }
+      // dW (+db): grad(Waug_l) = a[l-1]^T @ dZ[l]
+      const float* dZ = (l <= 5) ? b.dz[l] : b.dlg;
+      const int lddz = (l <= 5) ? b.ldz[l] : pitch4(K);
+      GemmDesc w = make_desc(b.a[l - 1], b.lda[l - 1], dZ, lddz, GD + W.off, W.pitch, win[l - 1] + 1, wout[l - 1], R,
+                             EPI_STORE, ACT_NONE, f);
+      setop(OP_DW1 + l - 1, f, w, true, false);
+      // dX: dZ[l-1] = (dZ[l] @ W_l^T) * relu'(h[l-1])
+      if (l >= 2) {
+        GemmDesc x = make_desc(dZ, lddz, PD + W.off, W.pitch, b.dz[l - 1], b.ldz[l - 1], R, win[l - 1], wout[l - 1],
+                               EPI_DX, ACT_RELU, f);
+        x.aux = b.hb[l - 1]; x.ldaux = b.lda[l - 1];
+        setop(OP_DX2 + l - 2, f, x, false, true);
+      }
+    }
+    rg0[f] = AdamRange{LD.off, LD.n};
+    ls[f] = LossDesc{b.lg, b.dlg, pitch4(K), b.labels_cur, b.hb[5], b.dz[5], b.lda[5], b.ldz[5], kDW[4]};
+    ev[f] = EvalDesc{b.elg, pitch4(K), b.yte, h->shapes[f].n_test, (h->shapes[f].n_test / B) * B, b.eval_out};
+    evs[f] = EvalDesc{b.elg, pitch4(K), b.ey_stage, h->shapes[f].n_test, 0, b.eval_out_s};
+    if (gan) {
+      const NetLayout& LG = h->net[1][f];
+      float* PG = h->P + LG.off; float* GG = h->Gr + LG.off;
+      const TensorLayout &W1 = LG.t[0], &Tg = LG.t[1], &Tb = LG.t[2], &W2 = LG.t[3], &W3 = LG.t[4];
+      const int ldzb = pitch4(nd + 1), ldu = pitch4(kGH + 1), ldx = pitch4(D);
+      setop(OP_G1, f, make_desc(b.zb, ldzb, PG + W1.off, W1.pitch, b.h1g, kGH, B, kGH, nd + 1, EPI_FWD, ACT_SOFTPLUS, f), false, false);
+      setop(OP_G2, f, make_desc(b.u, ldu, PG + W2.off, W2.pitch, b.h2g, ldu, B, kGH, kGH + 1, EPI_FWD, ACT_SOFTPLUS, f), false, false);
+      GemmDesc g3 = make_desc(b.h2g, ldu, PG + W3.off, W3.pitch, nullptr, 0, B, D, kGH + 1, EPI_FWD, ACT_NONE, f);
+      g3.C2 = b.a[0] + (size_t)2 * B * b.lda[0]; g3.ldc2 = b.lda[0]; g3.sigma = c.sigma_in; g3.tid = 0; g3.row0 = 2 * B;
+      setop(OP_G3D, f, g3, false, false);
+      g3.C2 = b.a[0]; g3.row0 = 0;
+      setop(OP_G3G, f, g3, false, false);
+      // dFake = dZ[1] @ W1^T  (no activation derivative: fake is G's linear output)
+      const TensorLayout& DW1 = LD.t[0];
+      setop(OP_DX1G, f, make_desc(b.dz[1], b.ldz[1], PD + DW1.off, DW1.pitch, b.dfake, ldx, B, D, kDW[0], EPI_DX, ACT_NONE, f), false, true);
+      setop(OP_GW3, f, make_desc(b.h2g, ldu, b.dfake, ldx, GG + W3.off, W3.pitch, kGH + 1, D, B, EPI_STORE, ACT_NONE, f), true, false);
+      GemmDesc gx3 = make_desc(b.dfake, ldx, PG + W3.off, W3.pitch, b.dz2g, kGH, B, kGH, D, EPI_DX, ACT_SOFTPLUS, f);
+      gx3.aux = b.h2g; gx3.ldaux = ldu;
+      setop(OP_GX3, f, gx3, false, true);
+      setop(OP_GW2, f, make_desc(b.u, ldu, b.dz2g, kGH, GG + W2.off, W2.pitch, kGH + 1, kGH, B, EPI_STORE, ACT_NONE, f), true, false);
+      setop(OP_GX2, f, make_desc(b.dz2g, kGH, PG + W2.off, W2.pitch, b.du, kGH, B, kGH, kGH, EPI_DX, ACT_NONE, f), false, true);
+      setop(OP_GW1, f, make_desc(b.zb, ldzb, b.dz1g, kGH, GG + W1.off, W1.pitch, nd + 1, kGH, B, EPI_STORE, ACT_NONE, f), true, false);
+      bn[f] = BnDesc{b.h1g, b.xhat, b.u, b.istd, PG + Tg.off, PG + Tb.off, b.du, b.dz1g, GG + Tg.off, GG + Tb.off,
+                     kGH, ldu, B, kGH};
+      rg1[f] = AdamRange{LG.off, LG.n};
+    }
+    FoldState& fs = h->h_folds[f];
+    fs.key0 = (uint32_t)(h->shapes[f].seed & 0xFFFFFFFFull);
+    fs.key1 = (uint32_t)(h->shapes[f].seed >> 32);
+    fs.D = D; fs.n_train = h->shapes[f].n_train; fs.n_test = h->shapes[f].n_test; fs.ldx = pitch4(D);
+    fs.x_train = b.xtr; fs.y_train = b.ytr; fs.y_test = b.yte;
+    for (int s = 0; s < 3; ++s) fs.idx[s] = b.idx + (size_t)s * h->shapes[f].n_train;
+    fs.stage_x = b.stage_x; fs.stage_y = b.stage_y; fs.stage_z = gan ? b.stage_z : nullptr;
+    fs.a0 = b.a[0]; fs.lda0 = b.lda[0]; fs.z = gan ? b.zb : nullptr; fs.ldz = pitch4(nd + 1);
+    fs.labels_cur = b.labels_cur;
+  }
+  cudaMemcpy(h->d_descs, h->h_descs.data(), h->h_descs.size() * sizeof(GemmDesc), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_folds, h->h_folds.data(), nf * sizeof(FoldState), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_loss, ls.data(), nf * sizeof(LossDesc), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_eval, ev.data(), nf * sizeof(EvalDesc), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_eval_s, evs.data(), nf * sizeof(EvalDesc), cudaMemcpyHostToDevice);
+  cudaMemcpy(h->d_ranges[0], rg0.data(), nf * sizeof(AdamRange), cudaMemcpyHostToDevice);
+  if (gan) {
+    cudaMemcpy(h->d_bn, bn.data(), nf * sizeof(BnDesc), cudaMemcpyHostToDevice);
+    cudaMemcpy(h->d_ranges[1], rg1.data(), nf * sizeof(AdamRange), cudaMemcpyHostToDevice);
+  }
+}
+
+void set_ones(mrgan_handle* h, float* p, int ld, int rows, int col) {
+  k_set_col<<<(rows + 127) / 128, 128, 0, h->stream>>>(p, ld, rows, col, 1.0f);
+}
+
+void init_ones(mrgan_handle* h) {
+  const mrgan_config& c = h->cfg;
+  const bool gan = c.model == MRGAN_MODEL_GAN;
+  for (int f = 0; f < h->nf; ++f) {
+    FoldBuffers& b = h->fb[f];
+    const int D = h->shapes[f].D;
+    int win[6] = {D, kDW[0], kDW[1], kDW[2], kDW[3], kDW[4]};
+    set_ones(h, b.a[0], b.lda[0], h->R, D);
+    set_ones(h, b.ex_stage, b.lda[0], h->NE, D);
+    set_ones(h, b.xte, b.lda[0], h->shapes[f].n_test, D);
+    for (int l = 1; l <= 5; ++l) {
+      set_ones(h, b.hb[l], b.lda[l], h->R, win[l]);
+      if (l < 5) set_ones(h, b.a[l], b.lda[l], h->R, win[l]);
+      set_ones(h, b.eh[l], b.lda[l], h->NE, win[l]);
+    }
+    if (gan) {
+      set_ones(h, b.zb, pitch4(c.noise_dim + 1), c.batch, c.noise_dim);
+      set_ones(h, b.u, pitch4(kGH + 1), c.batch, kGH);
+      set_ones(h, b.h2g, pitch4(kGH + 1), c.batch, kGH);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ launch sequences
+void launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override) {
+  const OpInfo& oi = h->ops[op];
+  int M = oi.maxM;
+  if (rows_override > 0 && !oi.at) M = rows_override;
+  const GemmDesc* d = h->d_descs + (size_t)op * h->nf + f0;
+#ifdef MRGAN_WITH_TC
+  if (h->cfg.precision == MRGAN_PREC_TF32 && tc_launch_gemm(h, op, f0, nfl, rows_override)) return;
+#endif
+  dim3 grid((oi.maxN + 63) / 64, (M + 63) / 64, nfl);
+  if (!oi.at && !oi.bt) k_gemm_simt<false, false><<<grid, 256, 0, h->stream>>>(d, h->d_folds, rows_override);
+  else if (!oi.at && oi.bt) k_gemm_simt<false, true><<<grid, 256, 0, h->stream>>>(d, h->d_folds, rows_override);
+  else k_gemm_simt<true, false><<<grid, 256, 0, h->stream>>>(d, h->d_folds, rows_override);
+  h->launches++;
+}
+
+int max_D(const mrgan_handle* h, int f0, int nfl) {
+  int m = 0;
+  for (int f = f0; f < f0 + nfl; ++f) m = h->shapes[f].D > m ? h->shapes[f].D : m;
+  return m;
+}
+
+void launch_prep(mrgan_handle* h, int f0, int nfl, int mode, int from_stage, int t, int nrows) {
+  const mrgan_config& c = h->cfg;
+  int cols = max_D(h, f0, nfl);
+  if (c.noise_dim > cols) cols = c.noise_dim;
+  dim3 grid((cols + 127) / 128, (nrows + 3) / 4, nfl);
+  k_prep<<<grid, 128, 0, h->stream>>>(h->d_folds, f0, mode, from_stage, t, c.batch, nrows, c.noise_dim, c.sigma_in, h->hp);
+  h->launches++;
+}
+
+void launch_adam(mrgan_handle* h, int f0, int nfl, int net) {
+  long long nmax = 0;
+  for (int f = f0; f < f0 + nfl; ++f) nmax = h->net[net][f].n > nmax ? h->net[net][f].n : nmax;
+  int blocks = (int)((nmax / 4 + 255) / 256);
+  if (blocks > 2048) blocks = 2048;
+  if (blocks < 1) blocks = 1;
+  k_adam<<<dim3(blocks, nfl), 256, 0, h->stream>>>(h->P, h->Mo, h->Vo, h->Gr, h->d_ranges[net], h->d_folds, f0, net, h->hp);
+  h->launches++;
+}
+
+void enqueue_gen_fwd(mrgan_handle* h, int f0, int nfl, int op_g3) {
+  launch_gemm(h, OP_G1, f0, nfl, 0);
+  k_bn_fwd<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, h->cfg.bn_eps);
+  h->launches++;
+  launch_gemm(h, OP_G2, f0, nfl, 0);
+  launch_gemm(h, op_g3, f0, nfl, 0);
+}
+
+// train_batch_disc (mr_gan.py:169)
+void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
+  const mrgan_config& c = h->cfg;
+  const int B = c.batch;
+  launch_prep(h, f0, nfl, 0, from_stage, t, 2 * B);
+  enqueue_gen_fwd(h, f0, nfl, OP_G3D);
+  for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 0);
+  k_loss_disc<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B, c.n_classes, c.unlabeled_weight);
+  h->launches++;
+  for (int l = 6; l >= 1; --l) {
+    launch_gemm(h, OP_DW1 + l - 1, f0, nfl, 0);
+    if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
+  }
+  launch_adam(h, f0, nfl, 0);
+}
+
+// train_batch_gen (mr_gan.py:170)
+void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
+  const mrgan_config& c = h->cfg;
+  const int B = c.batch;
+  launch_prep(h, f0, nfl, 1, from_stage, t, 2 * B);
+  enqueue_gen_fwd(h, f0, nfl, OP_G3G);
+  for (int l = 0; l < 5; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 2 * B);
+  k_fm<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B);
+  h->launches++;
+  for (int l = 5; l >= 2; --l) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, B);
+  launch_gemm(h, OP_DX1G, f0, nfl, 0);
+  launch_gemm(h, OP_GW3, f0, nfl, 0);
+  launch_gemm(h, OP_GX3, f0, nfl, 0);
+  launch_gemm(h, OP_GW2, f0, nfl, 0);
+  launch_gemm(h, OP_GX2, f0, nfl, 0);
+  k_bn_bwd<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0);
+  h->launches++;
+  launch_gemm(h, OP_GW1, f0, nfl, 0);
+  launch_adam(h, f0, nfl, 1);
+}
+
+// one model.fit batch of mr_nn (mr_nn.py:117)
+void enqueue_nn_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage, int n) {
+  const mrgan_config& c = h->cfg;
+  launch_prep(h, f0, nfl, 2, from_stage, t, n);
+  const int ov = (n == h->R) ? 0 : n;
+  for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, ov);
+  k_loss_mse<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, n, c.n_classes);
+  h->launches++;
+  for (int l = 6; l >= 1; --l) {
+    launch_gemm(h, OP_DW1 + l - 1, f0, nfl, ov);
+    if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, ov);
+  }
+  launch_adam(h, f0, nfl, 0);
+}
+
+// test_batch (mr_gan.py:171): phase 0, no noise
+void enqueue_eval(mrgan_handle* h, int f0, int nfl, bool staged, int n_override) {
+  launch_gemm(h, staged ? OP_E1S : OP_E1, f0, nfl, n_override);
+  for (int l = 1; l < 6; ++l) launch_gemm(h, OP_E2 + l - 1, f0, nfl, n_override);
+  k_argmax_err<<<dim3(1, 1, nfl), 256, 0, h->stream>>>((staged ? h->d_eval_s : h->d_eval) + f0, n_override, h->cfg.n_classes);
+  h->launches++;
+}
+
+int check_fold(mrgan_handle* h, int fold) {
+  if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
+  if (fold < 0 || fold >= h->nf) return fail(h, MRGAN_ERR_ARG, "fold index out of range");
+  return MRGAN_OK;
+}
+
+int finish_pending(mrgan_handle* h) {
+  if (h->epoch_pending) {
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    h->epoch_pending = false;
+  }
+  return MRGAN_OK;
+}
+
+// reference-order <-> internal (augmented, padded) parameter layout
+void pack_params(const mrgan_handle* h, int fold, int net, const float* src, std::vector<float>& dst, bool to_internal,
+                 float* out_ref) {
+  const NetLayout& L = h->net[net][fold];
+  long long o = 0;
+  auto mat = [&](const TensorLayout& t, int rows_w) {     // W[rows_w, cols] then b[cols]
+    for (int r = 0; r < rows_w + 1; ++r)
+      for (int cidx = 0; cidx < t.cols; ++cidx) {
+        const long long ii = t.off + (long long)r * t.pitch + cidx;
+        if (to_internal) dst[ii] = src[o]; else out_ref[o] = dst[ii];
+        ++o;
+      }
+  };
+  auto vec = [&](const TensorLayout& t) {
+    for (int cidx = 0; cidx < t.cols; ++cidx) {
+      if (to_internal) dst[t.off + cidx] = src[o]; else out_ref[o] = dst[t.off + cidx];
+      ++o;
+    }
+  };
+  if (net == 0) {
+    for (int l = 0; l < 6; ++l) mat(L.t[l], L.t[l].rows - 1);
+  } else {
+    mat(L.t[0], L.t[0].rows - 1); vec(L.t[1]); vec(L.t[2]); mat(L.t[3], L.t[3].rows - 1); mat(L.t[4], L.t[4].rows - 1);
+  }
+}
+
+int build_graph(mrgan_handle* h, int key, int nb, int n_idx_nn) {
+  if (h->graphs.count(key)) return MRGAN_OK;
+  const mrgan_config& c = h->cfg;
+  const long long before = h->launches;
+  cudaGraph_t g = nullptr;
+  CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  if (c.model == MRGAN_MODEL_GAN) {
+    for (int t = 0; t < nb; ++t) {
+      enqueue_disc_step(h, 0, h->nf, t, 0);
+      enqueue_gen_step(h, 0, h->nf, t, 0);
+    }
+    if (c.eval_each_epoch) enqueue_eval(h, 0, h->nf, false, 0);
+  } else {
+    for (int t = 0; t < nb; ++t) enqueue_nn_step(h, 0, h->nf, t, 0, c.batch);
+  }
+  k_epoch_reduce<<<h->nf, 32, 0, h->stream>>>(h->d_step_stats, h->d_eval, h->d_epoch_stats, h->nf, nb,
+                                              c.model == MRGAN_MODEL_GAN && c.eval_each_epoch);
+  h->launches++;
+  CK(cudaMemcpyAsync(h->h_epoch_stats, h->d_epoch_stats, (size_t)h->nf * 8 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamEndCapture(h->stream, &g));
+  cudaGraphExec_t ge = nullptr;
+  CK(cudaGraphInstantiate(&ge, g, 0));
+  CK(cudaGraphDestroy(g));
+  h->graphs[key] = ge;
+  h->graph_nodes[key] = h->launches - before;
+  h->launches = before;
+  (void)n_idx_nn;
+  return MRGAN_OK;
+}
+
+int upload_indices(mrgan_handle* h, const int32_t* const* streams, int n_streams, int n_idx) {
+  // host [nf][n_idx] per stream -> pinned staging -> device idx[f][s][n_train]
+  const int slot = h->idx_slot;
+  h->idx_slot ^= 1;
+  CK(cudaEventSynchronize(h->idx_free[slot]));
+  int* pin = h->h_idx_pinned[slot];
+  for (int f = 0; f < h->nf; ++f)
+    for (int s = 0; s < n_streams; ++s)
+      memcpy(pin + ((size_t)f * 3 + s) * h->n_train, streams[s] + (size_t)f * n_idx, (size_t)n_idx * sizeof(int));
+  for (int f = 0; f < h->nf; ++f)
+    CK(cudaMemcpyAsync(h->fb[f].idx, pin + (size_t)f * 3 * h->n_train, (size_t)3 * h->n_train * sizeof(int),
+                       cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->idx_free[slot], h->stream));
+  return MRGAN_OK;
+}
+
+}  // namespace
+
+// ====================================================================== C-ABI
+extern "C" {
+
+const char* mrgan_version(void) { return "mrgan-b200 0.1 (sm_100a)"; }
+
+int mrgan_default_config(int model, mrgan_config* cfg) {
+  if (!cfg) return fail(nullptr, MRGAN_ERR_ARG, "cfg is null");
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->model = model;
+  cfg->n_folds = 1;
+  cfg->n_classes = 6;
+  cfg->noise_dim = 100;
+  cfg->precision = MRGAN_PREC_FP32;
+  cfg->shared_t = 1;
+  cfg->eval_each_epoch = 1;
+  cfg->device = 0;
+  cfg->beta2 = 0.999f; cfg->adam_eps = 1e-8f; cfg->bn_eps = 2e-5f;
+  cfg->unlabeled_weight = 1.0f; cfg->sigma_in = 0.3f; cfg->sigma_hidden = 0.5f;
+  if (model == MRGAN_MODEL_NN) { cfg->batch = 20; cfg->lr = 1e-3f; cfg->beta1 = 0.9f; }
+  else { cfg->batch = 50; cfg->lr = 6e-4f; cfg->beta1 = 0.5f; }
+  return MRGAN_OK;
+}
+
+const char* mrgan_last_error(const mrgan_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_handle** out) {
+  mrgan_handle* h = nullptr;
+  if (!cfg || !folds || !out) return fail(nullptr, MRGAN_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->n_folds < 1 || cfg->batch < 1 || cfg->n_classes < 2 || cfg->n_classes > 64 || cfg->noise_dim < 1)
+    return fail(nullptr, MRGAN_ERR_ARG, "bad config (n_folds/batch/n_classes/noise_dim)");
+  if (cfg->model != MRGAN_MODEL_GAN && cfg->model != MRGAN_MODEL_NN) return fail(nullptr, MRGAN_ERR_ARG, "bad model");
+  if (cfg->model == MRGAN_MODEL_GAN && 3 * cfg->batch > 4096) return fail(nullptr, MRGAN_ERR_ARG, "batch too large");
+  for (int f = 0; f < cfg->n_folds; ++f) {
+    if (folds[f].D < 1 || folds[f].n_train < cfg->batch || folds[f].n_test < 1)
+      return fail(nullptr, MRGAN_ERR_ARG, "bad fold shape");
+    if (folds[f].n_train != folds[0].n_train)
+      return fail(nullptr, MRGAN_ERR_ARG, "all folds of a handle must have the same n_train");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev)
+    return fail(nullptr, MRGAN_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major < 10)
+    return fail(nullptr, MRGAN_ERR_NO_DEVICE, "device is not sm_100 (Blackwell): this library has no CPU fallback");
+#ifndef MRGAN_WITH_TC
+  if (cfg->precision == MRGAN_PREC_TF32) return fail(nullptr, MRGAN_ERR_ARG, "library built without the tcgen05 kernels");
+#endif
+  h = new mrgan_handle();
+  h->cfg = *cfg;
+  h->nf = cfg->n_folds;
+  h->R = cfg->model == MRGAN_MODEL_GAN ? 3 * cfg->batch : cfg->batch;
+  h->n_train = folds[0].n_train;
+  h->shapes.assign(folds, folds + h->nf);
+  h->fb.resize(h->nf);
+  h->hp = AdamHyper{cfg->lr, cfg->beta1, cfg->beta2, cfg->adam_eps, cfg->shared_t};
+  int ne = h->R;
+  for (int f = 0; f < h->nf; ++f) ne = folds[f].n_test > ne ? folds[f].n_test : ne;
+  h->NE = ne;
+  auto cleanup = [&](int code) { mrgan_destroy(h); return code; };
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, "cudaSetDevice failed"));
+  // flat parameter space: all D nets, then all G nets
+  long long off = 0;
+  for (int n = 0; n < (cfg->model == MRGAN_MODEL_GAN ? 2 : 1); ++n) {
+    h->net[n].resize(h->nf);
+    for (int f = 0; f < h->nf; ++f) {
+      NetLayout L = n == 0 ? layout_disc(folds[f].D, cfg->n_classes) : layout_gen(folds[f].D, cfg->noise_dim);
+      L.off = off;
+      off += L.n;
+      h->net[n][f] = L;
+    }
+  }
+  h->n_flat = off;
+  Arena sizing;
+  layout_buffers(h, sizing);
+  h->arena_bytes = sizing.off + 256;
+  cudaError_t e = cudaMalloc(&h->arena, h->arena_bytes);
+  if (e != cudaSuccess) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, std::string("cudaMalloc arena: ") + cudaGetErrorString(e)));
+  e = cudaMemset(h->arena, 0, h->arena_bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e)));
+  Arena real; real.base = h->arena;
+  layout_buffers(h, real);
+  bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
+  ok = ok && cudaMallocHost(&h->h_epoch_stats, (size_t)h->nf * 8 * sizeof(float)) == cudaSuccess;
+  ok = ok && cudaMallocHost(&h->h_scratch, 64 * sizeof(float)) == cudaSuccess;
+  for (int s = 0; s < 2 && ok; ++s) {
+    ok = ok && cudaMallocHost(&h->h_idx_pinned[s], (size_t)h->nf * 3 * h->n_train * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->idx_free[s], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, "stream/event/pinned allocation failed"));
+  build_descs(h);
+  init_ones(h);
+#ifdef MRGAN_WITH_TC
+  if (cfg->precision == MRGAN_PREC_TF32) {
+    int rc = tc_setup(h);
+    if (rc != MRGAN_OK) return cleanup(rc);
+  }
+#endif
+  e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, std::string("create: ") + cudaGetErrorString(e)));
+  *out = h;
+  return MRGAN_OK;
+}
+
+int mrgan_destroy(mrgan_handle* h) {
+  if (!h) return MRGAN_OK;
+  cudaSetDevice(h->cfg.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+#ifdef MRGAN_WITH_TC
+  tc_teardown(h);
+#endif
+  if (h->arena) cudaFree(h->arena);
+  if (h->h_epoch_stats) cudaFreeHost(h->h_epoch_stats);
+  if (h->h_scratch) cudaFreeHost(h->h_scratch);
+  for (int s = 0; s < 2; ++s) {
+    if (h->h_idx_pinned[s]) cudaFreeHost(h->h_idx_pinned[s]);
+    if (h->idx_free[s]) cudaEventDestroy(h->idx_free[s]);
+  }
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return MRGAN_OK;
+}
+
+int mrgan_sync(mrgan_handle* h) {
+  if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = finish_pending(h);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  return MRGAN_OK;
+}
+
+int64_t mrgan_num_params(const mrgan_handle* h, int fold, int net) {
+  if (!h || fold < 0 || fold >= h->nf || net < 0 || net > 1 || h->net[net].empty()) return -1;
+  return h->net[net][fold].n_ref;
+}
+
+int mrgan_set_params(mrgan_handle* h, int fold, int net, const float* src, int64_t n) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (net < 0 || net > 1 || h->net[net].empty()) return fail(h, MRGAN_ERR_ARG, "no such net in this model");
+  const NetLayout& L = h->net[net][fold];
+  if (!src || n != L.n_ref) return fail(h, MRGAN_ERR_ARG, "set_params: length does not match mrgan_num_params");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  std::vector<float> buf((size_t)L.n, 0.f);
+  pack_params(h, fold, net, src, buf, true, nullptr);
+  CK(cudaMemcpyAsync(h->P + L.off, buf.data(), (size_t)L.n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+#ifdef MRGAN_WITH_TC
+  if (h->cfg.precision == MRGAN_PREC_TF32) tc_params_changed(h, fold, net);
+#endif
+  return MRGAN_OK;
+}
+
+static int get_flat(mrgan_handle* h, int fold, int net, const float* dev, float* dst, int64_t n) {
+  const NetLayout& L = h->net[net][fold];
+  if (!dst || n != L.n_ref) return fail(h, MRGAN_ERR_ARG, "length does not match mrgan_num_params");
+  std::vector<float> buf((size_t)L.n);
+  CK(cudaMemcpyAsync(buf.data(), dev + L.off, (size_t)L.n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  pack_params(h, fold, net, nullptr, buf, false, dst);
+  return MRGAN_OK;
+}
+
+int mrgan_get_params(mrgan_handle* h, int fold, int net, float* dst, int64_t n) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (net < 0 || net > 1 || h->net[net].empty()) return fail(h, MRGAN_ERR_ARG, "no such net in this model");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  return get_flat(h, fold, net, h->P, dst, n);
+}
+
+int mrgan_get_adam(mrgan_handle* h, int fold, int net, float* m, float* v, int64_t n) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (net < 0 || net > 1 || h->net[net].empty()) return fail(h, MRGAN_ERR_ARG, "no such net in this model");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  rc = get_flat(h, fold, net, h->Mo, m, n); if (rc) return rc;
+  return get_flat(h, fold, net, h->Vo, v, n);
+}
+
+int mrgan_get_counters(mrgan_handle* h, int fold, int* iterations, int* rng_step) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  FoldState fs;
+  CK(cudaMemcpyAsync(&fs, h->d_folds + fold, sizeof(fs), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (iterations) *iterations = h->cfg.shared_t ? fs.iterations : fs.it_net[0];
+  if (rng_step) *rng_step = fs.rng_step;
+  return MRGAN_OK;
+}
+
+int mrgan_load_fold(mrgan_handle* h, int fold, const float* x_train, const int32_t* y_train, const float* x_test,
+                    const int32_t* y_test) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (!x_train || !y_train || !x_test || !y_test) return fail(h, MRGAN_ERR_ARG, "load_fold: null pointer");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  const mrgan_fold_shape& s = h->shapes[fold];
+  for (int i = 0; i < s.n_train; ++i)
+    if (y_train[i] < 0 || y_train[i] >= h->cfg.n_classes) return fail(h, MRGAN_ERR_ARG, "load_fold: y_train label out of range");
+  for (int i = 0; i < s.n_test; ++i)
+    if (y_test[i] < 0 || y_test[i] >= h->cfg.n_classes) return fail(h, MRGAN_ERR_ARG, "load_fold: y_test label out of range");
+  FoldBuffers& b = h->fb[fold];
+  const size_t w = (size_t)s.D * sizeof(float);
+  CK(cudaMemcpy2DAsync(b.xtr, (size_t)pitch4(s.D) * sizeof(float), x_train, w, w, s.n_train, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(b.xte, (size_t)b.lda[0] * sizeof(float), x_test, w, w, s.n_test, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(b.ytr, y_train, (size_t)s.n_train * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(b.yte, y_test, (size_t)s.n_test * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  b.loaded = true;
+  return MRGAN_OK;
+}
+
+int mrgan_disc_step(mrgan_handle* h, int fold, const float* x_lab, const int32_t* labels, const float* x_unl,
+                    const float* z, float out[3]) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (h->cfg.model != MRGAN_MODEL_GAN) return fail(h, MRGAN_ERR_STATE, "disc_step needs a GAN handle");
+  if (!x_lab || !labels || !x_unl || !z || !out) return fail(h, MRGAN_ERR_ARG, "disc_step: null pointer");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  const int B = h->cfg.batch, D = h->shapes[fold].D, nd = h->cfg.noise_dim;
+  for (int i = 0; i < B; ++i)
+    if (labels[i] < 0 || labels[i] >= h->cfg.n_classes) return fail(h, MRGAN_ERR_ARG, "disc_step: label out of range");
+  FoldBuffers& b = h->fb[fold];
+  const size_t w = (size_t)D * sizeof(float), ld = (size_t)pitch4(D) * sizeof(float);
+  CK(cudaMemcpy2DAsync(b.stage_x, ld, x_lab, w, w, B, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(b.stage_x + (size_t)B * pitch4(D), ld, x_unl, w, w, B, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(b.stage_y, labels, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(b.stage_z, z, (size_t)B * nd * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  enqueue_disc_step(h, fold, 1, 0, 1);
+  CK(cudaMemcpyAsync(h->h_scratch, h->d_step_stats + (size_t)fold * 4, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  out[0] = h->h_scratch[0]; out[1] = h->h_scratch[1]; out[2] = h->h_scratch[2];
+  return MRGAN_OK;
+}
+
+int mrgan_gen_step(mrgan_handle* h, int fold, const float* x_unl, const float* z, float out[1]) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (h->cfg.model != MRGAN_MODEL_GAN) return fail(h, MRGAN_ERR_STATE, "gen_step needs a GAN handle");
+  if (!x_unl || !z || !out) return fail(h, MRGAN_ERR_ARG, "gen_step: null pointer");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  const int B = h->cfg.batch, D = h->shapes[fold].D, nd = h->cfg.noise_dim;
+  FoldBuffers& b = h->fb[fold];
+  const size_t w = (size_t)D * sizeof(float), ld = (size_t)pitch4(D) * sizeof(float);
+  CK(cudaMemcpy2DAsync(b.stage_x + (size_t)B * pitch4(D), ld, x_unl, w, w, B, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(b.stage_z, z, (size_t)B * nd * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  enqueue_gen_step(h, fold, 1, 0, 1);
+  CK(cudaMemcpyAsync(h->h_scratch, h->d_step_stats + (size_t)fold * 4, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  out[0] = h->h_scratch[3];
+  return MRGAN_OK;
+}
+
+int mrgan_test_batch(mrgan_handle* h, int fold, const float* x, const int32_t* y, int n, float* err) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (!x || !y || !err) return fail(h, MRGAN_ERR_ARG, "test_batch: null pointer");
+  if (n < 1 || n > h->NE) return fail(h, MRGAN_ERR_ARG, "test_batch: n exceeds max(n_test, rows of a train step)");
+  for (int i = 0; i < n; ++i)
+    if (y[i] < 0 || y[i] >= h->cfg.n_classes) return fail(h, MRGAN_ERR_ARG, "test_batch: label out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  FoldBuffers& b = h->fb[fold];
+  const int D = h->shapes[fold].D;
+  const size_t w = (size_t)D * sizeof(float);
+  CK(cudaMemcpy2DAsync(b.ex_stage, (size_t)b.lda[0] * sizeof(float), x, w, w, n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(b.ey_stage, y, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  enqueue_eval(h, fold, 1, true, n);
+  CK(cudaMemcpyAsync(h->h_scratch, b.eval_out_s, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  err[0] = h->h_scratch[1];
+  return MRGAN_OK;
+}
+
+int mrgan_eval(mrgan_handle* h, int fold, float* err) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (!err) return fail(h, MRGAN_ERR_ARG, "eval: null pointer");
+  if (!h->fb[fold].loaded) return fail(h, MRGAN_ERR_STATE, "eval before mrgan_load_fold");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  enqueue_eval(h, fold, 1, false, 0);
+  CK(cudaMemcpyAsync(h->h_scratch, h->fb[fold].eval_out, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  err[0] = h->h_scratch[1];
+  return MRGAN_OK;
+}
+
+int mrgan_epoch_result(mrgan_handle* h, mrgan_epoch_stats* stats) {
+  if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = finish_pending(h); if (rc) return rc;
+  CK(cudaGetLastError());
+  if (stats)
+    for (int f = 0; f < h->nf; ++f) {
+      const float* s = h->h_epoch_stats + (size_t)f * 8;
+      stats[f] = mrgan_epoch_stats{s[0], s[1], s[2], s[3], s[4]};
+    }
+  return MRGAN_OK;
+}
+
+int mrgan_train_epoch(mrgan_handle* h, const int32_t* idx_lab, const int32_t* idx_unl, const int32_t* idx_unl2,
+                      mrgan_epoch_stats* stats) {
+  if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
+  if (h->cfg.model != MRGAN_MODEL_GAN) return fail(h, MRGAN_ERR_STATE, "train_epoch needs a GAN handle");
+  if (!idx_lab || !idx_unl || !idx_unl2) return fail(h, MRGAN_ERR_ARG, "train_epoch: null index array");
+  for (int f = 0; f < h->nf; ++f)
+    if (!h->fb[f].loaded) return fail(h, MRGAN_ERR_STATE, "train_epoch before mrgan_load_fold");
+  const int nb = h->n_train / h->cfg.batch;
+  const size_t tot = (size_t)h->nf * h->n_train;
+  for (size_t i = 0; i < tot; ++i)
+    if ((unsigned)idx_lab[i] >= (unsigned)h->n_train || (unsigned)idx_unl[i] >= (unsigned)h->n_train ||
+        (unsigned)idx_unl2[i] >= (unsigned)h->n_train)
+      return fail(h, MRGAN_ERR_ARG, "train_epoch: row index out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = finish_pending(h); if (rc) return rc;
+  rc = build_graph(h, nb, nb, 0); if (rc) return rc;
+  const int32_t* streams[3] = {idx_lab, idx_unl, idx_unl2};
+  rc = upload_indices(h, streams, 3, h->n_train); if (rc) return rc;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  CK(cudaGraphLaunch(h->graphs[nb], h->stream));
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->launches += h->graph_nodes[nb];
+  h->epoch_pending = true;
+  if (stats) return mrgan_epoch_result(h, stats);
+  return MRGAN_OK;
+}
+
+int mrnn_step(mrgan_handle* h, int fold, const float* x, const int32_t* labels, int n, float out[2]) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (h->cfg.model != MRGAN_MODEL_NN) return fail(h, MRGAN_ERR_STATE, "mrnn_step needs an NN handle");
+  if (!x || !labels || !out) return fail(h, MRGAN_ERR_ARG, "mrnn_step: null pointer");
+  if (n < 1 || n > h->cfg.batch) return fail(h, MRGAN_ERR_ARG, "mrnn_step: n must be in [1, batch]");
+  for (int i = 0; i < n; ++i)
+    if (labels[i] < 0 || labels[i] >= h->cfg.n_classes) return fail(h, MRGAN_ERR_ARG, "mrnn_step: label out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  FoldBuffers& b = h->fb[fold];
+  const int D = h->shapes[fold].D;
+  const size_t w = (size_t)D * sizeof(float);
+  CK(cudaMemcpy2DAsync(b.stage_x, (size_t)pitch4(D) * sizeof(float), x, w, w, n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(b.stage_y, labels, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  enqueue_nn_step(h, fold, 1, 0, 1, n);
+  CK(cudaMemcpyAsync(h->h_scratch, h->d_step_stats + (size_t)fold * 4, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  out[0] = h->h_scratch[0]; out[1] = h->h_scratch[1];
+  return MRGAN_OK;
+}
+
+int mrnn_train_epoch(mrgan_handle* h, const int32_t* idx, int n_idx, float* loss_acc) {
+  if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
+  if (h->cfg.model != MRGAN_MODEL_NN) return fail(h, MRGAN_ERR_STATE, "mrnn_train_epoch needs an NN handle");
+  if (!idx || n_idx < h->cfg.batch || n_idx > h->n_train || n_idx % h->cfg.batch)
+    return fail(h, MRGAN_ERR_ARG, "mrnn_train_epoch: n_idx must be a multiple of batch in [batch, n_train]");
+  for (int f = 0; f < h->nf; ++f)
+    if (!h->fb[f].loaded) return fail(h, MRGAN_ERR_STATE, "mrnn_train_epoch before mrgan_load_fold");
+  for (size_t i = 0; i < (size_t)h->nf * n_idx; ++i)
+    if ((unsigned)idx[i] >= (unsigned)h->n_train) return fail(h, MRGAN_ERR_ARG, "mrnn_train_epoch: row index out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = finish_pending(h); if (rc) return rc;
+  const int nb = n_idx / h->cfg.batch;
+  rc = build_graph(h, nb, nb, n_idx); if (rc) return rc;
+  const int32_t* streams[1] = {idx};
+  rc = upload_indices(h, streams, 1, n_idx); if (rc) return rc;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  CK(cudaGraphLaunch(h->graphs[nb], h->stream));
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->launches += h->graph_nodes[nb];
+  h->epoch_pending = true;
+  if (loss_acc) {
+    rc = finish_pending(h); if (rc) return rc;
+    CK(cudaGetLastError());
+    for (int f = 0; f < h->nf; ++f) { loss_acc[2 * f] = h->h_epoch_stats[f * 8]; loss_acc[2 * f + 1] = h->h_epoch_stats[f * 8 + 1]; }
+  }
+  return MRGAN_OK;
+}
+
+int mrnn_evaluate(mrgan_handle* h, int fold, float out[2]) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (!out) return fail(h, MRGAN_ERR_ARG, "evaluate: null pointer");
+  if (!h->fb[fold].loaded) return fail(h, MRGAN_ERR_STATE, "evaluate before mrgan_load_fold");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  enqueue_eval(h, fold, 1, false, 0);
+  CK(cudaMemcpyAsync(h->h_scratch, h->fb[fold].eval_out, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  out[0] = h->h_scratch[2]; out[1] = 1.0f - h->h_scratch[1];
+  return MRGAN_OK;
+}
+
+int mrgan_fill_normal(mrgan_handle* h, int fold, int step, int tensor_id, int rows, int cols, int row0, float* dst) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (!dst || rows < 1 || cols < 1) return fail(h, MRGAN_ERR_ARG, "fill_normal: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  float* d = nullptr;
+  const size_t n = (size_t)rows * cols;
+  CK(cudaMalloc(&d, n * sizeof(float)));
+  k_fill_normal<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d, h->d_folds, fold, step, tensor_id, rows, cols, row0);
+  h->launches++;
+  cudaError_t e = cudaMemcpyAsync(dst, d, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(h, MRGAN_ERR_CUDA, cudaGetErrorString(e));
+  return MRGAN_OK;
+}
+
+int mrgan_adam_flat(mrgan_handle* h, float* p, float* m, float* v, const float* g, int64_t n, int t) {
+  if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
+  if (!p || !m || !v || !g || n < 1 || t < 1) return fail(h, MRGAN_ERR_ARG, "adam_flat: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = finish_pending(h); if (rc) return rc;
+  const int64_t n4 = (n + 3) / 4;
+  float* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)n4 * 16 * 4));
+  CK(cudaMemsetAsync(d, 0, (size_t)n4 * 16 * 4, h->stream));
+  float *dp = d, *dm = d + n4 * 4, *dv = d + n4 * 8, *dg = d + n4 * 12;
+  cudaMemcpyAsync(dp, p, n * 4, cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(dm, m, n * 4, cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(dv, v, n * 4, cudaMemcpyHostToDevice, h->stream);
+  cudaMemcpyAsync(dg, g, n * 4, cudaMemcpyHostToDevice, h->stream);
+  const double b1t = pow((double)h->hp.b1, (double)t), b2t = pow((double)h->hp.b2, (double)t);
+  const float lr_t = (float)((double)h->hp.lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+  int blocks = (int)((n4 + 255) / 256); if (blocks > 4096) blocks = 4096;
+  k_adam_plain<<<blocks, 256, 0, h->stream>>>((float4*)dp, (float4*)dm, (float4*)dv, (const float4*)dg, n4, lr_t,
+                                              h->hp.b1, h->hp.b2, h->hp.eps);
+  h->launches++;
+  cudaMemcpyAsync(p, dp, n * 4, cudaMemcpyDeviceToHost, h->stream);
+  cudaMemcpyAsync(m, dm, n * 4, cudaMemcpyDeviceToHost, h->stream);
+  cudaError_t e = cudaMemcpyAsync(v, dv, n * 4, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(h, MRGAN_ERR_CUDA, cudaGetErrorString(e));
+  return MRGAN_OK;
+}
+
+int64_t mrgan_kernel_launches(const mrgan_handle* h) { return h ? h->launches : -1; }
+double mrgan_last_device_ms(const mrgan_handle* h) { return h ? h->last_ms : -1.0; }
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+"""Drop-in for the reference's ``mr_gan.py``: same ``dataset()`` / ``mr_gan()`` signatures,
+same ``--tables`` CLI and stdout strings (mr_gan.py:236-341), with the compiled training step
+(mr_gan.py:169-171) and the epoch loop (mr_gan.py:183-230) running as sm_100a CUDA behind the
+C-ABI of include/mrgan.h.  New arguments are keyword-only and default to the reference's
+behaviour.  No CPU fallback: without a B200 ``mr_gan()`` raises."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+from sklearn.model_selection import StratifiedKFold
+
+from . import foldprep, sweep, synthetic
+from .engine import FoldGroup
+from .model import MATERIALS, fold_key, init_disc, init_gen
+
+MODALITIES = ['Force', 'Temperature', 'Force and Temperature', 'Contact mic', 'Temperature and Contact Mic',
+              'Force, Temperature, and Contact Mic', 'Force and Contact Mic']      # mr_gan.py:237
+
+
+def dataset(modalities=0, forcetempTime=4, contactmicTime=0.2, leaveObjectOut=False, verbose=False, *,
+            seed=0, data_dir='data_processed'):
+    """mr_gan.py:23-71.  The MREO pickles are not distributed with the reference; when
+    ``data_dir`` does not hold them, data of the same shape is synthesised (synthetic.py)."""
+    path = os.path.join(data_dir, 'processed_0.1sbefore_%s_times_%.2f_%.2f.pkl' % (MATERIALS[0], forcetempTime, contactmicTime))
+    if os.path.exists(path):
+        from .realdata import load_processed
+        return load_processed(modalities, forcetempTime, contactmicTime, leaveObjectOut, verbose, data_dir)
+    out = synthetic.synthetic_dataset(modalities, forcetempTime, contactmicTime, leaveObjectOut, seed=seed)
+    if verbose and not leaveObjectOut:
+        print('X:', np.shape(out[0]), 'y:', np.shape(out[1]), '(synthetic MREO shape)')
+    return out
+
+
+def train_gan_folds(jobs, epochs=100, verbose=False, *, seed=0, precision='fp32', device=0, batch=50,
+                    eval_each_epoch=True, shared_t=True, return_group=False):
+    """Train a GROUP of independent folds side by side on one GPU.
+
+    jobs: list of dicts with keys ``trainTestSets`` (or ``X``, ``y``), ``percentlabeled``,
+    ``percentunlabeled`` (optional), ``job_id`` (optional, seeds the fold's streams).
+    Returns the list of test errors (mr_gan.py:230,234), one per job."""
+    folds, rngs = [], []
+    for i, job in enumerate(jobs):
+        rng = np.random.default_rng([int(seed), int(job.get('job_id', i))])
+        folds.append(foldprep.prepare_fold(job.get('X'), job.get('y'), job['percentlabeled'],
+                                           job.get('percentunlabeled'), job.get('trainTestSets'), rng))
+        rngs.append(rng)
+    shapes = [(f.x_train.shape[1], f.x_train.shape[0], f.x_test.shape[0], fold_key(seed, job.get('job_id', i)))
+              for i, (f, job) in enumerate(zip(folds, jobs))]
+    fg = FoldGroup(shapes, model='gan', precision=precision, device=device, batch=batch,
+                   eval_each_epoch=eval_each_epoch, shared_t=shared_t)
+    for i, (f, rng) in enumerate(zip(folds, rngs)):
+        D = f.x_train.shape[1]
+        if verbose:
+            print('Num of class examples in test set:', [int(np.sum(f.y_test == c)) for c in range(len(MATERIALS))])
+            print('X_train:', f.x_train.shape, 'y_train:', f.y_train.shape, 'X_test:', f.x_test.shape, 'y_test:', f.y_test.shape)
+            print('x_labeled:', (len(f.lab_rows), D), 'y_labeled:', (len(f.lab_rows),))
+        fg.set_params(i, 1, init_gen(D, rng))       # generator first, as mr_gan.py:110-114 builds it first
+        fg.set_params(i, 0, init_disc(D, rng))
+        fg.load_fold(i, f.x_train, f.y_train, f.x_test, f.y_test)
+    n_train = shapes[0][1]
+    if verbose:
+        print('Epochs:', epochs)
+        print('Batch size:', batch)
+        print('Training batches per epoch:', n_train // batch)
+        print('Testing batches per epoch:', shapes[0][2] // batch)
+
+    def draw():
+        per = [foldprep.epoch_indices(rng, n_train, f.lab_rows, f.unl_rows) for f, rng in zip(folds, rngs)]
+        return [np.stack([p[s] for p in per]) for s in range(3)]
+
+    nxt = draw()
+    for epoch in range(1, epochs + 1):
+        begin = time.time()
+        fg.train_epoch(*nxt, wait=False)          # one CUDA-graph launch: the whole epoch, all folds
+        if epoch < epochs:
+            nxt = draw()                          # host permutations of the next epoch overlap the GPU
+        st = fg.epoch_result()
+        if verbose:
+            for i in range(len(jobs)):
+                print('Epoch %d, time = %ds, loss labeled = %.4f, loss unlabeled = %.4f, train error = %.4f, test error = %.4f'
+                      % (epoch, time.time() - begin, st[i, 0], st[i, 1], st[i, 2], st[i, 4]))
+            sys.stdout.flush()
+    errors = [float(fg.eval(i)) for i in range(len(jobs))]
+    if verbose:
+        for e in errors:
+            print('Test error:', e)
+        sys.stdout.flush()
+    if return_group:
+        return errors, fg
+    fg.close()
+    return errors
+
+
+def mr_gan(X, y, percentlabeled=50, percentunlabeled=None, epochs=100, trainTestSets=None, verbose=False, *,
+           seed=None, precision='fp32', device=0, batch=50):
+    """mr_gan.py:73-234, one fold.  ``seed=None`` reproduces the reference's 'Non Deterministic output'."""
+    if seed is None:
+        seed = int(np.random.SeedSequence().entropy % (2 ** 63))      # mr_gan.py:74-75
+    job = dict(X=X, y=y, percentlabeled=percentlabeled, percentunlabeled=percentunlabeled, trainTestSets=trainTestSets)
+    return train_gan_folds([job], epochs=epochs, verbose=verbose, seed=seed, precision=precision, device=device,
+                           batch=batch)[0]
+
+
+# ------------------------------------------------------------------ CLI (mr_gan.py:236-341)
+def _kfold_jobs(X, y, seed, **kw):
+    skf = StratifiedKFold(n_splits=6, shuffle=True, random_state=seed)            # mr_gan.py:255
+    return [dict(trainTestSets=[X[tr], X[te], y[tr], y[te]], **kw) for tr, te in skf.split(X, y)]
+
+
+def _loo_jobs(objects, **kw):
+    """mr_gan.py:274-279: one job per held-out object."""
+    jobs = []
+    for name, data in objects.items():
+        Xtr = np.concatenate([d['x'] for n, d in objects.items() if n != name])
+        ytr = np.concatenate([d['y'] for n, d in objects.items() if n != name])
+        jobs.append(dict(trainTestSets=[Xtr, np.asarray(data['x']), ytr, np.asarray(data['y'])], name=name, **kw))
+    return jobs
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(description='Semi-supervised learning with GANs for material recognition on haptic data.')
+    parser.add_argument('-t', '--tables', nargs='+', help='[Required] Tables to recompute', required=True)
+    parser.add_argument('-v', '--verbose', help='Verbose', action='store_true')
+    # additive flags (defaults reproduce the reference's behaviour)
+    parser.add_argument('--seed', type=int, default=None, help='seed for splits, initial weights, permutations and noise')
+    parser.add_argument('--epochs', type=int, default=100)
+    parser.add_argument('--precision', choices=['fp32', 'tf32'], default='fp32')
+    parser.add_argument('--group', type=int, default=12, help='folds trained side by side per GPU launch')
+    parser.add_argument('--data-dir', default='data_processed')
+    args = parser.parse_args(argv)
+    seed = args.seed if args.seed is not None else int(np.random.SeedSequence().entropy % (2 ** 31))
+    rank, world, local = sweep.dist_env()
+    say = print if rank == 0 else (lambda *a, **k: None)
+    jid = [0]
+
+    def run(jobs):
+        for j in jobs:
+            j['job_id'] = jid[0]
+            jid[0] += 1
+        res = sweep.run_sharded(
+            jobs, lambda js, dev: train_gan_folds(js, epochs=args.epochs, verbose=args.verbose, seed=seed,
+                                                  precision=args.precision, device=dev),
+            group_size=args.group, key=lambda j: (len(j['trainTestSets'][0]), len(j['trainTestSets'][1])),
+            cost=lambda j: j['trainTestSets'][0].shape[1])
+        return res
+
+    def report(errors, label='Average error:'):
+        say(label, np.mean(errors), 'Average accuracy:', np.mean(1.0 - np.array(errors)))
+        sys.stdout.flush()
+
+    if '1' in args.tables:                      # mr_gan.py:244-261
+        say('\n', '-' * 25, 'Testing various amounts of labeled training data', '-' * 25)
+        say('-' * 100)
+        for modality in range(len(MODALITIES)):
+            say('-' * 25, MODALITIES[modality], 'modality', '-' * 25)
+            X, y = dataset(modalities=modality, seed=seed, data_dir=args.data_dir)
+            percents = [1, 2, 4, 8, 16, 50, 100]
+            jobs = [j for p in percents for j in _kfold_jobs(X, y, seed + p, percentlabeled=p)]
+            errors = run(jobs)
+            for k, p in enumerate(percents):
+                say('-' * 15, 'Percentage of training data labeled: %d%%' % p, '-' * 15)
+                for e in errors[6 * k:6 * k + 6]:
+                    say('Test error:', e, 'Test accuracy:', 1.0 - e)
+                report(errors[6 * k:6 * k + 6])
+
+    if '3' in args.tables:                      # mr_gan.py:263-283
+        say('\n', '-' * 25, 'Testing generalization with leave-one-object-out validation', '-' * 25)
+        say('-' * 100)
+        for modality in [2, 5]:
+            say('-' * 25, MODALITIES[modality], 'modality', '-' * 25)
+            objects = dataset(modalities=modality, leaveObjectOut=True, seed=seed, data_dir=args.data_dir)
+            percents = [1, 4, 16, 50, 100]
+            jobs = [j for p in percents for j in _loo_jobs(objects, percentlabeled=p)]
+            errors = run(jobs)
+            n = len(objects)
+            for k, p in enumerate(percents):
+                say('-' * 15, 'Percentage of training data labeled: %d%%' % p, '-' * 15)
+                for j, e in zip(jobs[n * k:n * k + n], errors[n * k:n * k + n]):
+                    say(j['name'], 'Test error:', e, 'Test accuracy:', 1.0 - e)
+                report(errors[n * k:n * k + n], 'Average leave-one-object-out error:')
+
+    if '5' in args.tables:                      # mr_gan.py:285-318
+        for header_mods, times, is_contact in (([0, 1, 2], [4, 3, 2, 1, 0.5, 0.2, 0.1], False),
+                                               ([3], [1, 0.7, 0.5, 0.3, 0.2, 0.1, 0.05], True)):
+            say('\n', '-' * 25, 'Testing various lengths of contact time in training data', '-' * 25)
+            say('-' * 100)
+            for modality in header_mods:
+                say('-' * 25, MODALITIES[modality], 'modality', '-' * 25)
+                jobs = []
+                for tm in times:
+                    kw = dict(contactmicTime=tm) if is_contact else dict(forcetempTime=tm)
+                    X, y = dataset(modalities=modality, seed=seed, data_dir=args.data_dir, **kw)
+                    jobs += _kfold_jobs(X, y, seed, percentlabeled=100)
+                errors = run(jobs)
+                for k, tm in enumerate(times):
+                    say('-' * 15, 'Length of training data: %.1fs' % tm, '-' * 15)
+                    for e in errors[6 * k:6 * k + 6]:
+                        say('Test error:', e, 'Test accuracy:', 1.0 - e)
+                    report(errors[6 * k:6 * k + 6])
+
+    if '6' in args.tables:                      # mr_gan.py:320-341
+        say('\n', '-' * 25, 'Testing performance as quantity of unlabeled data increases', '-' * 25)
+        say('-' * 100)
+        for modality in [2, 5]:
+            say('-' * 25, MODALITIES[modality], 'modality', '-' * 25)
+            X, y = dataset(modalities=modality, seed=seed, data_dir=args.data_dir)
+            for percentlabeled in [4]:
+                say('-' * 15, 'Percentage of training data labeled: %d%%' % percentlabeled, '-' * 15)
+                unl = [0, 4, 8, 16, 32, 64, 100 - percentlabeled]
+                jobs = [j for pu in unl for j in _kfold_jobs(X, y, seed + pu, percentlabeled=percentlabeled, percentunlabeled=pu)]
+                errors = run(jobs)
+                for k, pu in enumerate(unl):
+                    say('-' * 15, 'Percentage of training data unlabeled: %d%%' % pu, '-' * 15)
+                    for e in errors[6 * k:6 * k + 6]:
+                        say('Test error:', e, 'Test accuracy:', 1.0 - e)
+                    report(errors[6 * k:6 * k + 6])
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,70 @@
+"""Fold scheduler: runs many independent fold-trainings (the `--tables` sweeps of
+mr_gan.py:244-341 / mr_nn.py:129-168) grouped per GPU and sharded over the GPUs of one box.
+
+Each (modality, labeled %, fold) call of ``mr_gan()`` is independent (fresh models per call,
+mr_gan.py:109-171), so the sweep shards by fold with NO collective: under ``torchrun`` rank r
+takes the job groups r, r+W, r+2W, ... and rank 0 gathers one float per fold through
+``torch.distributed`` (gloo/nccl object gather) and prints in the reference's loop order."""
+import os
+
+import numpy as np
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+def make_groups(jobs, group_size, key=lambda j: 0):
+    """Split jobs (kept in order) into groups of <= group_size whose members share key(job)."""
+    groups, cur, cur_key = [], [], None
+    for i, j in enumerate(jobs):
+        k = key(j)
+        if cur and (k != cur_key or len(cur) >= group_size):
+            groups.append(cur)
+            cur = []
+        cur.append(i)
+        cur_key = k
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+def assign(groups, world, cost=None):
+    """Static longest-first assignment of groups to ranks (cost ~ sum of D)."""
+    order = sorted(range(len(groups)), key=(lambda g: -cost[g]) if cost else (lambda g: g))
+    load = [0.0] * world
+    owner = [0] * len(groups)
+    for g in order:
+        r = int(np.argmin(load))
+        owner[g] = r
+        load[r] += cost[g] if cost else 1.0
+    return owner
+
+
+def run_sharded(jobs, train_group, group_size=6, key=lambda j: 0, cost=lambda j: 1.0, init_dist=True):
+    """Run train_group(list_of_jobs, device) -> list of results over all jobs; returns results in job order
+    on every rank.  One process per GPU; no data-path collective."""
+    rank, world, local = dist_env()
+    groups = make_groups(jobs, group_size, key)
+    owner = assign(groups, world, [sum(cost(jobs[i]) for i in g) for g in groups])
+    mine = {}
+    for g, idxs in enumerate(groups):
+        if owner[g] != rank:
+            continue
+        res = train_group([jobs[i] for i in idxs], local)
+        for i, r in zip(idxs, res):
+            mine[i] = r
+    if world > 1:
+        import torch.distributed as dist
+        if not dist.is_initialized() and init_dist:
+            import torch
+            dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        mine = {}
+        for p in parts:
+            mine.update(p)
+    return [mine[i] for i in range(len(jobs))]

@@ -1,0 +1,237 @@
+"""GPU suite: the CUDA path, called through the C-ABI (ctypes), against the oracle and the
+committed golden vectors.  Tolerances (north_star): per-step losses within 1e-3 relative in
+fp32-accumulate mode; noise stream and Adam elementwise near-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from mr_gan_b200.engine import FoldGroup, MrganError
+from mr_gan_b200 import model
+from oracle import fold_loop, gan_oracle as O, make_golden, philox
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = ["fp32"]
+LOSS_RTOL = {"fp32": 1e-3, "tf32": 1e-3}        # the north_star's tolerance, both modes
+PARAM_TOL = {"fp32": 2e-4, "tf32": 2e-3}        # |dp| relative to lr-sized updates, see _param_close
+
+
+def _key64(key):
+    return (int(key[1]) << 32) | int(key[0])
+
+
+def test_noise_stream_matches_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, "noise_block.npz"))
+    key = tuple(int(k) for k in g['key'])
+    with FoldGroup([(16, 100, 20, _key64(key))]) as fg:
+        blk = fg.fill_normal(0, 9, 2, 10, 7, row0=50)
+        np.testing.assert_allclose(blk, g['block'], rtol=0, atol=2e-6)
+        big = fg.fill_normal(0, 1, 0, 150, 1200)
+        ref = philox.normal(key, 1, 0, 150, 1200)
+        np.testing.assert_allclose(big, ref, rtol=0, atol=3e-6)
+        assert abs(big.mean()) < 0.01 and abs(big.std() - 1) < 0.01
+
+
+def test_flat_adam_matches_oracle(golden_dir):
+    a = np.load(os.path.join(golden_dir, "adam_kat.npz"))
+    with FoldGroup([(16, 100, 20, 1)]) as fg:
+        p, m, v = a['p0'].astype(np.float32), np.zeros(257, np.float32), np.zeros(257, np.float32)
+        for t in (1, 2, 3):
+            p, m, v = fg.adam_flat(p, m, v, (a['g'] * t).astype(np.float32), t)
+        np.testing.assert_allclose(p, a['p3'], rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(m, a['m3'], rtol=2e-6, atol=1e-7)
+        np.testing.assert_allclose(v, a['v3'], rtol=2e-6, atol=1e-9)
+        # large odd-sized buffer: linear in nothing, but idempotent bookkeeping -> compare with numpy fp64
+        rng = np.random.default_rng(0)
+        n = 1_000_003
+        p0, g0 = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+        p1, m1, v1 = fg.adam_flat(p0, np.zeros(n, np.float32), np.zeros(n, np.float32), g0, 1)
+        P, M, V = [p0.astype(np.float64)], [np.zeros(n)], [np.zeros(n)]
+        O.adam_update(P, [g0.astype(np.float64)], M, V, 1, O.GAN_LR, O.GAN_B1, O.GAN_B2, O.GAN_EPS)
+        np.testing.assert_allclose(p1, P[0], rtol=1e-6, atol=1e-7)
+
+
+def _param_close(got, want, init, tol):
+    """Parameters move by ~lr per step; compare the UPDATE, relative to its own scale."""
+    for g, w, i in zip(got, want, init):
+        upd = np.abs(w - i).max() + 1e-12
+        assert np.abs(g - w).max() <= tol * max(upd, 1e-3), (np.abs(g - w).max(), upd)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("name", ["gan_steps_D36", "gan_steps_D30_B8", "gan_steps_D1200"])
+def test_step_api_against_golden_vectors(golden_dir, name, precision):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    D, B, n_pairs = int(g['D']), int(g['B']), int(g['n_pairs'])
+    key = tuple(int(k) for k in g['key'])
+    pD, pG, steps = make_golden.case_inputs(D, B, int(g['seed']), n_pairs)
+    with FoldGroup([(D, max(B, 60), 12, _key64(key))], precision=precision, batch=B) as fg:
+        fg.set_params(0, 0, pD)
+        fg.set_params(0, 1, pG)
+        # round trip of the parameter layout (reference order <-> augmented/padded device layout)
+        for a, b in zip(fg.get_params(0, 0) + fg.get_params(0, 1), pD + pG):
+            np.testing.assert_array_equal(a, b)
+        for i, s in enumerate(steps):
+            ll, lu, te = fg.train_batch_disc(0, s['x_lab'], s['labels'], s['x_unl'], s['z_d'])
+            lg = fg.train_batch_gen(0, s['x_unl2'], s['z_g'])
+            want = g['losses'][i]
+            np.testing.assert_allclose([ll, lu, lg], want[[0, 1, 3]], rtol=LOSS_RTOL[precision])
+            assert abs(te - want[2]) < 1e-6
+        assert fg.counters(0) == (2 * n_pairs, 2 * n_pairs)
+        fD = np.concatenate([p.ravel() for p in fg.get_params(0, 0)])
+        fG = np.concatenate([p.ravel() for p in fg.get_params(0, 1)])
+        iD = np.concatenate([p.ravel() for p in pD])
+        iG = np.concatenate([p.ravel() for p in pG])
+        _param_close([fD[g['idxD']]], [g['pD_final']], [iD[g['idxD']]], PARAM_TOL[precision])
+        _param_close([fG[g['idxG']]], [g['pG_final']], [iG[g['idxG']]], PARAM_TOL[precision])
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_step_api_full_state_against_live_oracle(precision):
+    """Every parameter tensor and both Adam slots after 2 step pairs, plus test_batch; odd sizes (B=25 -> 2B % 4 != 0)."""
+    D, B = 44, 25
+    key = philox.fold_key(3, 1)
+    pD, pG, steps = make_golden.case_inputs(D, B, 21, 2)
+    m = O.GanOracle(pD, pG)
+    rng = np.random.default_rng(4)
+    xt, yt = rng.standard_normal((37, D)).astype(np.float32), rng.integers(0, 6, 37).astype(np.int32)
+    with FoldGroup([(D, 100, 40, _key64(key))], precision=precision, batch=B) as fg:
+        fg.set_params(0, 0, pD)
+        fg.set_params(0, 1, pG)
+        for i, s in enumerate(steps):
+            got = fg.train_batch_disc(0, s['x_lab'], s['labels'], s['x_unl'], s['z_d'])
+            want = m.disc_step(s['x_lab'], s['labels'], s['x_unl'], s['z_d'], fold_loop.d_noise(key, 2 * i, B, D, 0),
+                               fold_loop.d_noise(key, 2 * i, B, D, B), fold_loop.d_noise(key, 2 * i, B, D, 2 * B))
+            np.testing.assert_allclose(got, want, rtol=LOSS_RTOL[precision], atol=1e-6)
+            got = fg.train_batch_gen(0, s['x_unl2'], s['z_g'])
+            want = m.gen_step(s['x_unl2'], s['z_g'], fold_loop.d_noise(key, 2 * i + 1, B, D, 0),
+                              fold_loop.d_noise(key, 2 * i + 1, B, D, B))
+            np.testing.assert_allclose(got, want, rtol=LOSS_RTOL[precision])
+        _param_close(fg.get_params(0, 0), m.pD, pD, PARAM_TOL[precision])
+        _param_close(fg.get_params(0, 1), m.pG, pG, PARAM_TOL[precision])
+        mD, vD = fg.get_adam(0, 0)
+        for a, b in zip(mD, m.mD):
+            np.testing.assert_allclose(a, b, rtol=0, atol=PARAM_TOL[precision] * max(np.abs(b).max(), 1e-6) * 5)
+        assert abs(fg.test_batch(0, xt, yt) - m.test_batch(xt, yt)) < 1e-6
+        assert abs(fg.test_batch(0, xt[:1], yt[:1]) - m.test_batch(xt[:1], yt[:1])) < 1e-6      # ragged: 1 row
+
+
+def _make_fold(D, n_train, n_test, seed, pl=1.0):
+    rng = np.random.default_rng(seed)
+    y = np.tile(np.arange(6), (n_train + n_test + 5) // 6)[:n_train + n_test]
+    cls = rng.standard_normal((6, D))
+    X = cls[y] + 1.5 * rng.standard_normal((len(y), D))
+    Xtr, Xte, ytr, yte, lab_rows, _ = fold_loop.prep_fold(X[:n_train], X[n_train:], y[:n_train], y[n_train:], pl, None, rng)
+    pD = [p.astype(np.float32) for p in O.init_disc_params(D, rng)]
+    pG = [p.astype(np.float32) for p in O.init_gen_params(D, rng)]
+    return dict(Xtr=Xtr.astype(np.float32), Xte=Xte.astype(np.float32), ytr=ytr.astype(np.int32), yte=yte.astype(np.int32),
+                lab_rows=lab_rows, pD=pD, pG=pG, rng=rng)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_epoch_graph_against_oracle_loop_heterogeneous_group(precision):
+    """Two folds with DIFFERENT input widths trained side by side for 2 epochs == the oracle's
+    restatement of mr_gan.py:183-223 run fold by fold, and == each fold trained alone (bitwise)."""
+    B, ntr, nte = 10, 60, 25
+    Ds, seeds = (24, 52), (100, 101)
+    folds = [_make_fold(D, ntr, nte, s) for D, s in zip(Ds, seeds)]
+    keys = [philox.fold_key(9, i) for i in range(2)]
+    idx = [[fold_loop.epoch_indices(f['rng'], ntr, f['lab_rows']) for f in folds] for _ in range(2)]
+
+    def run(group):
+        with FoldGroup([(Ds[i], ntr, nte, _key64(keys[i])) for i in group], precision=precision, batch=B) as fg:
+            for j, i in enumerate(group):
+                fg.set_params(j, 0, folds[i]['pD'])
+                fg.set_params(j, 1, folds[i]['pG'])
+                fg.load_fold(j, folds[i]['Xtr'], folds[i]['ytr'], folds[i]['Xte'], folds[i]['yte'])
+            stats = [fg.train_epoch(*[np.stack([idx[e][i][s] for i in group]) for s in range(3)]) for e in range(2)]
+            return stats, [fg.eval(j) for j in range(len(group))], [fg.get_params(j, 0) for j in range(len(group))], fg.kernel_launches
+
+    stats, errs, params, launches = run([0, 1])
+    assert launches > 2 * (ntr // B) * 40
+    for i in range(2):
+        m = O.GanOracle(folds[i]['pD'], folds[i]['pG'])
+        step = 0
+        for e in range(2):
+            st, step = fold_loop.train_epoch(m, folds[i]['Xtr'].astype(np.float64), folds[i]['ytr'], *idx[e][i], keys[i], step, B=B)
+            np.testing.assert_allclose(stats[e][i, [0, 1, 3]], st.mean(axis=0)[[0, 1, 3]], rtol=LOSS_RTOL[precision])
+            assert abs(stats[e][i, 2] - st.mean(axis=0)[2]) < 1e-5
+            assert abs(stats[e][i, 4] - fold_loop.eval_batches(m, folds[i]['Xte'].astype(np.float64), folds[i]['yte'], B=B)) < 1e-5
+        assert abs(errs[i] - m.test_batch(folds[i]['Xte'].astype(np.float64), folds[i]['yte'])) < 1e-6
+        _param_close(params[i], m.pD, folds[i]['pD'], PARAM_TOL[precision] * 10)
+        # grouping does not change a fold's result: folds are independent
+        s1, e1, p1, _ = run([i])
+        for e in range(2):
+            np.testing.assert_array_equal(s1[e][0], stats[e][i])
+        assert e1[0] == errs[i]
+        for a, b in zip(p1[0], params[i]):
+            np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_mr_nn_step_and_epoch_against_oracle(precision):
+    D, B = 40, 20
+    key = philox.fold_key(2, 0)
+    f = _make_fold(D, 120, 30, 7, pl=2.0)         # 20 labeled rows per class -> 120 labeled
+    m = O.NnOracle(f['pD'])
+    with FoldGroup([(D, 120, 30, _key64(key))], model="nn", precision=precision) as fg:
+        fg.set_params(0, 0, f['pD'])
+        fg.load_fold(0, f['Xtr'], f['ytr'], f['Xte'], f['yte'])
+        for step, n in enumerate((20, 7)):           # a full and a ragged batch (Keras keeps the last partial batch)
+            x, y = f['Xtr'][:n], f['ytr'][:n]
+            got = fg.nn_step(0, x, y)
+            want = m.step(x.astype(np.float64), y, fold_loop.d_noise(key, step, n, D, 0))
+            np.testing.assert_allclose(got, want, rtol=LOSS_RTOL[precision], atol=1e-6)
+        idx = f['lab_rows'][f['rng'].permutation(len(f['lab_rows']))].astype(np.int32)
+        got = fg.nn_train_epoch(idx[None, :])
+        want = []
+        for t in range(len(idx) // B):
+            rows = idx[t * B:(t + 1) * B]
+            want.append(m.step(f['Xtr'][rows].astype(np.float64), f['ytr'][rows], fold_loop.d_noise(key, 2 + t, B, D, 0)))
+        np.testing.assert_allclose(got[0], np.mean(want, axis=0), rtol=LOSS_RTOL[precision], atol=1e-6)
+        loss, acc = fg.nn_evaluate(0)
+        wl, wa = m.evaluate(f['Xte'].astype(np.float64), f['yte'])
+        assert abs(acc - wa) < 1e-6 and abs(loss - wl) <= LOSS_RTOL[precision] * wl
+        _param_close(fg.get_params(0, 0), m.pD, f['pD'], PARAM_TOL[precision] * 10)
+
+
+def test_error_behaviour_mirrors_reference_shape_checks():
+    with FoldGroup([(16, 100, 20, 1)]) as fg:
+        with pytest.raises(ValueError):
+            fg.train_batch_disc(0, np.zeros((49, 16)), np.zeros(49), np.zeros((49, 16)), np.zeros((49, 100)))   # B != 50, mr_gan.py:146
+        with pytest.raises(MrganError, match="label out of range"):
+            fg.train_batch_disc(0, np.zeros((50, 16)), np.full(50, 6), np.zeros((50, 16)), np.zeros((50, 100)))
+        with pytest.raises(MrganError, match="before mrgan_load_fold"):
+            fg.train_epoch(*[np.zeros((1, 100), np.int32)] * 3)
+        with pytest.raises(MrganError, match="fold index"):
+            fg.eval(3)
+    with pytest.raises(MrganError, match="same n_train"):
+        FoldGroup([(16, 100, 20, 1), (16, 150, 20, 2)])
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_full_size_properties_D1200(precision):
+    """BASELINE full size (D=1200, B=50, 6000/1200 rows), properties that need no oracle run:
+    determinism, independence from grouping, finite decreasing supervised loss, counters."""
+    D, ntr, nte, B = 1200, 6000, 1200, 50
+    f = _make_fold(D, ntr, nte, 5, pl=100)
+    idx = fold_loop.epoch_indices(f['rng'], ntr, f['lab_rows'])
+    key = _key64(philox.fold_key(1, 0))
+
+    def run(nfolds):
+        with FoldGroup([(D, ntr, nte, key)] * nfolds, precision=precision) as fg:
+            for j in range(nfolds):
+                fg.set_params(j, 0, f['pD'])
+                fg.set_params(j, 1, f['pG'])
+                fg.load_fold(j, f['Xtr'], f['ytr'], f['Xte'], f['yte'])
+            st = fg.train_epoch(*[np.stack([a] * nfolds) for a in idx])
+            return st, [fg.eval(j) for j in range(nfolds)], fg.counters(0)
+
+    st2, e2, cnt = run(2)
+    st1, e1, _ = run(1)
+    assert cnt == (240, 240)                                   # 120 D steps + 120 G steps, shared counter
+    np.testing.assert_array_equal(st2[0], st2[1])              # same seed -> identical folds
+    np.testing.assert_array_equal(st2[0], st1[0])              # grouping-independent, run-to-run deterministic
+    assert e2[0] == e2[1] == e1[0]
+    assert np.isfinite(st1).all() and st1[0, 0] < 1.5 and st1[0, 2] < 0.5 and e1[0] < 0.4   # it learns

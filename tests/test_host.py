@@ -1,0 +1,143 @@
+"""CPU suite, part 2: host logic (fold prep, permutations, synthetic shapes, scheduler, CLI) and
+the C-ABI library surface (loads, exports every declared symbol, fails loudly without a GPU)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from mr_gan_b200 import _lib, foldprep, model, mr_gan as mg, mr_nn as mn, sweep, synthetic
+from oracle import fold_loop, philox
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_fold_prep_matches_oracle_restatement():
+    X, y = synthetic.synthetic_dataset(1, forcetempTime=0.2, pokes=4, seed=3)      # [288, 20]
+    tr, te = np.arange(0, 288, 1)[::2], np.arange(1, 288, 2)
+    for pl, pu in ((0.2, None), (0.1, 0.1)):
+        f = foldprep.prepare_fold(None, None, pl, pu, [X[tr], X[te], y[tr], y[te]], np.random.default_rng(9))
+        o = fold_loop.prep_fold(X[tr], X[te], y[tr], y[te], pl, pu, np.random.default_rng(9))
+        np.testing.assert_allclose(f.x_train, o[0], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(f.x_test, o[1], rtol=1e-5, atol=1e-6)
+        np.testing.assert_array_equal(f.y_train, o[2])
+        np.testing.assert_array_equal(f.lab_rows, o[4])
+        if pu is None:
+            assert f.unl_rows is None
+        else:
+            np.testing.assert_array_equal(f.unl_rows, o[5])
+        # labeled subset: first 10*percent rows per class, class-major (mr_gan.py:102-103)
+        n = int(10 * pl)
+        assert list(f.y_train[f.lab_rows]) == [j for j in range(6) for _ in range(n)]
+        assert abs(f.x_train.mean()) < 1e-5 and abs(f.x_train.std() - 1) < 1e-3
+
+
+def test_epoch_indices_match_oracle_and_reference_structure():
+    lab_rows = np.array([3, 5, 7, 11, 13])
+    a = foldprep.epoch_indices(np.random.default_rng(1), 23, lab_rows)
+    b = fold_loop.epoch_indices(np.random.default_rng(1), 23, lab_rows)
+    for u, v in zip(a, b):
+        np.testing.assert_array_equal(u, v)
+        assert u.dtype == np.int32 and u.shape == (23,)
+    # mr_gan.py:189: 4 full permutations of the 5 labeled rows then a permutation of the first 3
+    for k in range(4):
+        assert sorted(a[0][5 * k:5 * k + 5]) == sorted(lab_rows)
+    assert sorted(a[0][20:]) == sorted(lab_rows[:3])
+    assert sorted(a[1]) == list(range(23)) and sorted(a[2]) == list(range(23)) and not (a[1] == a[2]).all()
+    # table-6 path (mr_gan.py:197-200): streams drawn from the unlabeled subset only
+    unl = np.array([0, 1, 2, 3, 4, 5, 6, 7])
+    c = foldprep.epoch_indices(np.random.default_rng(2), 23, lab_rows, unl)
+    assert set(c[1]) <= set(unl) and set(c[2]) <= set(unl)
+
+
+def test_synthetic_shapes_follow_reference_feature_layout():
+    assert [synthetic.feature_width(m) for m in range(7)] == [800, 400, 1200, 2432, 2832, 3632, 3232]
+    assert [synthetic.feature_width(3, contactmicTime=c) for c in (1, 0.7, 0.5, 0.3, 0.2, 0.1, 0.05)] == \
+        [12032, 8448, 6016, 3712, 2432, 1280, 640]
+    assert [synthetic.feature_width(2, forcetempTime=t) for t in (4, 3, 2, 1, 0.5, 0.2, 0.1)] == \
+        [1200, 900, 600, 300, 150, 60, 30]
+    X, y = synthetic.synthetic_dataset(1, pokes=5, seed=0)
+    assert X.shape == (360, 400) and list(np.bincount(y)) == [60] * 6
+    X2, _ = synthetic.synthetic_dataset(1, pokes=5, seed=0)
+    np.testing.assert_array_equal(X, X2)
+    objs = synthetic.synthetic_dataset(1, pokes=5, seed=0, leaveObjectOut=True)
+    assert len(objs) == 72 and all(o['x'].shape == (5, 400) for o in objs.values())
+
+
+def test_model_shapes_and_parameter_counts():
+    for D in (10, 400, 1200, 3632):
+        assert sum(int(np.prod(s)) for s in model.disc_shapes(D)) == 1000 * D + 753756
+        assert sum(int(np.prod(s)) for s in model.gen_shapes(D)) == 501 * D + 302000
+    p = model.init_gen(30, np.random.default_rng(0))
+    assert (p[2] == 1).all() and (p[3] == 0).all() and (p[1] == 0).all()
+    w = model.init_disc(30, np.random.default_rng(0))[0]
+    assert np.abs(w).max() <= np.sqrt(6.0 / (30 + 1000)) and w.dtype == np.float32
+    lo, hi = philox.fold_key(77, 5)
+    assert model.fold_key(77, 5) == (hi << 32) | lo
+
+
+def test_sweep_grouping_and_assignment():
+    jobs = [dict(n=6000, D=d) for d in (800, 800, 400, 1200, 1200, 1200, 1200)] + [dict(n=7100, D=800)]
+    groups = sweep.make_groups(jobs, 3, key=lambda j: j['n'])
+    assert groups == [[0, 1, 2], [3, 4, 5], [6], [7]]
+    owner = sweep.assign(groups, 2, [sum(jobs[i]['D'] for i in g) for g in groups])
+    loads = [sum(sum(jobs[i]['D'] for i in g) for g, o in zip(groups, owner) if o == r) for r in (0, 1)]
+    assert max(loads) <= 4000 and sorted(set(owner)) == [0, 1]
+    res = sweep.run_sharded(jobs, lambda js, dev: [j['D'] * 2 for j in js], group_size=3, key=lambda j: j['n'])
+    assert res == [2 * j['D'] for j in jobs]
+
+
+def test_cli_surface_matches_reference_flags():
+    for mod in (mg, mn):
+        with pytest.raises(SystemExit):
+            mod.main([])                                       # --tables is required (mr_gan.py:240)
+    assert mg.MODALITIES[5] == 'Force, Temperature, and Contact Mic'
+    jobs = mg._kfold_jobs(*synthetic.synthetic_dataset(1, forcetempTime=0.1, pokes=2, seed=0), 0, percentlabeled=1)
+    assert len(jobs) == 6 and jobs[0]['trainTestSets'][0].shape == (120, 10)
+    loo = mg._loo_jobs(synthetic.synthetic_dataset(1, forcetempTime=0.1, pokes=2, seed=0, leaveObjectOut=True), percentlabeled=1)
+    assert len(loo) == 72 and loo[0]['trainTestSets'][0].shape == (142, 10) and loo[0]['trainTestSets'][1].shape == (2, 10)
+
+
+# ------------------------------------------------------------------ C-ABI surface (no compute)
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "mrgan.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mr(?:gan|nn)_[a-z_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    assert sorted(_lib.SYMBOLS) == declared            # the ctypes table and the header agree
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.mrgan_version()
+    cfg = _lib.Config()
+    assert lib.mrgan_default_config(0, C.byref(cfg)) == 0
+    assert (cfg.batch, cfg.n_classes, cfg.noise_dim, cfg.shared_t) == (50, 6, 100, 1)       # mr_gan.py:77-80
+    assert np.isclose(cfg.lr, 6e-4) and np.isclose(cfg.beta1, 0.5) and np.isclose(cfg.bn_eps, 2e-5)
+    assert lib.mrgan_default_config(1, C.byref(cfg)) == 0
+    assert cfg.batch == 20 and np.isclose(cfg.lr, 1e-3) and np.isclose(cfg.beta1, 0.9)      # mr_nn.py:114,117
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mr_gan_b200.engine import FoldGroup, MrganError
+    with pytest.raises(MrganError, match="no CPU fallback"):
+        FoldGroup([(16, 100, 20, 1)])
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mr_gan_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+    code = "import sys; import mr_gan_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
