@@ -136,6 +136,12 @@ int  mrgan_fill_normal(mrgan_handle* h, int fold, int step, int tensor_id, int r
                        int row0, float* dst /* host [rows, cols] */);
 int  mrgan_adam_flat(mrgan_handle* h, float* p, float* m, float* v, const float* g, int64_t n,
                      int t /* 1-based */);              /* host buffers; fused flat Adam, SURVEY a8 */
+/* Average device time (CUDA events on the handle's stream) of `reps` back-to-back launches of one
+ * kernel of the step over ALL folds of the handle -- the live roofline probe bench.py uses.
+ * Mutates the training state (run it after the measured region). */
+enum { MRGAN_TIME_ADAM_D = 0, MRGAN_TIME_ADAM_G = 1, MRGAN_TIME_DW1 = 2, MRGAN_TIME_FWD1 = 3,
+       MRGAN_TIME_DISC_STEP = 4, MRGAN_TIME_GEN_STEP = 5 };
+int  mrgan_time_op(mrgan_handle* h, int which, int reps, float* ms_avg);
 int64_t mrgan_kernel_launches(const mrgan_handle* h); /* kernels launched so far (graph nodes count per replay) */
 double  mrgan_last_device_ms(const mrgan_handle* h);  /* CUDA-event time of the last train_epoch */
 const char* mrgan_version(void);

@@ -996,6 +996,39 @@ int mrgan_adam_flat(mrgan_handle* h, float* p, float* m, float* v, const float* 
   return MRGAN_OK;
 }
 
+int mrgan_time_op(mrgan_handle* h, int which, int reps, float* ms_avg) {
+  if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
+  if (!ms_avg || reps < 1) return fail(h, MRGAN_ERR_ARG, "time_op: bad argument");
+  const bool gan = h->cfg.model == MRGAN_MODEL_GAN;
+  if (!gan && (which == MRGAN_TIME_ADAM_G || which == MRGAN_TIME_GEN_STEP)) return fail(h, MRGAN_ERR_STATE, "time_op: no generator in this model");
+  for (int f = 0; f < h->nf; ++f)
+    if (!h->fb[f].loaded) return fail(h, MRGAN_ERR_STATE, "time_op before mrgan_load_fold");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = finish_pending(h); if (rc) return rc;
+  auto once = [&]() {
+    switch (which) {
+      case MRGAN_TIME_ADAM_D: launch_adam(h, 0, h->nf, 0); break;
+      case MRGAN_TIME_ADAM_G: launch_adam(h, 0, h->nf, 1); break;
+      case MRGAN_TIME_DW1: launch_gemm(h, OP_DW1, 0, h->nf, 0); break;
+      case MRGAN_TIME_FWD1: launch_gemm(h, OP_D1, 0, h->nf, 0); break;
+      case MRGAN_TIME_DISC_STEP: if (gan) enqueue_disc_step(h, 0, h->nf, 0, 0); else enqueue_nn_step(h, 0, h->nf, 0, 0, h->cfg.batch); break;
+      case MRGAN_TIME_GEN_STEP: enqueue_gen_step(h, 0, h->nf, 0, 0); break;
+      default: break;
+    }
+  };
+  if (which < 0 || which > MRGAN_TIME_GEN_STEP) return fail(h, MRGAN_ERR_ARG, "time_op: unknown op");
+  once();                                   // warm-up
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (int i = 0; i < reps; ++i) once();
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  *ms_avg = ms / reps;
+  return MRGAN_OK;
+}
+
 int64_t mrgan_kernel_launches(const mrgan_handle* h) { return h ? h->launches : -1; }
 double mrgan_last_device_ms(const mrgan_handle* h) { return h ? h->last_ms : -1.0; }
 

@@ -233,6 +233,14 @@ class FoldGroup:
         self._chk(self.lib.mrgan_adam_flat(self._h, _lib.fptr(p), _lib.fptr(m), _lib.fptr(v), _lib.fptr(g), p.size, t))
         return p, m, v
 
+    TIME_OPS = {"adam_d": 0, "adam_g": 1, "dw1": 2, "fwd1": 3, "disc_step": 4, "gen_step": 5}
+
+    def time_op(self, which, reps=20):
+        """Average device ms of one kernel (or one whole step) over all folds; mutates training state."""
+        out = np.zeros(1, dtype=np.float32)
+        self._chk(self.lib.mrgan_time_op(self._h, self.TIME_OPS[which], reps, _lib.fptr(out)))
+        return float(out[0])
+
     @property
     def kernel_launches(self):
         return int(self.lib.mrgan_kernel_launches(self._h))

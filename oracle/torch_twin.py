@@ -106,7 +106,7 @@ class TorchGan:
         ll, lu, err = self.disc_loss(*a, **k)
         grads = torch.autograd.grad(ll + O.UNLABELED_WEIGHT * lu, self.pD)
         self.adamD.apply(list(grads), self._t('D'))
-        return float(ll), float(lu), float(err)
+        return float(ll.detach()), float(lu.detach()), float(err)
 
     def gen_loss(self, x_unl, z, n_fake=None, n_real=None):
         x_unl, z = self._cv(x_unl), self._cv(z)
@@ -121,7 +121,7 @@ class TorchGan:
         loss = self.gen_loss(*a, **k)
         grads = torch.autograd.grad(loss, self.pG)
         self.adamG.apply(list(grads), self._t('G'))
-        return float(loss)
+        return float(loss.detach())
 
     @torch.no_grad()
     def test_batch(self, x, y):
@@ -149,4 +149,4 @@ class TorchNn:
         grads = torch.autograd.grad(loss, self.pD)
         self.iterations += 1
         self.adam.apply(list(grads), self.iterations)
-        return float(loss), float((logits.argmax(dim=1) == labels).double().mean())
+        return float(loss.detach()), float((logits.argmax(dim=1) == labels).double().mean())
