@@ -142,6 +142,15 @@ int  mrgan_adam_flat(mrgan_handle* h, float* p, float* m, float* v, const float*
 enum { MRGAN_TIME_ADAM_D = 0, MRGAN_TIME_ADAM_G = 1, MRGAN_TIME_DW1 = 2, MRGAN_TIME_FWD1 = 3,
        MRGAN_TIME_DISC_STEP = 4, MRGAN_TIME_GEN_STEP = 5 };
 int  mrgan_time_op(mrgan_handle* h, int which, int reps, float* ms_avg);
+/* Debug/test hook: copy an intermediate buffer of the last step of one fold to the host
+ * (dst is [rows, cols] dense).  which: 0..5 = noisy layer inputs a[l], 10+l = post-ReLU h[l],
+ * 20+l = dZ[l], 30 = logits, 31 = dlogits, 32 = dFake, 40 = z, 41 = G h1, 42 = G BN out,
+ * 43 = G h2, 44 = G dZ2, 45 = G dU, 46 = G dZ1. */
+int  mrgan_debug_buffer(mrgan_handle* h, int fold, int which, float* dst, int rows, int cols);
+/* Test hook: one stand-alone GEMM through the step's kernels (use_tc = 1: tcgen05 path, 0: fp32 path).
+ * mode 0: C[M,N] = A[M,K] B[K,N]   mode 1: C[M,N] = A[M,K] B[N,K]^T   mode 2: C[M,N] = A[K,M]^T B[K,N]
+ * Dense row-major host arrays. */
+int  mrgan_debug_gemm(mrgan_handle* h, int mode, int M, int N, int K, const float* A, const float* B, float* C, int use_tc);
 int64_t mrgan_kernel_launches(const mrgan_handle* h); /* kernels launched so far (graph nodes count per replay) */
 double  mrgan_last_device_ms(const mrgan_handle* h);  /* CUDA-event time of the last train_epoch */
 const char* mrgan_version(void);

@@ -330,10 +330,12 @@ k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fol
 // mr_nn.py:114 loss='mse' vs one-hot, metrics=['accuracy'].
 __global__ void __launch_bounds__(256)
 k_loss_mse(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total,
-           int t, int n, int K) {
+           int t, int n, int rows_total, int K) {
   __shared__ float sh[32];
   const LossDesc d = descs[blockIdx.z];
   float s_loss = 0.f, s_acc = 0.f;
+  for (int r = n + threadIdx.x; r < rows_total; r += blockDim.x)     // ragged batch: no gradient from the unused rows
+    for (int k = 0; k < K; ++k) d.dlogits[(size_t)r * d.ld + k] = 0.f;
   for (int r = threadIdx.x; r < n; r += blockDim.x) {
     const float* l = d.logits + (size_t)r * d.ld;
     float* dl = d.dlogits + (size_t)r * d.ld;

@@ -1,0 +1,292 @@
+// kernels_tc.cuh -- tcgen05 / TMEM / TMA grouped GEMM of the training step (precision = tf32).
+//
+// One warp-specialised kernel serves all dense contractions of the step, grouped over folds
+// (blockIdx.z) with per-(op, fold) TMA descriptors resident in HBM:
+//
+//   role            MMA-A (M = 128 "feature" rows)          MMA-B (N = bn columns)            accumulator
+//   forward         W^T  from Waug[k, n]  (MN-major)        act  from A[r, k]   (K-major)     D[n, r]
+//   backward dX     W    from Waug[k, n]  (K-major)         dZ   from dZ[r, n]  (K-major)     D[k, r]
+//   backward dW     dZ^T from dZ[r, n]    (MN-major)        A^T  from A[r, k]   (MN-major)    D[n, k]
+//
+// i.e. the weight-side dimension always sits on the 128 TMEM lanes ("swap-AB": the batch is only
+// 50..150 rows, mr_gan.py:78) and fp32 master weights feed kind::tf32 MMAs directly -- no low
+// precision shadow copy, no transposed copy (both operand majors are legal for tf32 descriptors).
+// The lane <-> memory-contiguous-dimension match makes every epilogue access coalesced:
+// thread = one feature, registers = rows (forward / dX) or input features (dW).
+//
+// Pipeline: warp 0 = TMA producer (4-stage mbarrier ring, 32 contraction elements per stage),
+// warp 1 = TMEM allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue
+// (tcgen05.ld 32x32b -> bias-free activation + Philox GaussianNoise | act' mask | fused Adam).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+enum { EPI_ADAM = 3 };
+
+struct alignas(64) TcOp {
+  CUtensorMap mapA, mapB;
+  GemmDesc g;                 // epilogue description shared with the fp32 path (C, C2, aux, act, noise ...)
+  float *P, *Mo, *Vo;         // fused Adam (EPI_ADAM): tensor base inside the flat buffers
+  int ME, NE, KE;             // extents: MMA-M (features), MMA-N, contraction
+  int bn;                     // MMA-N per tile (multiple of 16, <= 256; multiple of 32 when B is MN-major)
+  int epi;                    // EPI_FWD / EPI_DX / EPI_STORE / EPI_ADAM
+  int pad_[3];
+};
+
+#define TC_STAGES 4
+#define TC_KBLK 32            // contraction elements per stage (one 128-byte swizzle row of fp32)
+#define TC_SPIN_LIMIT (1ll << 31)   // cycles; a stuck barrier traps instead of hanging the GPU
+
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > TC_SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_map(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// shared-memory matrix descriptor (version 1).  lbo/sbo in bytes.
+//   K-major operand : layout 2 = SWIZZLE_128B (16-byte chunks XOR row&7; TMA SWIZZLE_128B), sbo = 8 rows = 1024 B
+//   MN-major operand: 32-bit types only support layout 1 = SWIZZLE_128B_BASE32B (32-byte chunks XOR k-row&3;
+//                     TMA SWIZZLE_128B_ATOM_32B): 4 k-rows of 128 B per atom -> sbo = 512 B, lbo = next 32-element MN block
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+}  // namespace tc
+
+// A_MN / B_MN: operand is MN-major (its MMA M/N dimension is the memory-contiguous one).
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192, 1)
+k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_override, AdamHyper hp) {
+  using namespace tc;
+  const TcOp& op = ops[blockIdx.z];
+  const int ME = op.ME, KE = op.KE, bn = op.bn;
+  int NE = op.NE;
+  if (rows_override > 0 && !B_MN) NE = rows_override;      // fewer batch rows (G step)
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * bn;
+  if (m0 >= ME || n0 >= NE) return;                         // uniform per CTA: nothing allocated yet
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)bn * 128, stage_bytes = a_bytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * stage_bytes);
+  uint64_t* full = bars;                    // [TC_STAGES]
+  uint64_t* empty = bars + TC_STAGES;       // [TC_STAGES]
+  uint64_t* tmem_full = bars + 2 * TC_STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (KE + TC_KBLK - 1) / TC_KBLK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_map(&op.mapA);
+    prefetch_map(&op.mapB);
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: 256 fp32 columns x 128 lanes for the accumulator tile
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_expect_tx(&full[s], stage_bytes);
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        const int k0 = kb * TC_KBLK;
+        if (A_MN) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * 4096, m0 + 32 * b, k0);
+        } else {
+          tma_load_2d(&op.mapA, &full[s], sa, k0, m0);
+        }
+        if (B_MN) {
+          for (int b = 0; b < bn / 32; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * 4096, n0 + 32 * b, k0);
+        } else {
+          tma_load_2d(&op.mapB, &full[s], sb, k0, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t lboA = A_MN ? 4096u : 16u, lboB = B_MN ? 4096u : 16u;
+      const uint32_t sboA = A_MN ? 512u : 1024u, sboB = B_MN ? 512u : 1024u;
+      const uint32_t layA = A_MN ? 1u : 2u, layB = B_MN ? 1u : 2u;
+      const uint32_t stepA = A_MN ? 1024u : 32u, stepB = B_MN ? 1024u : 32u;   // bytes per 8 contraction elements
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
+#pragma unroll
+        for (int k = 0; k < TC_KBLK / 8; ++k) {
+          const uint64_t da = smem_desc(sa + k * stepA, lboA, sboA, layA);
+          const uint64_t db = smem_desc(sb + k * stepB, lboB, sboB, layB);
+          mma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
+      }
+      mma_commit(tmem_full);              // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+    const int lane_base = 32 * (warp & 3);
+    const int f = m0 + lane_base + lane;                  // this thread's feature index (MMA-M)
+    const bool f_ok = f < ME;
+    mbar_wait(tmem_full, 0);
+    fence_after();
+    const GemmDesc& g = op.g;
+    const int epi = op.epi;
+    const int ncols = min(bn, NE - n0);
+    const uint32_t trow = tmem_base + ((uint32_t)lane_base << 16);
+    uint32_t key0 = 0, key1 = 0, step = 0;
+    float lr_t = 0.f;
+    const bool noisy = (epi == EPI_FWD) && g.C2 != nullptr && g.sigma != 0.f;
+    if (noisy || epi == EPI_ADAM) {
+      const FoldState& fs = folds[g.fold];
+      key0 = fs.key0; key1 = fs.key1; step = (uint32_t)fs.rng_step; lr_t = fs.lr_t;
+    }
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+      float v[16];
+      tmem_ld16(trow + (uint32_t)c0, v);                   // warp-collective: every lane takes part
+      if (!f_ok) continue;
+      if (epi == EPI_FWD) {
+        // rows r = n0 + c0 + j; noise is grouped by 4 consecutive rows of one column (= this feature)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r0 = n0 + c0 + 4 * q;
+          if (r0 >= NE) break;
+          float nz[4] = {0.f, 0.f, 0.f, 0.f};
+          if (noisy) {
+            if (((g.row0 + r0) & 3) == 0) normal4(key0, key1, (uint32_t)(g.row0 + r0) >> 2, (uint32_t)f, step, (uint32_t)g.tid, nz);
+            else for (int i = 0; i < 4; ++i) nz[i] = normal1(key0, key1, (uint32_t)(g.row0 + r0 + i), (uint32_t)f, step, (uint32_t)g.tid);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = r0 + i;
+            if (r >= NE) break;
+            float x = v[4 * q + i];
+            if (g.act == ACT_RELU) x = fmaxf(x, 0.f);
+            else if (g.act == ACT_SOFTPLUS) x = softplusf(x);
+            if (g.C) g.C[(size_t)r * g.ldc + f] = x;
+            if (g.C2) g.C2[(size_t)r * g.ldc2 + f] = x + g.sigma * nz[i];
+          }
+        }
+      } else if (epi == EPI_DX) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int r = n0 + c0 + j;
+          if (r >= NE) break;
+          float x = v[j];
+          if (g.act == ACT_RELU) x = (g.aux[(size_t)r * g.ldaux + f] > 0.f) ? x : 0.f;
+          else if (g.act == ACT_SOFTPLUS) x *= 1.0f - expf(-g.aux[(size_t)r * g.ldaux + f]);
+          g.C[(size_t)r * g.ldc + f] = x;
+        }
+      } else if (epi == EPI_STORE) {
+        // dW: accumulator D[n = f, k]; gradient tensor is [k, n] row-major -> lanes are contiguous
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = n0 + c0 + j;
+          if (k >= NE) break;
+          g.C[(size_t)k * g.ldc + f] = v[j];
+        }
+      } else {   // EPI_ADAM: Keras-2.0.9 Adam fused into the dW epilogue (gradient never leaves the SM)
+        const float b1 = hp.b1, b2 = hp.b2, c1 = 1.0f - hp.b1, c2 = 1.0f - hp.b2;
+        float pw[16], pm[16], pv[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = n0 + c0 + j;
+          if (k < NE) {
+            const size_t idx = (size_t)k * g.ldc + f;
+            pw[j] = op.P[idx]; pm[j] = op.Mo[idx]; pv[j] = op.Vo[idx];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int k = n0 + c0 + j;
+          if (k < NE) {
+            const size_t idx = (size_t)k * g.ldc + f;
+            const float gr = v[j];
+            const float m = fmaf(b1, pm[j], c1 * gr), vv = fmaf(b2, pv[j], c2 * gr * gr);
+            op.Mo[idx] = m; op.Vo[idx] = vv;
+            op.P[idx] = pw[j] - lr_t * m / (sqrtf(vv) + hp.eps);
+          }
+        }
+      }
+    }
+  }
+
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}

@@ -62,6 +62,17 @@ struct FoldBuffers {
 
 }  // namespace
 
+struct mrgan_handle;
+#ifdef MRGAN_WITH_TC
+namespace {
+int tc_setup(mrgan_handle* h);
+void tc_teardown(mrgan_handle* h);
+bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override);
+void tc_params_changed(mrgan_handle* h, int fold, int net);
+int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g);
+}
+#endif
+
 struct mrgan_handle {
   mrgan_config cfg;
   int nf = 0, R = 0, NE = 0, n_train = 0;
@@ -86,6 +97,12 @@ struct mrgan_handle {
   long long launches = 0;
   std::string err;
   AdamHyper hp;
+#ifdef MRGAN_WITH_TC
+  TcOp* d_tcops = nullptr;            // [NUM_OPS][nf] tensor maps + epilogue descriptors
+  int tc_bn[NUM_OPS] = {0}, tc_maxME[NUM_OPS] = {0}, tc_maxNE[NUM_OPS] = {0};
+  bool tc_fused_adam = true;          // dW epilogue applies Adam in place (no gradient round trip)
+  AdamRange* d_ranges_tc[2] = {nullptr, nullptr};   // what is left for k_adam: BN gamma/beta (G), nothing (D)
+#endif
 };
 
 namespace {
@@ -383,7 +400,11 @@ void launch_adam(mrgan_handle* h, int f0, int nfl, int net) {
   int blocks = (int)((nmax / 4 + 255) / 256);
   if (blocks > 2048) blocks = 2048;
   if (blocks < 1) blocks = 1;
-  k_adam<<<dim3(blocks, nfl), 256, 0, h->stream>>>(h->P, h->Mo, h->Vo, h->Gr, h->d_ranges[net], h->d_folds, f0, net, h->hp);
+  const AdamRange* ranges = h->d_ranges[net];
+#ifdef MRGAN_WITH_TC
+  if (h->cfg.precision == MRGAN_PREC_TF32 && h->tc_fused_adam) { ranges = h->d_ranges_tc[net]; blocks = 1; }
+#endif
+  k_adam<<<dim3(blocks, nfl), 256, 0, h->stream>>>(h->P, h->Mo, h->Vo, h->Gr, ranges, h->d_folds, f0, net, h->hp);
   h->launches++;
 }
 
@@ -404,9 +425,9 @@ void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) 
   for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 0);
   k_loss_disc<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B, c.n_classes, c.unlabeled_weight);
   h->launches++;
-  for (int l = 6; l >= 1; --l) {
-    launch_gemm(h, OP_DW1 + l - 1, f0, nfl, 0);
+  for (int l = 6; l >= 1; --l) {      // dX first: it reads W_l, which the fused-Adam dW epilogue overwrites
     if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
+    launch_gemm(h, OP_DW1 + l - 1, f0, nfl, 0);
   }
   launch_adam(h, f0, nfl, 0);
 }
@@ -422,10 +443,10 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   h->launches++;
   for (int l = 5; l >= 2; --l) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, B);
   launch_gemm(h, OP_DX1G, f0, nfl, 0);
-  launch_gemm(h, OP_GW3, f0, nfl, 0);
   launch_gemm(h, OP_GX3, f0, nfl, 0);
-  launch_gemm(h, OP_GW2, f0, nfl, 0);
+  launch_gemm(h, OP_GW3, f0, nfl, 0);
   launch_gemm(h, OP_GX2, f0, nfl, 0);
+  launch_gemm(h, OP_GW2, f0, nfl, 0);
   k_bn_bwd<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0);
   h->launches++;
   launch_gemm(h, OP_GW1, f0, nfl, 0);
@@ -435,14 +456,15 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
 // one model.fit batch of mr_nn (mr_nn.py:117)
 void enqueue_nn_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage, int n) {
   const mrgan_config& c = h->cfg;
+  // a ragged batch (n < batch) runs at full height: k_loss_mse zeroes the gradient rows >= n, so the
+  // stale rows contribute nothing to dW/db and every GEMM keeps its static shape
   launch_prep(h, f0, nfl, 2, from_stage, t, n);
-  const int ov = (n == h->R) ? 0 : n;
-  for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, ov);
-  k_loss_mse<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, n, c.n_classes);
+  for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 0);
+  k_loss_mse<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, n, h->R, c.n_classes);
   h->launches++;
   for (int l = 6; l >= 1; --l) {
-    launch_gemm(h, OP_DW1 + l - 1, f0, nfl, ov);
-    if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, ov);
+    if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
+    launch_gemm(h, OP_DW1 + l - 1, f0, nfl, 0);
   }
   launch_adam(h, f0, nfl, 0);
 }
@@ -545,6 +567,157 @@ int upload_indices(mrgan_handle* h, const int32_t* const* streams, int n_streams
 }
 
 }  // namespace
+
+
+#ifdef MRGAN_WITH_TC
+// ------------------------------------------------------------------ tcgen05 path: host side
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2D fp32 tensor [rows, cols] with `pitch` floats per row; box = 32 columns (one 128B swizzle row) x box_rows
+bool make_map(EncodeTiledFn fn, CUtensorMap* m, const float* base, int cols, int rows, int pitch, int box_rows,
+              bool mn_major) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1u, 1u};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+size_t tc_smem_bytes(int bn) { return 1024 + (size_t)TC_STAGES * (128 * 128 + (size_t)bn * 128) + 256; }
+
+int tc_setup(mrgan_handle* h);
+
+EncodeTiledFn tc_encoder() {
+  EncodeTiledFn fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&fn, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess) return nullptr;
+  return fn;
+}
+
+void tc_set_smem_attr() {
+  const int max_smem = (int)tc_smem_bytes(256);
+  cudaFuncSetAttribute(k_gemm_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(k_gemm_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(k_gemm_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+}
+
+// fills the tcgen05 view of one GEMM (shapes in the fp32 path's convention); mode 0 fwd, 1 dX, 2 dW
+bool tc_fill_op(EncodeTiledFn fn, TcOp& t, const GemmDesc& g, int mode) {
+  t.g = g;
+  t.ME = g.N; t.NE = g.M; t.KE = g.K;
+  if (mode == 0) {            // forward: C[M rows, N feats] = act[M, K] @ W[K, N]
+    t.epi = EPI_FWD;
+    t.bn = g.M <= 256 ? round_up(g.M, 16) : 160;
+    return make_map(fn, &t.mapA, g.B, g.N, g.K, g.ldb, 32, true) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false);
+  }
+  if (mode == 1) {            // dX: C[M rows, N in-feats] = dZ[M, K] @ W[N, K]^T
+    t.epi = EPI_DX;
+    t.bn = g.M <= 256 ? round_up(g.M, 16) : 160;
+    return make_map(fn, &t.mapA, g.B, g.K, g.N, g.ldb, 128, false) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false);
+  }
+  t.epi = EPI_STORE;          // dW: C[M in-feats(+1), N out-feats] = act[K rows, M]^T @ dZ[K rows, N]
+  t.bn = 128;
+  return make_map(fn, &t.mapA, g.B, g.N, g.K, g.ldb, 32, true) && make_map(fn, &t.mapB, g.A, g.M, g.K, g.lda, 32, true);
+}
+
+int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g) {
+  EncodeTiledFn fn = tc_encoder();
+  if (!fn) return fail(h, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  TcOp t; memset(&t, 0, sizeof(t));
+  if (!tc_fill_op(fn, t, g, mode)) return fail(h, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  TcOp* d = nullptr;
+  CK(cudaMalloc(&d, sizeof(TcOp)));
+  CK(cudaMemcpyAsync(d, &t, sizeof(t), cudaMemcpyHostToDevice, h->stream));
+  tc_set_smem_attr();
+  dim3 grid((t.ME + 127) / 128, (t.NE + t.bn - 1) / t.bn, 1);
+  const size_t smem = tc_smem_bytes(t.bn);
+  if (mode == 0) k_gemm_tc<true, false><<<grid, 192, smem, h->stream>>>(d, h->d_folds, 0, h->hp);
+  else if (mode == 1) k_gemm_tc<false, false><<<grid, 192, smem, h->stream>>>(d, h->d_folds, 0, h->hp);
+  else k_gemm_tc<true, true><<<grid, 192, smem, h->stream>>>(d, h->d_folds, 0, h->hp);
+  h->launches++;
+  CK(cudaStreamSynchronize(h->stream));
+  cudaFree(d);
+  return MRGAN_OK;
+}
+
+int tc_setup(mrgan_handle* h) {
+  EncodeTiledFn fn = tc_encoder();
+  if (!fn) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  const int nf = h->nf;
+  std::vector<TcOp> ops((size_t)NUM_OPS * nf);
+  memset(ops.data(), 0, ops.size() * sizeof(TcOp));
+  for (int op = 0; op < NUM_OPS; ++op) {
+    const OpInfo& oi = h->ops[op];
+    if (!oi.used) continue;
+    for (int f = 0; f < nf; ++f) {
+      const GemmDesc& g = h->h_descs[(size_t)op * nf + f];
+      TcOp& t = ops[(size_t)op * nf + f];
+      const int mode = (!oi.at && !oi.bt) ? 0 : ((!oi.at && oi.bt) ? 1 : 2);
+      if (!tc_fill_op(fn, t, g, mode)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+      if (mode == 2) {
+        if (h->tc_fused_adam) t.epi = EPI_ADAM;
+        const size_t off = (size_t)(g.C - h->Gr);
+        t.P = h->P + off; t.Mo = h->Mo + off; t.Vo = h->Vo + off;
+      }
+      if (t.bn > h->tc_bn[op]) h->tc_bn[op] = t.bn;
+      if (t.ME > h->tc_maxME[op]) h->tc_maxME[op] = t.ME;
+      if (t.NE > h->tc_maxNE[op]) h->tc_maxNE[op] = t.NE;
+    }
+  }
+  if (cudaMalloc(&h->d_tcops, ops.size() * sizeof(TcOp)) != cudaSuccess) return fail(nullptr, MRGAN_ERR_CUDA, "cudaMalloc tc ops");
+  cudaMemcpy(h->d_tcops, ops.data(), ops.size() * sizeof(TcOp), cudaMemcpyHostToDevice);
+  // what is left for the flat Adam kernel when dW applies Adam itself
+  std::vector<AdamRange> r0(nf), r1(nf);
+  for (int f = 0; f < nf; ++f) {
+    r0[f] = AdamRange{h->net[0][f].off, 0};
+    if (h->cfg.model == MRGAN_MODEL_GAN) {
+      const NetLayout& LG = h->net[1][f];
+      r1[f] = AdamRange{LG.off + LG.t[1].off, LG.t[3].off - LG.t[1].off};     // gamma, beta (contiguous, padded)
+    }
+  }
+  for (int n = 0; n < 2; ++n) {
+    if (cudaMalloc(&h->d_ranges_tc[n], nf * sizeof(AdamRange)) != cudaSuccess) return fail(nullptr, MRGAN_ERR_CUDA, "cudaMalloc");
+    cudaMemcpy(h->d_ranges_tc[n], (n == 0 ? r0 : r1).data(), nf * sizeof(AdamRange), cudaMemcpyHostToDevice);
+  }
+  tc_set_smem_attr();
+  return MRGAN_OK;
+}
+
+void tc_teardown(mrgan_handle* h) {
+  if (h->d_tcops) cudaFree(h->d_tcops);
+  for (int n = 0; n < 2; ++n) if (h->d_ranges_tc[n]) cudaFree(h->d_ranges_tc[n]);
+  h->d_tcops = nullptr;
+}
+
+void tc_params_changed(mrgan_handle*, int, int) {}   // fp32 master weights are the MMA operands: nothing to refresh
+
+bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override) {
+  const OpInfo& oi = h->ops[op];
+  const int bn = h->tc_bn[op];
+  int NE = h->tc_maxNE[op];
+  if (rows_override > 0 && !oi.at) NE = rows_override;
+  dim3 grid((h->tc_maxME[op] + 127) / 128, (NE + bn - 1) / bn, nfl);
+  const TcOp* d = h->d_tcops + (size_t)op * h->nf + f0;
+  const size_t smem = tc_smem_bytes(bn);
+  if (!oi.at && !oi.bt) k_gemm_tc<true, false><<<grid, 192, smem, h->stream>>>(d, h->d_folds, rows_override, h->hp);
+  else if (!oi.at && oi.bt) k_gemm_tc<false, false><<<grid, 192, smem, h->stream>>>(d, h->d_folds, rows_override, h->hp);
+  else k_gemm_tc<true, true><<<grid, 192, smem, h->stream>>>(d, h->d_folds, 0, h->hp);
+  h->launches++;
+  return true;
+}
+
+}  // namespace
+#endif  // MRGAN_WITH_TC
 
 // ====================================================================== C-ABI
 extern "C" {
@@ -1026,6 +1199,77 @@ int mrgan_time_op(mrgan_handle* h, int which, int reps, float* ms_avg) {
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   *ms_avg = ms / reps;
+  return MRGAN_OK;
+}
+
+int mrgan_debug_buffer(mrgan_handle* h, int fold, int which, float* dst, int rows, int cols) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (!dst || rows < 1 || cols < 1) return fail(h, MRGAN_ERR_ARG, "debug_buffer: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  const FoldBuffers& b = h->fb[fold];
+  const int K = h->cfg.n_classes, D = h->shapes[fold].D, nd = h->cfg.noise_dim;
+  const bool gan = h->cfg.model == MRGAN_MODEL_GAN;
+  const float* src = nullptr; int ld = 0;
+  if (which >= 0 && which <= 5) { src = b.a[which]; ld = b.lda[which]; }
+  else if (which >= 11 && which <= 15) { src = b.hb[which - 10]; ld = b.lda[which - 10]; }
+  else if (which >= 21 && which <= 25) { src = b.dz[which - 20]; ld = b.ldz[which - 20]; }
+  else if (which == 30) { src = b.lg; ld = pitch4(K); }
+  else if (which == 31) { src = b.dlg; ld = pitch4(K); }
+  else if (gan && which == 32) { src = b.dfake; ld = pitch4(D); }
+  else if (gan && which == 40) { src = b.zb; ld = pitch4(nd + 1); }
+  else if (gan && which == 41) { src = b.h1g; ld = kGH; }
+  else if (gan && which == 42) { src = b.u; ld = pitch4(kGH + 1); }
+  else if (gan && which == 43) { src = b.h2g; ld = pitch4(kGH + 1); }
+  else if (gan && which == 44) { src = b.dz2g; ld = kGH; }
+  else if (gan && which == 45) { src = b.du; ld = kGH; }
+  else if (gan && which == 46) { src = b.dz1g; ld = kGH; }
+  if (!src || cols > ld) return fail(h, MRGAN_ERR_ARG, "debug_buffer: unknown buffer or too many columns");
+  CK(cudaMemcpy2DAsync(dst, (size_t)cols * sizeof(float), src, (size_t)ld * sizeof(float), (size_t)cols * sizeof(float), rows,
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MRGAN_OK;
+}
+
+int mrgan_debug_gemm(mrgan_handle* h, int mode, int M, int N, int K, const float* A, const float* B, float* C, int use_tc) {
+  if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
+  if (mode < 0 || mode > 2 || M < 1 || N < 1 || K < 1 || !A || !B || !C) return fail(h, MRGAN_ERR_ARG, "debug_gemm: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = finish_pending(h); if (rc) return rc;
+  // operand shapes (rows, cols) as stored
+  const int ar = mode == 2 ? K : M, ac = mode == 2 ? M : K;
+  const int br = mode == 1 ? N : K, bc = mode == 1 ? K : N;
+  const int lda = pitch4(ac), ldb = pitch4(bc), ldc = pitch4(N);
+  float *dA = nullptr, *dB = nullptr, *dC = nullptr; GemmDesc* dd = nullptr;
+  CK(cudaMalloc(&dA, (size_t)ar * lda * 4)); CK(cudaMalloc(&dB, (size_t)br * ldb * 4)); CK(cudaMalloc(&dC, (size_t)M * ldc * 4));
+  CK(cudaMalloc(&dd, sizeof(GemmDesc)));
+  CK(cudaMemsetAsync(dA, 0, (size_t)ar * lda * 4, h->stream)); CK(cudaMemsetAsync(dB, 0, (size_t)br * ldb * 4, h->stream));
+  CK(cudaMemsetAsync(dC, 0, (size_t)M * ldc * 4, h->stream));
+  CK(cudaMemcpy2DAsync(dA, (size_t)lda * 4, A, (size_t)ac * 4, (size_t)ac * 4, ar, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(dB, (size_t)ldb * 4, B, (size_t)bc * 4, (size_t)bc * 4, br, cudaMemcpyHostToDevice, h->stream));
+  GemmDesc g = make_desc(dA, lda, dB, ldb, dC, ldc, M, N, K, mode == 0 ? EPI_FWD : (mode == 1 ? EPI_DX : EPI_STORE), ACT_NONE, 0);
+  CK(cudaMemcpyAsync(dd, &g, sizeof(g), cudaMemcpyHostToDevice, h->stream));
+  bool done = false;
+#ifdef MRGAN_WITH_TC
+  if (use_tc) {
+    rc = tc_debug_gemm(h, mode, g);
+    if (rc) return rc;
+    done = true;
+  }
+#endif
+  if (use_tc && !done) return fail(h, MRGAN_ERR_ARG, "library built without the tcgen05 kernels");
+  if (!done) {
+    dim3 grid((N + 63) / 64, (M + 63) / 64, 1);
+    if (mode == 0) k_gemm_simt<false, false><<<grid, 256, 0, h->stream>>>(dd, h->d_folds, 0);
+    else if (mode == 1) k_gemm_simt<false, true><<<grid, 256, 0, h->stream>>>(dd, h->d_folds, 0);
+    else k_gemm_simt<true, false><<<grid, 256, 0, h->stream>>>(dd, h->d_folds, 0);
+    h->launches++;
+  }
+  cudaError_t e = cudaMemcpy2DAsync(C, (size_t)N * 4, dC, (size_t)ldc * 4, (size_t)N * 4, M, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dd);
+  if (e != cudaSuccess) return fail(h, MRGAN_ERR_CUDA, std::string("debug_gemm: ") + cudaGetErrorString(e));
   return MRGAN_OK;
 }
 

@@ -233,6 +233,25 @@ class FoldGroup:
         self._chk(self.lib.mrgan_adam_flat(self._h, _lib.fptr(p), _lib.fptr(m), _lib.fptr(v), _lib.fptr(g), p.size, t))
         return p, m, v
 
+    def debug_buffer(self, fold, which, rows, cols):
+        """Test hook: an intermediate buffer of the last step (see mrgan_debug_buffer in include/mrgan.h)."""
+        out = np.empty((rows, cols), dtype=np.float32)
+        self._chk(self.lib.mrgan_debug_buffer(self._h, fold, which, _lib.fptr(out), rows, cols))
+        return out
+
+    def debug_gemm(self, mode, A, B, use_tc=True):
+        """Test hook: stand-alone GEMM through the step's kernels (see mrgan_debug_gemm)."""
+        A, B = _f32(A), _f32(B)
+        if mode == 0:
+            M, K, N = A.shape[0], A.shape[1], B.shape[1]
+        elif mode == 1:
+            M, K, N = A.shape[0], A.shape[1], B.shape[0]
+        else:
+            K, M, N = A.shape[0], A.shape[1], B.shape[1]
+        out = np.zeros((M, N), dtype=np.float32)
+        self._chk(self.lib.mrgan_debug_gemm(self._h, mode, M, N, K, _lib.fptr(A), _lib.fptr(B), _lib.fptr(out), int(use_tc)))
+        return out
+
     TIME_OPS = {"adam_d": 0, "adam_g": 1, "dw1": 2, "fwd1": 3, "disc_step": 4, "gen_step": 5}
 
     def time_op(self, which, reps=20):

@@ -12,7 +12,7 @@ from oracle import fold_loop, gan_oracle as O, make_golden, philox
 
 pytestmark = pytest.mark.gpu
 
-PRECISIONS = ["fp32"]
+PRECISIONS = ["fp32", "tf32"]
 LOSS_RTOL = {"fp32": 1e-3, "tf32": 1e-3}        # the north_star's tolerance, both modes
 PARAM_TOL = {"fp32": 1e-3, "tf32": 2e-2}        # |dp| relative to lr-sized updates, see _param_close
 
@@ -239,3 +239,52 @@ def test_full_size_properties_D1200(precision):
     np.testing.assert_array_equal(st2[0], st1[0])              # grouping-independent, run-to-run deterministic
     assert e2[0] == e2[1] == e1[0]
     assert np.isfinite(st1).all() and st1[0, 0] < 1.5 and st1[0, 2] < 0.5 and e1[0] < 0.4   # it learns
+
+
+def test_tf32_tensor_core_path_layer_by_layer_against_fp32_path():
+    """Localises errors of the tcgen05 kernels: every intermediate buffer of one D step and one G step,
+    tf32 path vs fp32 path (same weights, batches and noise stream).  TF32 keeps 10 mantissa bits of each
+    operand, so activations agree to ~1e-3 of their scale."""
+    D, B = 100, 50
+    key = _key64(philox.fold_key(3, 1))
+    pD, pG, steps = make_golden.case_inputs(D, B, 31, 1)
+    s = steps[0]
+    bufs = {}
+    for prec in ("fp32", "tf32"):
+        with FoldGroup([(D, 100, 40, key)], precision=prec, batch=B) as fg:
+            fg.set_params(0, 0, pD)
+            fg.set_params(0, 1, pG)
+            out = {}
+            out['loss_d'] = fg.train_batch_disc(0, s['x_lab'], s['labels'], s['x_unl'], s['z_d'])
+            widths = [D, 1000, 500, 250, 250, 250]
+            for name, which, rows, cols in ([("z", 40, B, 100), ("g_h1", 41, B, 500), ("g_u", 42, B, 500), ("g_h2", 43, B, 500)]
+                                            + [("a%d" % l, l, 3 * B, widths[l]) for l in range(5)]
+                                            + [("h%d" % l, 10 + l, 3 * B, widths[l]) for l in range(1, 6)]
+                                            + [("logits", 30, 3 * B, 6), ("dlogits", 31, 3 * B, 6)]
+                                            + [("dz%d" % l, 20 + l, 3 * B, widths[l]) for l in range(5, 0, -1)]):
+                out["D:" + name] = fg.debug_buffer(0, which, rows, cols)
+            out['pD'] = fg.get_params(0, 0)
+            out['loss_g'] = fg.train_batch_gen(0, s['x_unl2'], s['z_g'])
+            for name, which, rows, cols in ([("h%d" % l, 10 + l, 2 * B, widths[l]) for l in range(1, 6)]
+                                            + [("dz%d" % l, 20 + l, B, widths[l]) for l in range(5, 0, -1)]
+                                            + [("dfake", 32, B, D), ("g_dz2", 44, B, 500), ("g_du", 45, B, 500), ("g_dz1", 46, B, 500)]):
+                out["G:" + name] = fg.debug_buffer(0, which, rows, cols)
+            out['pG'] = fg.get_params(0, 1)
+            bufs[prec] = out
+    a, b = bufs["fp32"], bufs["tf32"]
+    report = []
+    for k in a:
+        if k in ("pD", "pG", "loss_d", "loss_g"):
+            continue
+        scale = np.abs(a[k]).max() + 1e-20
+        err = np.abs(a[k] - b[k]).max() / scale
+        report.append((k, float(err)))
+    bad = [(k, e) for k, e in report if not e < 2e-2]
+    assert not bad, "first mismatching buffers (name, max err / scale): %s\nall: %s" % (bad[:6], report)
+    np.testing.assert_allclose(b['loss_d'], a['loss_d'], rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(b['loss_g'], a['loss_g'], rtol=5e-3)
+    for net in ("pD", "pG"):
+        init = pD if net == "pD" else pG
+        for i, (x, y, p0) in enumerate(zip(a[net], b[net], init)):
+            upd = max(np.sqrt(np.mean((x - p0) ** 2)), 1e-4)
+            assert np.sqrt(np.mean((x - y) ** 2)) <= 0.05 * upd, (net, i, np.sqrt(np.mean((x - y) ** 2)), upd)
