@@ -46,6 +46,7 @@ struct GemmDesc {
   int act, epi;
   float sigma; int tid; int row0;   // noise added to C2: sigma * n(row0 + m, n)
   int fold;
+  int rnd;                          // tf32 mode: bit 0 / bit 1 = round C / C2 to tf32 (they feed a tcgen05 MMA)
 };
 
 struct AdamHyper { float lr, b1, b2, eps; int shared_t; };
@@ -85,6 +86,22 @@ __device__ __forceinline__ float normal1(uint32_t k0, uint32_t k1, uint32_t row,
   normal4(k0, k1, row >> 2, col, step, tid, n);
   return n[row & 3];
 }
+
+// Round-to-nearest onto the tf32 grid (10 mantissa bits).  kind::tf32 MMAs TRUNCATE their fp32 operands;
+// an operand that already sits on the grid passes through unchanged, so producers round (unbiased) once.
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+// kind::tf32 truncates the fp32 master weights it reads: w -> w (1 - e), e in [0, 2^-10).  For mantissas
+// that are log-uniform (any smooth distribution over a few octaves) E[e] = 2^-11 / (2 ln 2) = 3.52e-4, for
+// uniform mantissas 2^-11 ln 2 = 3.38e-4.  Every pre-activation therefore shrinks by ~3.45e-4 per layer (a
+// systematic 2e-3 on the 6-layer logits and on the feature-matching loss).  The forward / dX epilogues of the
+// tf32 path multiply the accumulator by this constant, which removes the mean and leaves a zero-mean error of
+// ~2e-4 per pre-activation.  Activation / gradient operands are rounded to nearest by their producers instead.
+#define TF32_TRUNC_DEBIAS 1.000345f
 
 __device__ __forceinline__ float softplusf(float x) {
   // log(1+e^x), stable on both tails (K.softplus)

@@ -162,7 +162,7 @@ k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ fo
 // from_stage: rows come from the step-API staging buffers instead of the resident fold.
 __global__ void __launch_bounds__(128)
 k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, int t, int B, int nrows,
-       int noise_dim, float sigma_in, AdamHyper hp) {
+       int noise_dim, float sigma_in, AdamHyper hp, int tf32) {
   FoldState& fs = folds[fold_base + blockIdx.z];
   const int c = blockIdx.x * 128 + threadIdx.x;
   const int rg = blockIdx.y;
@@ -196,7 +196,8 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
       const int lr = (mode == 2) ? r : (r < B ? r : r - B);
       const float* src = from_stage ? fs.stage_x + (size_t)r * fs.ldx
                                     : fs.x_train + (size_t)fs.idx[stream][(size_t)t * B + lr] * fs.ldx;
-      fs.a0[(size_t)r * fs.lda0 + c] = src[c] + sigma_in * nz[i];
+      const float v = src[c] + sigma_in * nz[i];
+      fs.a0[(size_t)r * fs.lda0 + c] = tf32 ? rna_tf32(v) : v;
     }
   }
   if (mode != 2 && c < noise_dim) {       // generator input z (mr_gan.py:206,212)
@@ -206,7 +207,8 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
     for (int i = 0; i < 4; ++i) {
       const int r = rg * 4 + i;
       if (r >= B) break;
-      fs.z[(size_t)r * fs.ldz + c] = from_stage ? fs.stage_z[(size_t)r * noise_dim + c] : nz[i];
+      const float v = from_stage ? fs.stage_z[(size_t)r * noise_dim + c] : nz[i];
+      fs.z[(size_t)r * fs.ldz + c] = tf32 ? rna_tf32(v) : v;
     }
   }
 }
@@ -220,7 +222,7 @@ struct BnDesc {
 };
 
 // mr_gan.py:112 BatchNormalization(epsilon=2e-5) in training phase: biased batch variance.
-__global__ void __launch_bounds__(128) k_bn_fwd(const BnDesc* __restrict__ descs, float eps) {
+__global__ void __launch_bounds__(128) k_bn_fwd(const BnDesc* __restrict__ descs, float eps, int tf32) {
   const BnDesc d = descs[blockIdx.z];
   const int j = blockIdx.x * 128 + threadIdx.x;
   if (j >= d.W) return;
@@ -235,12 +237,13 @@ __global__ void __launch_bounds__(128) k_bn_fwd(const BnDesc* __restrict__ descs
   for (int r = 0; r < d.B; ++r) {
     const float xh = (d.h1[(size_t)r * d.ld + j] - mu) * istd;
     d.xhat[(size_t)r * d.ld + j] = xh;
-    d.u[(size_t)r * d.ldu + j] = fmaf(g, xh, b);
+    const float u = fmaf(g, xh, b);
+    d.u[(size_t)r * d.ldu + j] = tf32 ? rna_tf32(u) : u;
   }
 }
 
 // BN backward + softplus' of the layer in front of it (G layer 1): du -> dgamma, dbeta, dz1.
-__global__ void __launch_bounds__(128) k_bn_bwd(const BnDesc* __restrict__ descs) {
+__global__ void __launch_bounds__(128) k_bn_bwd(const BnDesc* __restrict__ descs, int tf32) {
   const BnDesc d = descs[blockIdx.z];
   const int j = blockIdx.x * 128 + threadIdx.x;
   if (j >= d.W) return;
@@ -257,7 +260,8 @@ __global__ void __launch_bounds__(128) k_bn_bwd(const BnDesc* __restrict__ descs
     const float xh = d.xhat[(size_t)r * d.ld + j];
     const float dxh = d.du[(size_t)r * d.ld + j] * g;
     const float dh1 = istd * (dxh - invB * g * s1 - xh * invB * g * s2);
-    d.dz1[(size_t)r * d.ld + j] = dh1 * (1.0f - expf(-d.h1[(size_t)r * d.ld + j]));
+    const float dz = dh1 * (1.0f - expf(-d.h1[(size_t)r * d.ld + j]));
+    d.dz1[(size_t)r * d.ld + j] = tf32 ? rna_tf32(dz) : dz;
   }
 }
 
@@ -272,7 +276,7 @@ struct LossDesc {
 // (mr_gan.py:146-149,161) and their gradients.
 __global__ void __launch_bounds__(256)
 k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total,
-            int t, int B, int K, float w_unl) {
+            int t, int B, int K, float w_unl, int tf32) {
   __shared__ float sh[32];
   const LossDesc d = descs[blockIdx.z];
   float s_lab = 0.f, s_unl = 0.f, s_err = 0.f;
@@ -288,14 +292,20 @@ k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, 
       const int y = d.labels[r];
       s_lab += lse - l[y];
       s_err += (am != y) ? 1.f : 0.f;
-      for (int k = 0; k < K; ++k) dl[k] = (expf(l[k] - mx) * inv - (k == y ? 1.f : 0.f)) / B;
+      for (int k = 0; k < K; ++k) {
+        const float g = (expf(l[k] - mx) * inv - (k == y ? 1.f : 0.f)) / B;
+        dl[k] = tf32 ? rna_tf32(g) : g;
+      }
     } else {
       const float sp = softplusf(lse), sg = 1.0f / (1.0f + expf(-lse));
       float coef;
       if (r < 2 * B) { s_unl += 0.5f * (sp - lse); coef = 0.5f * (sg - 1.0f); }
       else           { s_unl += 0.5f * sp;         coef = 0.5f * sg; }
       coef *= w_unl / B;
-      for (int k = 0; k < K; ++k) dl[k] = coef * expf(l[k] - mx) * inv;
+      for (int k = 0; k < K; ++k) {
+        const float g = coef * expf(l[k] - mx) * inv;
+        dl[k] = tf32 ? rna_tf32(g) : g;
+      }
     }
   }
   s_lab = block_sum(s_lab, sh);
@@ -310,7 +320,8 @@ k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, 
 // Feature matching (mr_gan.py:152-154): rows [0,B) = fake, [B,2B) = real mid activations.
 // Writes dZ5 (already multiplied by ReLU') for the fake rows.
 __global__ void __launch_bounds__(256)
-k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total, int t, int B) {
+k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total, int t, int B,
+     int tf32) {
   __shared__ float sh[32];
   const LossDesc d = descs[blockIdx.z];
   float s = 0.f;
@@ -319,7 +330,8 @@ k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fol
     for (int r = 0; r < B; ++r) { mg += d.mid[(size_t)r * d.ldmid + j]; mr += d.mid[(size_t)(r + B) * d.ldmid + j]; }
     const float diff = (mg - mr) / B;
     s = fmaf(diff, diff, s);
-    const float g = 2.0f * diff / ((float)d.Wmid * B);
+    float g = 2.0f * diff / ((float)d.Wmid * B);
+    if (tf32) g = rna_tf32(g);
     for (int r = 0; r < B; ++r)
       d.dmid[(size_t)r * d.lddmid + j] = (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : 0.f;
   }
@@ -330,7 +342,7 @@ k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fol
 // mr_nn.py:114 loss='mse' vs one-hot, metrics=['accuracy'].
 __global__ void __launch_bounds__(256)
 k_loss_mse(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total,
-           int t, int n, int rows_total, int K) {
+           int t, int n, int rows_total, int K, int tf32) {
   __shared__ float sh[32];
   const LossDesc d = descs[blockIdx.z];
   float s_loss = 0.f, s_acc = 0.f;
@@ -346,7 +358,8 @@ k_loss_mse(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, i
     for (int k = 0; k < K; ++k) {
       const float diff = l[k] - (k == y ? 1.f : 0.f);
       q = fmaf(diff, diff, q);
-      dl[k] = 2.0f * diff / ((float)n * K);
+      const float g = 2.0f * diff / ((float)n * K);
+      dl[k] = tf32 ? rna_tf32(g) : g;
     }
     s_loss += q / K;
     s_acc += (am == y) ? 1.f : 0.f;

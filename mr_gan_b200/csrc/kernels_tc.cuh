@@ -232,11 +232,11 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
           for (int i = 0; i < 4; ++i) {
             const int r = r0 + i;
             if (r >= NE) break;
-            float x = v[4 * q + i];
+            float x = v[4 * q + i] * TF32_TRUNC_DEBIAS;
             if (g.act == ACT_RELU) x = fmaxf(x, 0.f);
             else if (g.act == ACT_SOFTPLUS) x = softplusf(x);
-            if (g.C) g.C[(size_t)r * g.ldc + f] = x;
-            if (g.C2) g.C2[(size_t)r * g.ldc2 + f] = x + g.sigma * nz[i];
+            if (g.C) g.C[(size_t)r * g.ldc + f] = (g.rnd & 1) ? rna_tf32(x) : x;
+            if (g.C2) { const float y = x + g.sigma * nz[i]; g.C2[(size_t)r * g.ldc2 + f] = (g.rnd & 2) ? rna_tf32(y) : y; }
           }
         }
       } else if (epi == EPI_DX) {
@@ -244,10 +244,10 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         for (int j = 0; j < 16; ++j) {
           const int r = n0 + c0 + j;
           if (r >= NE) break;
-          float x = v[j];
+          float x = v[j] * TF32_TRUNC_DEBIAS;
           if (g.act == ACT_RELU) x = (g.aux[(size_t)r * g.ldaux + f] > 0.f) ? x : 0.f;
           else if (g.act == ACT_SOFTPLUS) x *= 1.0f - expf(-g.aux[(size_t)r * g.ldaux + f]);
-          g.C[(size_t)r * g.ldc + f] = x;
+          g.C[(size_t)r * g.ldc + f] = (g.rnd & 1) ? rna_tf32(x) : x;
         }
       } else if (epi == EPI_STORE) {
         // dW: accumulator D[n = f, k]; gradient tensor is [k, n] row-major -> lanes are contiguous

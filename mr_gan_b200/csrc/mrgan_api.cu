@@ -153,6 +153,10 @@ NetLayout layout_gen(int D, int nd) {
   return L;
 }
 
+__global__ void k_round_tf32(float* p, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = rna_tf32(p[i]);
+}
+
 __global__ void k_set_col(float* p, int ld, int rows, int col, float v) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < rows) p[(size_t)r * ld + col] = v;
@@ -239,7 +243,9 @@ void build_descs(mrgan_handle* h) {
   h->h_folds.assign(nf, FoldState{});
   std::vector<BnDesc> bn(nf); std::vector<LossDesc> ls(nf); std::vector<EvalDesc> ev(nf), evs(nf);
   std::vector<AdamRange> rg0(nf), rg1(nf);
-  auto setop = [&](int op, int f, const GemmDesc& d, bool at, bool bt) {
+  const bool tf32 = c.precision == MRGAN_PREC_TF32;
+  auto setop = [&](int op, int f, GemmDesc d, bool at, bool bt, int rnd = 0) {
+    d.rnd = tf32 ? rnd : 0;
     h->h_descs[(size_t)op * nf + f] = d;
     OpInfo& oi = h->ops[op];
     oi.at = at; oi.bt = bt; oi.used = true;
@@ -262,14 +268,14 @@ void build_descs(mrgan_handle* h) {
       GemmDesc d = make_desc(b.a[l - 1], b.lda[l - 1], PD + W.off, W.pitch, C, ldc, R, wout[l - 1], win[l - 1] + 1,
                              EPI_FWD, l <= 5 ? ACT_RELU : ACT_NONE, f);
       if (l <= 4) { d.C2 = b.a[l]; d.ldc2 = b.lda[l]; d.sigma = sig[l]; d.tid = l; d.row0 = 0; }
-      setop(OP_D1 + l - 1, f, d, false, false);
+      setop(OP_D1 + l - 1, f, d, false, false, (l == 5 ? 1 : 0) | 2);
       // eval twin: no noise, reads the clean activations
       const float* EA = (l == 1) ? b.xte : b.eh[l - 1];
       float* EC = (l <= 5) ? b.eh[l] : b.elg;
       GemmDesc e = make_desc(EA, b.lda[l - 1], PD + W.off, W.pitch, EC, ldc, h->shapes[f].n_test, wout[l - 1],
                              win[l - 1] + 1, EPI_FWD, l <= 5 ? ACT_RELU : ACT_NONE, f);
-      setop(l == 1 ? OP_E1 : OP_E2 + l - 2, f, e, false, false);
-      if (l == 1) { e.A = b.ex_stage; setop(OP_E1S, f, e, false, false); }
+      setop(l == 1 ? OP_E1 : OP_E2 + l - 2, f, e, false, false, l <= 5 ? 1 : 0);
+      if (l == 1) { e.A = b.ex_stage; setop(OP_E1S, f, e, false, false, 1); }
       // dW (+db): grad(Waug_l) = a[l-1]^T @ dZ[l]
       const float* dZ = (l <= 5) ? b.dz[l] : b.dlg;
       const int lddz = (l <= 5) ? b.ldz[l] : pitch4(K);
@@ -281,7 +287,7 @@ void build_descs(mrgan_handle* h) {
         GemmDesc x = make_desc(dZ, lddz, PD + W.off, W.pitch, b.dz[l - 1], b.ldz[l - 1], R, win[l - 1], wout[l - 1],
                                EPI_DX, ACT_RELU, f);
         x.aux = b.hb[l - 1]; x.ldaux = b.lda[l - 1];
-        setop(OP_DX2 + l - 2, f, x, false, true);
+        setop(OP_DX2 + l - 2, f, x, false, true, 1);
       }
     }
     rg0[f] = AdamRange{LD.off, LD.n};
@@ -294,19 +300,19 @@ void build_descs(mrgan_handle* h) {
       const TensorLayout &W1 = LG.t[0], &Tg = LG.t[1], &Tb = LG.t[2], &W2 = LG.t[3], &W3 = LG.t[4];
       const int ldzb = pitch4(nd + 1), ldu = pitch4(kGH + 1), ldx = pitch4(D);
       setop(OP_G1, f, make_desc(b.zb, ldzb, PG + W1.off, W1.pitch, b.h1g, kGH, B, kGH, nd + 1, EPI_FWD, ACT_SOFTPLUS, f), false, false);
-      setop(OP_G2, f, make_desc(b.u, ldu, PG + W2.off, W2.pitch, b.h2g, ldu, B, kGH, kGH + 1, EPI_FWD, ACT_SOFTPLUS, f), false, false);
+      setop(OP_G2, f, make_desc(b.u, ldu, PG + W2.off, W2.pitch, b.h2g, ldu, B, kGH, kGH + 1, EPI_FWD, ACT_SOFTPLUS, f), false, false, 1);
       GemmDesc g3 = make_desc(b.h2g, ldu, PG + W3.off, W3.pitch, nullptr, 0, B, D, kGH + 1, EPI_FWD, ACT_NONE, f);
       g3.C2 = b.a[0] + (size_t)2 * B * b.lda[0]; g3.ldc2 = b.lda[0]; g3.sigma = c.sigma_in; g3.tid = 0; g3.row0 = 2 * B;
-      setop(OP_G3D, f, g3, false, false);
+      setop(OP_G3D, f, g3, false, false, 2);
       g3.C2 = b.a[0]; g3.row0 = 0;
-      setop(OP_G3G, f, g3, false, false);
+      setop(OP_G3G, f, g3, false, false, 2);
       // dFake = dZ[1] @ W1^T  (no activation derivative: fake is G's linear output)
       const TensorLayout& DW1 = LD.t[0];
-      setop(OP_DX1G, f, make_desc(b.dz[1], b.ldz[1], PD + DW1.off, DW1.pitch, b.dfake, ldx, B, D, kDW[0], EPI_DX, ACT_NONE, f), false, true);
+      setop(OP_DX1G, f, make_desc(b.dz[1], b.ldz[1], PD + DW1.off, DW1.pitch, b.dfake, ldx, B, D, kDW[0], EPI_DX, ACT_NONE, f), false, true, 1);
       setop(OP_GW3, f, make_desc(b.h2g, ldu, b.dfake, ldx, GG + W3.off, W3.pitch, kGH + 1, D, B, EPI_STORE, ACT_NONE, f), true, false);
       GemmDesc gx3 = make_desc(b.dfake, ldx, PG + W3.off, W3.pitch, b.dz2g, kGH, B, kGH, D, EPI_DX, ACT_SOFTPLUS, f);
       gx3.aux = b.h2g; gx3.ldaux = ldu;
-      setop(OP_GX3, f, gx3, false, true);
+      setop(OP_GX3, f, gx3, false, true, 1);
       setop(OP_GW2, f, make_desc(b.u, ldu, b.dz2g, kGH, GG + W2.off, W2.pitch, kGH + 1, kGH, B, EPI_STORE, ACT_NONE, f), true, false);
       setop(OP_GX2, f, make_desc(b.dz2g, kGH, PG + W2.off, W2.pitch, b.du, kGH, B, kGH, kGH, EPI_DX, ACT_NONE, f), false, true);
       setop(OP_GW1, f, make_desc(b.zb, ldzb, b.dz1g, kGH, GG + W1.off, W1.pitch, nd + 1, kGH, B, EPI_STORE, ACT_NONE, f), true, false);
@@ -390,7 +396,8 @@ void launch_prep(mrgan_handle* h, int f0, int nfl, int mode, int from_stage, int
   int cols = max_D(h, f0, nfl);
   if (c.noise_dim > cols) cols = c.noise_dim;
   dim3 grid((cols + 127) / 128, (nrows + 3) / 4, nfl);
-  k_prep<<<grid, 128, 0, h->stream>>>(h->d_folds, f0, mode, from_stage, t, c.batch, nrows, c.noise_dim, c.sigma_in, h->hp);
+  k_prep<<<grid, 128, 0, h->stream>>>(h->d_folds, f0, mode, from_stage, t, c.batch, nrows, c.noise_dim, c.sigma_in, h->hp,
+                                             c.precision == MRGAN_PREC_TF32);
   h->launches++;
 }
 
@@ -410,7 +417,7 @@ void launch_adam(mrgan_handle* h, int f0, int nfl, int net) {
 
 void enqueue_gen_fwd(mrgan_handle* h, int f0, int nfl, int op_g3) {
   launch_gemm(h, OP_G1, f0, nfl, 0);
-  k_bn_fwd<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, h->cfg.bn_eps);
+  k_bn_fwd<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, h->cfg.bn_eps, h->cfg.precision == MRGAN_PREC_TF32);
   h->launches++;
   launch_gemm(h, OP_G2, f0, nfl, 0);
   launch_gemm(h, op_g3, f0, nfl, 0);
@@ -423,7 +430,8 @@ void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) 
   launch_prep(h, f0, nfl, 0, from_stage, t, 2 * B);
   enqueue_gen_fwd(h, f0, nfl, OP_G3D);
   for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 0);
-  k_loss_disc<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B, c.n_classes, c.unlabeled_weight);
+  k_loss_disc<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B, c.n_classes, c.unlabeled_weight,
+                                                         c.precision == MRGAN_PREC_TF32);
   h->launches++;
   for (int l = 6; l >= 1; --l) {      // dX first: it reads W_l, which the fused-Adam dW epilogue overwrites
     if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
@@ -439,7 +447,7 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   launch_prep(h, f0, nfl, 1, from_stage, t, 2 * B);
   enqueue_gen_fwd(h, f0, nfl, OP_G3G);
   for (int l = 0; l < 5; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 2 * B);
-  k_fm<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B);
+  k_fm<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B, c.precision == MRGAN_PREC_TF32);
   h->launches++;
   for (int l = 5; l >= 2; --l) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, B);
   launch_gemm(h, OP_DX1G, f0, nfl, 0);
@@ -447,7 +455,7 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   launch_gemm(h, OP_GW3, f0, nfl, 0);
   launch_gemm(h, OP_GX2, f0, nfl, 0);
   launch_gemm(h, OP_GW2, f0, nfl, 0);
-  k_bn_bwd<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0);
+  k_bn_bwd<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, c.precision == MRGAN_PREC_TF32);
   h->launches++;
   launch_gemm(h, OP_GW1, f0, nfl, 0);
   launch_adam(h, f0, nfl, 1);
@@ -460,7 +468,8 @@ void enqueue_nn_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage, in
   // stale rows contribute nothing to dW/db and every GEMM keeps its static shape
   launch_prep(h, f0, nfl, 2, from_stage, t, n);
   for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 0);
-  k_loss_mse<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, n, h->R, c.n_classes);
+  k_loss_mse<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, n, h->R, c.n_classes,
+                                                        c.precision == MRGAN_PREC_TF32);
   h->launches++;
   for (int l = 6; l >= 1; --l) {
     if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
@@ -935,6 +944,10 @@ int mrgan_load_fold(mrgan_handle* h, int fold, const float* x_train, const int32
   CK(cudaMemcpy2DAsync(b.xte, (size_t)b.lda[0] * sizeof(float), x_test, w, w, s.n_test, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(b.ytr, y_train, (size_t)s.n_train * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(b.yte, y_test, (size_t)s.n_test * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (h->cfg.precision == MRGAN_PREC_TF32) {   // X_test feeds the first eval MMA directly: put it on the tf32 grid (RN) once
+    k_round_tf32<<<256, 256, 0, h->stream>>>(b.xte, (size_t)s.n_test * b.lda[0]);
+    h->launches++;
+  }
   CK(cudaStreamSynchronize(h->stream));
   b.loaded = true;
   return MRGAN_OK;
@@ -996,6 +1009,10 @@ int mrgan_test_batch(mrgan_handle* h, int fold, const float* x, const int32_t* y
   const size_t w = (size_t)D * sizeof(float);
   CK(cudaMemcpy2DAsync(b.ex_stage, (size_t)b.lda[0] * sizeof(float), x, w, w, n, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(b.ey_stage, y, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (h->cfg.precision == MRGAN_PREC_TF32) {
+    k_round_tf32<<<64, 256, 0, h->stream>>>(b.ex_stage, (size_t)n * b.lda[0]);
+    h->launches++;
+  }
   enqueue_eval(h, fold, 1, true, n);
   CK(cudaMemcpyAsync(h->h_scratch, b.eval_out_s, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
