@@ -33,7 +33,6 @@ struct alignas(64) TcOp {
   int pad_[3];
 };
 
-#define TC_STAGES 4
 #define TC_KBLK 32            // contraction elements per stage (one 128-byte swizzle row of fp32)
 #define TC_SPIN_LIMIT (1ll << 31)   // cycles; a stuck barrier traps instead of hanging the GPU
 
@@ -104,11 +103,25 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 }  // namespace tc
 
 // A_MN / B_MN: operand is MN-major (its MMA M/N dimension is the memory-contiguous one).
-template <bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192, 1)
+// STAGES: depth of the TMA->MMA ring; TMEM_COLS: accumulator columns allocated (power of 2 >= bn);
+// MINB: CTAs per SM the register allocation must allow (dW uses 2 so that one CTA's Adam epilogue
+// streams HBM while the other loads operands and runs its MMAs).
+template <bool A_MN, bool B_MN, int STAGES, int TMEM_COLS, int MINB>
+__global__ void __launch_bounds__(192, MINB)
 k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_override, AdamHyper hp) {
   using namespace tc;
   const TcOp& op = ops[blockIdx.z];
@@ -121,11 +134,11 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)bn * 128, stage_bytes = a_bytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_STAGES * stage_bytes);
-  uint64_t* full = bars;                    // [TC_STAGES]
-  uint64_t* empty = bars + TC_STAGES;       // [TC_STAGES]
-  uint64_t* tmem_full = bars + 2 * TC_STAGES;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* full = bars;                    // [STAGES]
+  uint64_t* empty = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (KE + TC_KBLK - 1) / TC_KBLK;
@@ -133,12 +146,12 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   if (warp == 0 && lane == 0) {
     prefetch_map(&op.mapA);
     prefetch_map(&op.mapB);
-    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {   // TMEM: 256 fp32 columns x 128 lanes for the accumulator tile
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(256u) : "memory");
+  if (warp == 1) {   // TMEM: TMEM_COLS fp32 columns x 128 lanes for the accumulator tile
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"((uint32_t)TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   fence_before();
@@ -150,8 +163,8 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
     // ===================== TMA producer =====================
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_expect_tx(&full[s], stage_bytes);
         uint8_t* sa = smem + (size_t)s * stage_bytes;
@@ -180,8 +193,8 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
       const uint32_t layA = A_MN ? 1u : 2u, layB = B_MN ? 1u : 2u;
       const uint32_t stepA = A_MN ? 1024u : 32u, stepB = B_MN ? 1024u : 32u;   // bytes per 8 contraction elements
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)(kb / TC_STAGES) & 1u;
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&full[s], ph);
         fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
@@ -200,10 +213,9 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
     const int lane_base = 32 * (warp & 3);
     const int f = m0 + lane_base + lane;                  // this thread's feature index (MMA-M)
     const bool f_ok = f < ME;
-    mbar_wait(tmem_full, 0);
-    fence_after();
-    const GemmDesc& g = op.g;
+    const GemmDesc g = op.g;             // by value: descriptor fields must not be re-read from HBM around every store
     const int epi = op.epi;
+    float* const adamP = op.P; float* const adamM = op.Mo; float* const adamV = op.Vo;
     const int ncols = min(bn, NE - n0);
     const uint32_t trow = tmem_base + ((uint32_t)lane_base << 16);
     uint32_t key0 = 0, key1 = 0, step = 0;
@@ -213,70 +225,118 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
       const FoldState& fs = folds[g.fold];
       key0 = fs.key0; key1 = fs.key1; step = (uint32_t)fs.rng_step; lr_t = fs.lr_t;
     }
-    for (int c0 = 0; c0 < ncols; c0 += 16) {
-      float v[16];
-      tmem_ld16(trow + (uint32_t)c0, v);                   // warp-collective: every lane takes part
-      if (!f_ok) continue;
-      if (epi == EPI_FWD) {
-        // rows r = n0 + c0 + j; noise is grouped by 4 consecutive rows of one column (= this feature)
+
+    if (epi == EPI_ADAM) {
+      // Keras-2.0.9 Adam fused into the dW epilogue: the gradient never leaves the SM.  Accumulator D[n = f, k];
+      // the weight tensor is [k, n] row-major, so for a fixed k the 32 lanes touch one 128-byte line of each of
+      // W, m, v.  The three streams are register double-buffered one 16-column chunk ahead, and the first chunk
+      // is requested BEFORE the accumulator is ready, so HBM latency overlaps the TMA/MMA phase.
+      const float b1 = hp.b1, b2 = hp.b2, c1 = 1.0f - hp.b1, c2 = 1.0f - hp.b2, eps = hp.eps;
+      // 8-column chunks: 2 x 24 prefetch registers keep the kernel under the 2-CTA/SM register budget (no spills,
+      // which would force every load to be waited for immediately)
+      auto fetch = [&](int c0, float (&pw)[8], float (&pm)[8], float (&pv)[8]) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r0 = n0 + c0 + 4 * q;
-          if (r0 >= NE) break;
-          float nz[4] = {0.f, 0.f, 0.f, 0.f};
-          if (noisy) {
-            if (((g.row0 + r0) & 3) == 0) normal4(key0, key1, (uint32_t)(g.row0 + r0) >> 2, (uint32_t)f, step, (uint32_t)g.tid, nz);
-            else for (int i = 0; i < 4; ++i) nz[i] = normal1(key0, key1, (uint32_t)(g.row0 + r0 + i), (uint32_t)f, step, (uint32_t)g.tid);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = r0 + i;
-            if (r >= NE) break;
-            float x = v[4 * q + i] * TF32_TRUNC_DEBIAS;
-            if (g.act == ACT_RELU) x = fmaxf(x, 0.f);
-            else if (g.act == ACT_SOFTPLUS) x = softplusf(x);
-            if (g.C) g.C[(size_t)r * g.ldc + f] = (g.rnd & 1) ? rna_tf32(x) : x;
-            if (g.C2) { const float y = x + g.sigma * nz[i]; g.C2[(size_t)r * g.ldc2 + f] = (g.rnd & 2) ? rna_tf32(y) : y; }
+        for (int j = 0; j < 8; ++j) {
+          if (f_ok && c0 + j < ncols) {
+            const size_t idx = (size_t)(n0 + c0 + j) * g.ldc + f;
+            pw[j] = __ldcs(adamP + idx); pm[j] = __ldcs(adamM + idx); pv[j] = __ldcs(adamV + idx);
           }
         }
-      } else if (epi == EPI_DX) {
+      };
+      auto apply = [&](int c0, const float (&v)[8], const float (&pw)[8], const float (&pm)[8], const float (&pv)[8]) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int r = n0 + c0 + j;
-          if (r >= NE) break;
-          float x = v[j] * TF32_TRUNC_DEBIAS;
-          if (g.act == ACT_RELU) x = (g.aux[(size_t)r * g.ldaux + f] > 0.f) ? x : 0.f;
-          else if (g.act == ACT_SOFTPLUS) x *= 1.0f - expf(-g.aux[(size_t)r * g.ldaux + f]);
-          g.C[(size_t)r * g.ldc + f] = (g.rnd & 1) ? rna_tf32(x) : x;
-        }
-      } else if (epi == EPI_STORE) {
-        // dW: accumulator D[n = f, k]; gradient tensor is [k, n] row-major -> lanes are contiguous
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k = n0 + c0 + j;
-          if (k >= NE) break;
-          g.C[(size_t)k * g.ldc + f] = v[j];
-        }
-      } else {   // EPI_ADAM: Keras-2.0.9 Adam fused into the dW epilogue (gradient never leaves the SM)
-        const float b1 = hp.b1, b2 = hp.b2, c1 = 1.0f - hp.b1, c2 = 1.0f - hp.b2;
-        float pw[16], pm[16], pv[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k = n0 + c0 + j;
-          if (k < NE) {
-            const size_t idx = (size_t)k * g.ldc + f;
-            pw[j] = op.P[idx]; pm[j] = op.Mo[idx]; pv[j] = op.Vo[idx];
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k = n0 + c0 + j;
-          if (k < NE) {
-            const size_t idx = (size_t)k * g.ldc + f;
+        for (int j = 0; j < 8; ++j) {
+          if (f_ok && c0 + j < ncols) {
+            const size_t idx = (size_t)(n0 + c0 + j) * g.ldc + f;
             const float gr = v[j];
             const float m = fmaf(b1, pm[j], c1 * gr), vv = fmaf(b2, pv[j], c2 * gr * gr);
-            op.Mo[idx] = m; op.Vo[idx] = vv;
-            op.P[idx] = pw[j] - lr_t * m / (sqrtf(vv) + hp.eps);
+            __stcs(adamM + idx, m); __stcs(adamV + idx, vv);
+            __stcs(adamP + idx, pw[j] - lr_t * __fdividef(m, sqrtf(vv) + eps));
+          }
+        }
+      };
+      float pwA[8], pmA[8], pvA[8], pwB[8], pmB[8], pvB[8], v[8];
+      fetch(0, pwA, pmA, pvA);
+      fetch(8, pwB, pmB, pvB);
+      mbar_wait(tmem_full, 0);
+      fence_after();
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        tmem_ld8(trow + (uint32_t)c0, v);
+        apply(c0, v, pwA, pmA, pvA);
+        if (c0 + 16 < ncols) fetch(c0 + 16, pwA, pmA, pvA);
+        if (c0 + 8 < ncols) {
+          tmem_ld8(trow + (uint32_t)(c0 + 8), v);
+          apply(c0 + 8, v, pwB, pmB, pvB);
+          if (c0 + 24 < ncols) fetch(c0 + 24, pwB, pmB, pvB);
+        }
+      }
+    } else if (epi == EPI_DX) {
+      // dZ_prev[r, f] = acc * act'(h_prev[r, f]); h is prefetched one chunk ahead (and before the accumulator is ready)
+      auto fetch = [&](int c0, float (&av)[16]) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          av[j] = (f_ok && g.act != ACT_NONE && c0 + j < ncols) ? __ldg(g.aux + (size_t)(n0 + c0 + j) * g.ldaux + f) : 1.0f;
+      };
+      auto apply = [&](int c0, const float (&v)[16], const float (&av)[16]) {
+        if (!f_ok) return;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (c0 + j >= ncols) break;
+          float x = v[j] * TF32_TRUNC_DEBIAS;
+          if (g.act == ACT_RELU) x = (av[j] > 0.f) ? x : 0.f;
+          else if (g.act == ACT_SOFTPLUS) x *= 1.0f - __expf(-av[j]);
+          g.C[(size_t)(n0 + c0 + j) * g.ldc + f] = (g.rnd & 1) ? rna_tf32(x) : x;
+        }
+      };
+      float avA[16], avB[16], v[16];
+      fetch(0, avA);
+      mbar_wait(tmem_full, 0);
+      fence_after();
+      for (int c0 = 0; c0 < ncols; c0 += 32) {
+        tmem_ld16(trow + (uint32_t)c0, v);
+        if (c0 + 16 < ncols) fetch(c0 + 16, avB);
+        apply(c0, v, avA);
+        if (c0 + 16 < ncols) {
+          tmem_ld16(trow + (uint32_t)(c0 + 16), v);
+          if (c0 + 32 < ncols) fetch(c0 + 32, avA);
+          apply(c0 + 16, v, avB);
+        }
+      }
+    } else {
+      mbar_wait(tmem_full, 0);
+      fence_after();
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        float v[16];
+        tmem_ld16(trow + (uint32_t)c0, v);                   // warp-collective: every lane takes part
+        if (!f_ok) continue;
+        if (epi == EPI_FWD) {
+          // rows r = n0 + c0 + j; noise is grouped by 4 consecutive rows of one column (= this feature)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int r0 = n0 + c0 + 4 * q;
+            if (r0 >= NE) break;
+            float nz[4] = {0.f, 0.f, 0.f, 0.f};
+            if (noisy) {
+              if (((g.row0 + r0) & 3) == 0) normal4(key0, key1, (uint32_t)(g.row0 + r0) >> 2, (uint32_t)f, step, (uint32_t)g.tid, nz);
+              else for (int i = 0; i < 4; ++i) nz[i] = normal1(key0, key1, (uint32_t)(g.row0 + r0 + i), (uint32_t)f, step, (uint32_t)g.tid);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = r0 + i;
+              if (r >= NE) break;
+              float x = v[4 * q + i] * TF32_TRUNC_DEBIAS;
+              if (g.act == ACT_RELU) x = fmaxf(x, 0.f);
+              else if (g.act == ACT_SOFTPLUS) x = softplusf(x);
+              if (g.C) g.C[(size_t)r * g.ldc + f] = (g.rnd & 1) ? rna_tf32(x) : x;
+              if (g.C2) { const float y = x + g.sigma * nz[i]; g.C2[(size_t)r * g.ldc2 + f] = (g.rnd & 2) ? rna_tf32(y) : y; }
+            }
+          }
+        } else {   // EPI_STORE: dW into the flat gradient buffer (data-parallel mode: all-reduced before Adam)
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int k = n0 + c0 + j;
+            if (k >= NE) break;
+            g.C[(size_t)k * g.ldc + f] = v[j];
           }
         }
       }
@@ -287,6 +347,6 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   __syncthreads();
   if (warp == 1) {
     fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
 }

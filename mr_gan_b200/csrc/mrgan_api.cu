@@ -67,7 +67,7 @@ struct mrgan_handle;
 namespace {
 int tc_setup(mrgan_handle* h);
 void tc_teardown(mrgan_handle* h);
-bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override);
+bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override, cudaStream_t st);
 void tc_params_changed(mrgan_handle* h, int fold, int net);
 int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g);
 }
@@ -80,6 +80,8 @@ struct mrgan_handle {
   std::vector<NetLayout> net[2];
   std::vector<FoldBuffers> fb;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;        // dW (+Adam) kernels run here, concurrently with the latency-bound dX chain
+  cudaEvent_t ev_pool[16] = {nullptr}; int ev_next = 0;
   char* arena = nullptr; size_t arena_bytes = 0;
   float *P = nullptr, *Mo = nullptr, *Vo = nullptr, *Gr = nullptr; long long n_flat = 0;
   FoldState* d_folds = nullptr; std::vector<FoldState> h_folds;
@@ -370,19 +372,33 @@ void init_ones(mrgan_handle* h) {
 }
 
 // ------------------------------------------------------------------ launch sequences
-void launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override) {
+void launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override, cudaStream_t st = nullptr) {
+  if (!st) st = h->stream;
   const OpInfo& oi = h->ops[op];
   int M = oi.maxM;
   if (rows_override > 0 && !oi.at) M = rows_override;
   const GemmDesc* d = h->d_descs + (size_t)op * h->nf + f0;
 #ifdef MRGAN_WITH_TC
-  if (h->cfg.precision == MRGAN_PREC_TF32 && tc_launch_gemm(h, op, f0, nfl, rows_override)) return;
+  if (h->cfg.precision == MRGAN_PREC_TF32 && tc_launch_gemm(h, op, f0, nfl, rows_override, st)) return;
 #endif
   dim3 grid((oi.maxN + 63) / 64, (M + 63) / 64, nfl);
-  if (!oi.at && !oi.bt) k_gemm_simt<false, false><<<grid, 256, 0, h->stream>>>(d, h->d_folds, rows_override);
-  else if (!oi.at && oi.bt) k_gemm_simt<false, true><<<grid, 256, 0, h->stream>>>(d, h->d_folds, rows_override);
-  else k_gemm_simt<true, false><<<grid, 256, 0, h->stream>>>(d, h->d_folds, rows_override);
+  if (!oi.at && !oi.bt) k_gemm_simt<false, false><<<grid, 256, 0, st>>>(d, h->d_folds, rows_override);
+  else if (!oi.at && oi.bt) k_gemm_simt<false, true><<<grid, 256, 0, st>>>(d, h->d_folds, rows_override);
+  else k_gemm_simt<true, false><<<grid, 256, 0, st>>>(d, h->d_folds, rows_override);
   h->launches++;
+}
+
+// side stream: fork = "side waits for everything enqueued on main so far", join = the reverse.
+// Works both eagerly and under stream capture (where it becomes graph edges).
+void fork_side(mrgan_handle* h) {
+  cudaEvent_t e = h->ev_pool[h->ev_next++ & 15];
+  cudaEventRecord(e, h->stream);
+  cudaStreamWaitEvent(h->side, e, 0);
+}
+void join_side(mrgan_handle* h) {
+  cudaEvent_t e = h->ev_pool[h->ev_next++ & 15];
+  cudaEventRecord(e, h->side);
+  cudaStreamWaitEvent(h->stream, e, 0);
 }
 
 int max_D(const mrgan_handle* h, int f0, int nfl) {
@@ -435,8 +451,10 @@ void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) 
   h->launches++;
   for (int l = 6; l >= 1; --l) {      // dX first: it reads W_l, which the fused-Adam dW epilogue overwrites
     if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
-    launch_gemm(h, OP_DW1 + l - 1, f0, nfl, 0);
+    fork_side(h);                     // dW_l (+Adam) streams HBM on the side while main continues the dX chain
+    launch_gemm(h, OP_DW1 + l - 1, f0, nfl, 0, h->side);
   }
+  join_side(h);
   launch_adam(h, f0, nfl, 0);
 }
 
@@ -452,12 +470,16 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   for (int l = 5; l >= 2; --l) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, B);
   launch_gemm(h, OP_DX1G, f0, nfl, 0);
   launch_gemm(h, OP_GX3, f0, nfl, 0);
-  launch_gemm(h, OP_GW3, f0, nfl, 0);
+  fork_side(h);
+  launch_gemm(h, OP_GW3, f0, nfl, 0, h->side);
   launch_gemm(h, OP_GX2, f0, nfl, 0);
-  launch_gemm(h, OP_GW2, f0, nfl, 0);
+  fork_side(h);
+  launch_gemm(h, OP_GW2, f0, nfl, 0, h->side);
   k_bn_bwd<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, c.precision == MRGAN_PREC_TF32);
   h->launches++;
-  launch_gemm(h, OP_GW1, f0, nfl, 0);
+  fork_side(h);
+  launch_gemm(h, OP_GW1, f0, nfl, 0, h->side);
+  join_side(h);
   launch_adam(h, f0, nfl, 1);
 }
 
@@ -473,8 +495,10 @@ void enqueue_nn_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage, in
   h->launches++;
   for (int l = 6; l >= 1; --l) {
     if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
-    launch_gemm(h, OP_DW1 + l - 1, f0, nfl, 0);
+    fork_side(h);
+    launch_gemm(h, OP_DW1 + l - 1, f0, nfl, 0, h->side);
   }
+  join_side(h);
   launch_adam(h, f0, nfl, 0);
 }
 
@@ -601,7 +625,14 @@ bool make_map(EncodeTiledFn fn, CUtensorMap* m, const float* base, int cols, int
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-size_t tc_smem_bytes(int bn) { return 1024 + (size_t)TC_STAGES * (128 * 128 + (size_t)bn * 128) + 256; }
+// forward / dX: 4-stage ring, up to 256 accumulator columns, 1 CTA per SM
+// dW (+ fused Adam): 2-stage ring (the contraction is only ~150 rows = 5 blocks), 128 columns, 2 CTAs per SM
+#define TC_FWD_STAGES 4
+#define TC_DW_STAGES 2
+#define K_TC_FWD k_gemm_tc<true, false, TC_FWD_STAGES, 256, 1>
+#define K_TC_DX k_gemm_tc<false, false, TC_FWD_STAGES, 256, 1>
+#define K_TC_DW k_gemm_tc<true, true, TC_DW_STAGES, 128, 2>
+size_t tc_smem_bytes(int bn, int stages) { return 1024 + (size_t)stages * (128 * 128 + (size_t)bn * 128) + 256; }
 
 int tc_setup(mrgan_handle* h);
 
@@ -614,10 +645,9 @@ EncodeTiledFn tc_encoder() {
 }
 
 void tc_set_smem_attr() {
-  const int max_smem = (int)tc_smem_bytes(256);
-  cudaFuncSetAttribute(k_gemm_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  cudaFuncSetAttribute(k_gemm_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  cudaFuncSetAttribute(k_gemm_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(K_TC_FWD, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
+  cudaFuncSetAttribute(K_TC_DX, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
+  cudaFuncSetAttribute(K_TC_DW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(128, TC_DW_STAGES));
 }
 
 // fills the tcgen05 view of one GEMM (shapes in the fp32 path's convention); mode 0 fwd, 1 dX, 2 dW
@@ -649,10 +679,9 @@ int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g) {
   CK(cudaMemcpyAsync(d, &t, sizeof(t), cudaMemcpyHostToDevice, h->stream));
   tc_set_smem_attr();
   dim3 grid((t.ME + 127) / 128, (t.NE + t.bn - 1) / t.bn, 1);
-  const size_t smem = tc_smem_bytes(t.bn);
-  if (mode == 0) k_gemm_tc<true, false><<<grid, 192, smem, h->stream>>>(d, h->d_folds, 0, h->hp);
-  else if (mode == 1) k_gemm_tc<false, false><<<grid, 192, smem, h->stream>>>(d, h->d_folds, 0, h->hp);
-  else k_gemm_tc<true, true><<<grid, 192, smem, h->stream>>>(d, h->d_folds, 0, h->hp);
+  if (mode == 0) K_TC_FWD<<<grid, 192, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp);
+  else if (mode == 1) K_TC_DX<<<grid, 192, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp);
+  else K_TC_DW<<<grid, 192, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp);
   h->launches++;
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(d);
@@ -710,17 +739,16 @@ void tc_teardown(mrgan_handle* h) {
 
 void tc_params_changed(mrgan_handle*, int, int) {}   // fp32 master weights are the MMA operands: nothing to refresh
 
-bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override) {
+bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override, cudaStream_t st) {
   const OpInfo& oi = h->ops[op];
   const int bn = h->tc_bn[op];
   int NE = h->tc_maxNE[op];
   if (rows_override > 0 && !oi.at) NE = rows_override;
   dim3 grid((h->tc_maxME[op] + 127) / 128, (NE + bn - 1) / bn, nfl);
   const TcOp* d = h->d_tcops + (size_t)op * h->nf + f0;
-  const size_t smem = tc_smem_bytes(bn);
-  if (!oi.at && !oi.bt) k_gemm_tc<true, false><<<grid, 192, smem, h->stream>>>(d, h->d_folds, rows_override, h->hp);
-  else if (!oi.at && oi.bt) k_gemm_tc<false, false><<<grid, 192, smem, h->stream>>>(d, h->d_folds, rows_override, h->hp);
-  else k_gemm_tc<true, true><<<grid, 192, smem, h->stream>>>(d, h->d_folds, 0, h->hp);
+  if (!oi.at && !oi.bt) K_TC_FWD<<<grid, 192, tc_smem_bytes(bn, TC_FWD_STAGES), st>>>(d, h->d_folds, rows_override, h->hp);
+  else if (!oi.at && oi.bt) K_TC_DX<<<grid, 192, tc_smem_bytes(bn, TC_FWD_STAGES), st>>>(d, h->d_folds, rows_override, h->hp);
+  else K_TC_DW<<<grid, 192, tc_smem_bytes(bn, TC_DW_STAGES), st>>>(d, h->d_folds, 0, h->hp);
   h->launches++;
   return true;
 }
@@ -812,6 +840,8 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   Arena real; real.base = h->arena;
   layout_buffers(h, real);
   bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 16 && ok; ++i) ok = cudaEventCreateWithFlags(&h->ev_pool[i], cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
   ok = ok && cudaMallocHost(&h->h_epoch_stats, (size_t)h->nf * 8 * sizeof(float)) == cudaSuccess;
   ok = ok && cudaMallocHost(&h->h_scratch, 64 * sizeof(float)) == cudaSuccess;
@@ -852,6 +882,8 @@ int mrgan_destroy(mrgan_handle* h) {
   }
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int i = 0; i < 16; ++i) if (h->ev_pool[i]) cudaEventDestroy(h->ev_pool[i]);
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return MRGAN_OK;
@@ -1288,6 +1320,56 @@ int mrgan_debug_gemm(mrgan_handle* h, int mode, int M, int N, int K, const float
   cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dd);
   if (e != cudaSuccess) return fail(h, MRGAN_ERR_CUDA, std::string("debug_gemm: ") + cudaGetErrorString(e));
   return MRGAN_OK;
+}
+
+int mrgan_debug_gemm_time(mrgan_handle* h, int mode, int M, int N, int K, int groups, int reps, float* ms) {
+  if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
+  if (mode < 0 || mode > 2 || M < 1 || N < 1 || K < 1 || groups < 1 || reps < 1 || !ms) return fail(h, MRGAN_ERR_ARG, "debug_gemm_time: bad argument");
+#ifndef MRGAN_WITH_TC
+  return fail(h, MRGAN_ERR_ARG, "library built without the tcgen05 kernels");
+#else
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = finish_pending(h); if (rc) return rc;
+  const int ar = mode == 2 ? K : M, ac = mode == 2 ? M : K;
+  const int br = mode == 1 ? N : K, bc = mode == 1 ? K : N;
+  const int lda = pitch4(ac), ldb = pitch4(bc), ldc = pitch4(N);
+  const size_t sa = (size_t)ar * lda, sb = (size_t)br * ldb, sc = (size_t)M * ldc;
+  float* buf = nullptr;
+  CK(cudaMalloc(&buf, (sa + sb + sc) * groups * 4));
+  CK(cudaMemsetAsync(buf, 0, (sa + sb + sc) * groups * 4, h->stream));
+  EncodeTiledFn fn = tc_encoder();
+  if (!fn) return fail(h, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+  std::vector<TcOp> ops(groups);
+  memset(ops.data(), 0, sizeof(TcOp) * groups);
+  for (int g = 0; g < groups; ++g) {
+    float* A = buf + (sa + sb + sc) * g; float* B = A + sa; float* C = B + sb;
+    GemmDesc d = make_desc(A, lda, B, ldb, C, ldc, M, N, K, mode == 0 ? EPI_FWD : (mode == 1 ? EPI_DX : EPI_STORE), ACT_NONE, 0);
+    if (!tc_fill_op(fn, ops[g], d, mode)) return fail(h, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  }
+  TcOp* dops = nullptr;
+  CK(cudaMalloc(&dops, sizeof(TcOp) * groups));
+  CK(cudaMemcpyAsync(dops, ops.data(), sizeof(TcOp) * groups, cudaMemcpyHostToDevice, h->stream));
+  tc_set_smem_attr();
+  const TcOp& t = ops[0];
+  dim3 grid((t.ME + 127) / 128, (t.NE + t.bn - 1) / t.bn, groups);
+  auto once = [&]() {
+    if (mode == 0) K_TC_FWD<<<grid, 192, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp);
+    else if (mode == 1) K_TC_DX<<<grid, 192, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp);
+    else K_TC_DW<<<grid, 192, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp);
+  };
+  once();
+  CK(cudaEventRecord(h->ev0, h->stream));
+  for (int i = 0; i < reps; ++i) once();
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  float t_ms = 0.f;
+  CK(cudaEventElapsedTime(&t_ms, h->ev0, h->ev1));
+  *ms = t_ms / reps;
+  h->launches += reps + 1;
+  cudaFree(buf); cudaFree(dops);
+  return MRGAN_OK;
+#endif
 }
 
 int64_t mrgan_kernel_launches(const mrgan_handle* h) { return h ? h->launches : -1; }
