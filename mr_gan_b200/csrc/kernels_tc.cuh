@@ -120,8 +120,9 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
 // STAGES: depth of the TMA->MMA ring; TMEM_COLS: accumulator columns allocated (power of 2 >= bn);
 // MINB: CTAs per SM the register allocation must allow (dW uses 2 so that one CTA's Adam epilogue
 // streams HBM while the other loads operands and runs its MMAs).
-template <bool A_MN, bool B_MN, int STAGES, int TMEM_COLS, int MINB>
-__global__ void __launch_bounds__(192, MINB)
+// EPW: epilogue warps (4 or 8; with 8 the accumulator columns are split between two warp groups).
+template <bool A_MN, bool B_MN, int STAGES, int TMEM_COLS, int MINB, int EPW>
+__global__ void __launch_bounds__(64 + 32 * EPW, MINB)
 k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_override, AdamHyper hp) {
   using namespace tc;
   const TcOp& op = ops[blockIdx.z];
@@ -209,14 +210,16 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
       mma_commit(tmem_full);              // accumulator complete
     }
   } else {
-    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+    // ===================== epilogue (EPW warps; a warp may only touch TMEM lanes 32*(warp%4)..+31) =====================
     const int lane_base = 32 * (warp & 3);
+    const int chalf = (EPW == 8) ? (((min(bn, NE - n0) + 1) / 2 + 15) & ~15) : bn;   // columns per warp group
+    const int cbeg = (EPW == 8) ? ((warp - 2) >> 2) * chalf : 0;
     const int f = m0 + lane_base + lane;                  // this thread's feature index (MMA-M)
     const bool f_ok = f < ME;
     const GemmDesc g = op.g;             // by value: descriptor fields must not be re-read from HBM around every store
     const int epi = op.epi;
     float* const adamP = op.P; float* const adamM = op.Mo; float* const adamV = op.Vo;
-    const int ncols = min(bn, NE - n0);
+    const int ncols = min(min(bn, NE - n0), cbeg + chalf);      // this warp's column range is [cbeg, ncols)
     const uint32_t trow = tmem_base + ((uint32_t)lane_base << 16);
     uint32_t key0 = 0, key1 = 0, step = 0;
     float lr_t = 0.f;
@@ -256,11 +259,11 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         }
       };
       float pwA[8], pmA[8], pvA[8], pwB[8], pmB[8], pvB[8], v[8];
-      fetch(0, pwA, pmA, pvA);
-      fetch(8, pwB, pmB, pvB);
+      fetch(cbeg, pwA, pmA, pvA);
+      fetch(cbeg + 8, pwB, pmB, pvB);
       mbar_wait(tmem_full, 0);
       fence_after();
-      for (int c0 = 0; c0 < ncols; c0 += 16) {
+      for (int c0 = cbeg; c0 < ncols; c0 += 16) {
         tmem_ld8(trow + (uint32_t)c0, v);
         apply(c0, v, pwA, pmA, pvA);
         if (c0 + 16 < ncols) fetch(c0 + 16, pwA, pmA, pvA);
@@ -289,10 +292,10 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         }
       };
       float avA[16], avB[16], v[16];
-      fetch(0, avA);
+      fetch(cbeg, avA);
       mbar_wait(tmem_full, 0);
       fence_after();
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
+      for (int c0 = cbeg; c0 < ncols; c0 += 32) {
         tmem_ld16(trow + (uint32_t)c0, v);
         if (c0 + 16 < ncols) fetch(c0 + 16, avB);
         apply(c0, v, avA);
@@ -305,7 +308,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
     } else {
       mbar_wait(tmem_full, 0);
       fence_after();
-      for (int c0 = 0; c0 < ncols; c0 += 16) {
+      for (int c0 = cbeg; c0 < ncols; c0 += 16) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c0, v);                   // warp-collective: every lane takes part
         if (!f_ok) continue;

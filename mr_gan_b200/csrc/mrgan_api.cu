@@ -629,9 +629,11 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // dW (+ fused Adam): 2-stage ring (the contraction is only ~150 rows = 5 blocks), 128 columns, 2 CTAs per SM
 #define TC_FWD_STAGES 4
 #define TC_DW_STAGES 2
-#define K_TC_FWD k_gemm_tc<true, false, TC_FWD_STAGES, 256, 1>
-#define K_TC_DX k_gemm_tc<false, false, TC_FWD_STAGES, 256, 1>
-#define K_TC_DW k_gemm_tc<true, true, TC_DW_STAGES, 128, 2>
+#define TC_FWD_THREADS (64 + 32 * 8)
+#define TC_DW_THREADS (64 + 32 * 4)
+#define K_TC_FWD k_gemm_tc<true, false, TC_FWD_STAGES, 256, 1, 8>
+#define K_TC_DX k_gemm_tc<false, false, TC_FWD_STAGES, 256, 1, 8>
+#define K_TC_DW k_gemm_tc<true, true, TC_DW_STAGES, 128, 2, 4>
 size_t tc_smem_bytes(int bn, int stages) { return 1024 + (size_t)stages * (128 * 128 + (size_t)bn * 128) + 256; }
 
 int tc_setup(mrgan_handle* h);
@@ -679,9 +681,9 @@ int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g) {
   CK(cudaMemcpyAsync(d, &t, sizeof(t), cudaMemcpyHostToDevice, h->stream));
   tc_set_smem_attr();
   dim3 grid((t.ME + 127) / 128, (t.NE + t.bn - 1) / t.bn, 1);
-  if (mode == 0) K_TC_FWD<<<grid, 192, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp);
-  else if (mode == 1) K_TC_DX<<<grid, 192, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp);
-  else K_TC_DW<<<grid, 192, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp);
+  if (mode == 0) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp);
+  else if (mode == 1) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp);
+  else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp);
   h->launches++;
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(d);
@@ -746,9 +748,9 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
   if (rows_override > 0 && !oi.at) NE = rows_override;
   dim3 grid((h->tc_maxME[op] + 127) / 128, (NE + bn - 1) / bn, nfl);
   const TcOp* d = h->d_tcops + (size_t)op * h->nf + f0;
-  if (!oi.at && !oi.bt) K_TC_FWD<<<grid, 192, tc_smem_bytes(bn, TC_FWD_STAGES), st>>>(d, h->d_folds, rows_override, h->hp);
-  else if (!oi.at && oi.bt) K_TC_DX<<<grid, 192, tc_smem_bytes(bn, TC_FWD_STAGES), st>>>(d, h->d_folds, rows_override, h->hp);
-  else K_TC_DW<<<grid, 192, tc_smem_bytes(bn, TC_DW_STAGES), st>>>(d, h->d_folds, 0, h->hp);
+  if (!oi.at && !oi.bt) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(bn, TC_FWD_STAGES), st>>>(d, h->d_folds, rows_override, h->hp);
+  else if (!oi.at && oi.bt) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(bn, TC_FWD_STAGES), st>>>(d, h->d_folds, rows_override, h->hp);
+  else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(bn, TC_DW_STAGES), st>>>(d, h->d_folds, 0, h->hp);
   h->launches++;
   return true;
 }
@@ -1353,9 +1355,9 @@ int mrgan_debug_gemm_time(mrgan_handle* h, int mode, int M, int N, int K, int gr
   const TcOp& t = ops[0];
   dim3 grid((t.ME + 127) / 128, (t.NE + t.bn - 1) / t.bn, groups);
   auto once = [&]() {
-    if (mode == 0) K_TC_FWD<<<grid, 192, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp);
-    else if (mode == 1) K_TC_DX<<<grid, 192, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp);
-    else K_TC_DW<<<grid, 192, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp);
+    if (mode == 0) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp);
+    else if (mode == 1) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp);
+    else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp);
   };
   once();
   CK(cudaEventRecord(h->ev0, h->stream));
