@@ -353,3 +353,173 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
 }
+
+// ====================================================================================================
+// k_dw_adam_tc -- dW (+db) on tcgen05 with the Keras-2.0.9 Adam update fused in, optimizer state staged by TMA.
+//
+// grad(Waug_l)[k, n] = sum_r A[r, k] dZ[r, n]  as  D[n (128 lanes), k (128 columns)], then for the same tile
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; W -= lr_t m / (sqrt(v) + eps)              
+// W, m and v tiles never go through the LSU: one thread streams them HBM -> smem -> HBM in [KC rows x 128 cols]
+// chunks with cp.async.bulk.tensor (full 128-byte lines, deep queues); the 4 epilogue warps combine each chunk
+// with the matching 8 accumulator columns from TMEM in shared memory.  24 B per parameter of HBM traffic, which
+// is the algorithmic minimum for Adam; the gradient never leaves the SM.
+//   smem: 2 operand stages x 32 KB + NB chunk buffers x (3 x KC x 512 B); 2 CTAs per SM.
+// ====================================================================================================
+struct alignas(64) TcAdamOp {
+  CUtensorMap mapA, mapB;          // dZ[r, n] and A[r, k], both MN-major operands (32-byte-atom 128B swizzle)
+  CUtensorMap mapP, mapM, mapV;    // Waug, m, v as [rows k, cols n], box = 128 cols x KC rows, no swizzle
+  int ME, NE, KE;                  // out-features n, in-features(+1) k, contraction rows r
+  int fold;
+};
+
+#define TCA_KC 8
+#define TCA_NB 3
+
+namespace tc {
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"((uint64_t)map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+}  // namespace tc
+
+__global__ void __launch_bounds__(192, 2)
+k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, AdamHyper hp) {
+  using namespace tc;
+  constexpr int STAGES = 2, KC = TCA_KC, NB = TCA_NB;
+  constexpr uint32_t STAGE_BYTES = 2 * 128 * 128;            // A (4 x 4 KB blocks) + B (4 x 4 KB blocks)
+  constexpr uint32_t ARR_BYTES = KC * 128 * 4;               // one array (W, m or v) of one chunk
+  const TcAdamOp& op = ops[blockIdx.z];
+  const int ME = op.ME, NE = op.NE, KE = op.KE;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;     // n-feature tile (lanes), k-feature tile (columns)
+  if (m0 >= ME || n0 >= NE) return;
+
+  extern __shared__ __align__(1024) uint8_t smem_dyn[];
+  uint8_t* smem = smem_dyn;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();                // swizzled TMA tiles need 1024-byte alignment
+  uint8_t* cbuf = smem + STAGES * STAGE_BYTES;                // [NB][3][KC][128] floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cbuf + NB * 3 * ARR_BYTES);
+  uint64_t* full = bars;                       // [STAGES]   operands landed
+  uint64_t* empty = bars + STAGES;             // [STAGES]   operands consumed
+  uint64_t* tmem_full = bars + 2 * STAGES;     //            accumulator complete
+  uint64_t* cfull = bars + 2 * STAGES + 1;     // [NB]       optimizer-state chunk landed
+  uint64_t* cdone = cfull + NB;                // [NB]       chunk updated in smem (128 arrivals)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(cdone + NB);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (KE + TC_KBLK - 1) / TC_KBLK;
+  const int ncols = min(128, NE - n0);
+  const int nch = (ncols + KC - 1) / KC;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_map(&op.mapA); prefetch_map(&op.mapB); prefetch_map(&op.mapP); prefetch_map(&op.mapM); prefetch_map(&op.mapV);
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    for (int b = 0; b < NB; ++b) { mbar_init(&cfull[b], 1); mbar_init(&cdone[b], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---- DMA thread: optimizer-state chunks first (they do not depend on the MMA), then the operands ----
+      auto load_chunk = [&](int c) {
+        const int b = c % NB;
+        uint8_t* dst = cbuf + (size_t)b * 3 * ARR_BYTES;
+        mbar_expect_tx(&cfull[b], 3 * ARR_BYTES);
+        tma_load_2d(&op.mapP, &cfull[b], dst, m0, n0 + c * KC);
+        tma_load_2d(&op.mapM, &cfull[b], dst + ARR_BYTES, m0, n0 + c * KC);
+        tma_load_2d(&op.mapV, &cfull[b], dst + 2 * ARR_BYTES, m0, n0 + c * KC);
+      };
+      for (int c = 0; c < NB && c < nch; ++c) load_chunk(c);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
+        uint8_t* sb = sa + 128 * 128;
+        const int k0 = kb * TC_KBLK;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * 4096, m0 + 32 * b, k0);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * 4096, n0 + 32 * b, k0);
+      }
+      // ---- write-back of updated chunks and refill of the freed buffers ----
+      for (int c = 0; c < nch; ++c) {
+        const int b = c % NB;
+        mbar_wait(&cdone[b], (uint32_t)(c / NB) & 1u);
+        const uint8_t* src = cbuf + (size_t)b * 3 * ARR_BYTES;
+        tma_store_2d(&op.mapP, src, m0, n0 + c * KC);
+        tma_store_2d(&op.mapM, src + ARR_BYTES, m0, n0 + c * KC);
+        tma_store_2d(&op.mapV, src + 2 * ARR_BYTES, m0, n0 + c * KC);
+        bulk_commit();
+        if (c + NB < nch) { bulk_wait_read0(); load_chunk(c + NB); }
+      }
+      bulk_wait_read0();
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(&full[s], ph);
+        fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES), sb = sa + 128 * 128;
+#pragma unroll
+        for (int k = 0; k < TC_KBLK / 8; ++k)
+          mma_tf32(tmem_base, smem_desc(sa + k * 1024u, 4096u, 512u, 1u), smem_desc(sb + k * 1024u, 4096u, 512u, 1u), idesc,
+                   (kb > 0 || k > 0) ? 1u : 0u);
+        mma_commit(&empty[s]);
+      }
+      mma_commit(tmem_full);
+    }
+  } else {
+    // ---- epilogue: 4 warps, thread = output feature n (TMEM lane = smem column) ----
+    const int lane_base = 32 * (warp & 3);
+    const int nl = lane_base + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)lane_base << 16);
+    const float lr_t = folds[op.fold].lr_t;
+    const float b1 = hp.b1, b2 = hp.b2, c1 = 1.0f - hp.b1, c2 = 1.0f - hp.b2, eps = hp.eps;
+    mbar_wait(tmem_full, 0);
+    fence_after();
+    for (int c = 0; c < nch; ++c) {
+      const int b = c % NB;
+      float* sP = reinterpret_cast<float*>(cbuf + (size_t)b * 3 * ARR_BYTES);
+      float* sM = sP + KC * 128;
+      float* sV = sM + KC * 128;
+      float g[KC];
+      tmem_ld8(trow + (uint32_t)(c * KC), g);
+      mbar_wait(&cfull[b], (uint32_t)(c / NB) & 1u);
+#pragma unroll
+      for (int j = 0; j < KC; ++j) {
+        const int i = j * 128 + nl;
+        const float m = fmaf(b1, sM[i], c1 * g[j]), v = fmaf(b2, sV[i], c2 * g[j] * g[j]);
+        sM[i] = m; sV[i] = v;
+        sP[i] -= lr_t * __fdividef(m, sqrtf(v) + eps);
+      }
+      fence_proxy_async();              // generic-proxy writes -> visible to the bulk store
+      mbar_arrive(&cdone[b]);
+    }
+  }
+
+  fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+  }
+}

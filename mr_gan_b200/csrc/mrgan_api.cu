@@ -103,6 +103,8 @@ struct mrgan_handle {
   TcOp* d_tcops = nullptr;            // [NUM_OPS][nf] tensor maps + epilogue descriptors
   int tc_bn[NUM_OPS] = {0}, tc_maxME[NUM_OPS] = {0}, tc_maxNE[NUM_OPS] = {0};
   bool tc_fused_adam = true;          // dW epilogue applies Adam in place (no gradient round trip)
+  bool tc_adam_tma = true;            // ... with W/m/v staged through smem by TMA (k_dw_adam_tc) instead of the LSU
+  TcAdamOp* d_tcadam = nullptr;       // [NUM_OPS][nf]
   AdamRange* d_ranges_tc[2] = {nullptr, nullptr};   // what is left for k_adam: BN gamma/beta (G), nothing (D)
 #endif
 };
@@ -612,13 +614,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 // 2D fp32 tensor [rows, cols] with `pitch` floats per row; box = 32 columns (one 128B swizzle row) x box_rows
 bool make_map(EncodeTiledFn fn, CUtensorMap* m, const float* base, int cols, int rows, int pitch, int box_rows,
-              bool mn_major) {
+              bool mn_major, int box_cols = 32) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
-  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1u, 1u};
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE,
+            box_cols != 32 ? CU_TENSOR_MAP_SWIZZLE_NONE : (mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -634,6 +637,7 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 #define K_TC_FWD k_gemm_tc<true, false, TC_FWD_STAGES, 256, 1, 8>
 #define K_TC_DX k_gemm_tc<false, false, TC_FWD_STAGES, 256, 1, 8>
 #define K_TC_DW k_gemm_tc<true, true, TC_DW_STAGES, 128, 2, 4>
+#define TCA_SMEM_BYTES (2 * 2 * 128 * 128 + TCA_NB * 3 * TCA_KC * 128 * 4 + 256)
 size_t tc_smem_bytes(int bn, int stages) { return 1024 + (size_t)stages * (128 * 128 + (size_t)bn * 128) + 256; }
 
 int tc_setup(mrgan_handle* h);
@@ -650,6 +654,7 @@ void tc_set_smem_attr() {
   cudaFuncSetAttribute(K_TC_FWD, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
   cudaFuncSetAttribute(K_TC_DX, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
   cudaFuncSetAttribute(K_TC_DW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(128, TC_DW_STAGES));
+  cudaFuncSetAttribute(k_dw_adam_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCA_SMEM_BYTES);
 }
 
 // fills the tcgen05 view of one GEMM (shapes in the fp32 path's convention); mode 0 fwd, 1 dX, 2 dW
@@ -716,6 +721,26 @@ int tc_setup(mrgan_handle* h) {
   }
   if (cudaMalloc(&h->d_tcops, ops.size() * sizeof(TcOp)) != cudaSuccess) return fail(nullptr, MRGAN_ERR_CUDA, "cudaMalloc tc ops");
   cudaMemcpy(h->d_tcops, ops.data(), ops.size() * sizeof(TcOp), cudaMemcpyHostToDevice);
+  if (h->tc_fused_adam && h->tc_adam_tma) {
+    std::vector<TcAdamOp> aops((size_t)NUM_OPS * nf);
+    memset(aops.data(), 0, aops.size() * sizeof(TcAdamOp));
+    for (int op = 0; op < NUM_OPS; ++op) {
+      const OpInfo& oi = h->ops[op];
+      if (!oi.used || !oi.at) continue;
+      for (int f = 0; f < nf; ++f) {
+        const TcOp& t = ops[(size_t)op * nf + f];
+        TcAdamOp& a = aops[(size_t)op * nf + f];
+        a.mapA = t.mapA; a.mapB = t.mapB; a.ME = t.ME; a.NE = t.NE; a.KE = t.KE; a.fold = t.g.fold;
+        // W / m / v as [rows = in+1, cols = out] with the tensor's pitch; box 128 cols x KC rows, clipped at the logical extents
+        if (!make_map(fn, &a.mapP, t.P, t.ME, t.NE, t.g.ldc, TCA_KC, false, 128) ||
+            !make_map(fn, &a.mapM, t.Mo, t.ME, t.NE, t.g.ldc, TCA_KC, false, 128) ||
+            !make_map(fn, &a.mapV, t.Vo, t.ME, t.NE, t.g.ldc, TCA_KC, false, 128))
+          return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled (optimizer state) failed");
+      }
+    }
+    if (cudaMalloc(&h->d_tcadam, aops.size() * sizeof(TcAdamOp)) != cudaSuccess) return fail(nullptr, MRGAN_ERR_CUDA, "cudaMalloc tc adam ops");
+    cudaMemcpy(h->d_tcadam, aops.data(), aops.size() * sizeof(TcAdamOp), cudaMemcpyHostToDevice);
+  }
   // what is left for the flat Adam kernel when dW applies Adam itself
   std::vector<AdamRange> r0(nf), r1(nf);
   for (int f = 0; f < nf; ++f) {
@@ -735,6 +760,7 @@ int tc_setup(mrgan_handle* h) {
 
 void tc_teardown(mrgan_handle* h) {
   if (h->d_tcops) cudaFree(h->d_tcops);
+  if (h->d_tcadam) cudaFree(h->d_tcadam);
   for (int n = 0; n < 2; ++n) if (h->d_ranges_tc[n]) cudaFree(h->d_ranges_tc[n]);
   h->d_tcops = nullptr;
 }
@@ -750,6 +776,7 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
   const TcOp* d = h->d_tcops + (size_t)op * h->nf + f0;
   if (!oi.at && !oi.bt) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(bn, TC_FWD_STAGES), st>>>(d, h->d_folds, rows_override, h->hp);
   else if (!oi.at && oi.bt) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(bn, TC_FWD_STAGES), st>>>(d, h->d_folds, rows_override, h->hp);
+  else if (h->d_tcadam) k_dw_adam_tc<<<grid, 192, TCA_SMEM_BYTES, st>>>(h->d_tcadam + (size_t)op * h->nf + f0, h->d_folds, h->hp);
   else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(bn, TC_DW_STAGES), st>>>(d, h->d_folds, 0, h->hp);
   h->launches++;
   return true;
