@@ -318,3 +318,53 @@ def test_tf32_tensor_core_path_layer_by_layer_against_fp32_path():
         for i, (x, y, p0) in enumerate(zip(a[net], b[net], init)):
             upd = max(np.sqrt(np.mean((x - p0) ** 2)), 1e-4)
             assert np.sqrt(np.mean((x - y) ** 2)) <= 0.35 * upd, (net, i, np.sqrt(np.mean((x - y) ** 2)), upd)
+
+
+def test_fp32_path_tracks_oracle_over_epochs_at_reference_batch():
+    """Trajectory parity at the reference's batch size: 3 epochs x 12 batches (36 D+G step pairs, B=50) of the
+    CUDA-graph epoch path vs the oracle's restatement of mr_gan.py:183-223 with the replayed noise stream."""
+    D, B, ntr, nte = 60, 50, 600, 150
+    f = _make_fold(D, ntr, nte, 11, pl=2.0)
+    key = philox.fold_key(4, 0)
+    idx = [fold_loop.epoch_indices(f['rng'], ntr, f['lab_rows']) for _ in range(3)]
+    m = O.GanOracle(f['pD'], f['pG'])
+    with FoldGroup([(D, ntr, nte, _key64(key))], precision="fp32") as fg:
+        fg.set_params(0, 0, f['pD'])
+        fg.set_params(0, 1, f['pG'])
+        fg.load_fold(0, f['Xtr'], f['ytr'], f['Xte'], f['yte'])
+        step = 0
+        for e in range(3):
+            got = fg.train_epoch(*[a[None, :] for a in idx[e]])[0]
+            st, step = fold_loop.train_epoch(m, f['Xtr'].astype(np.float64), f['ytr'], *idx[e], key, step, B=B)
+            want = st.mean(axis=0)
+            np.testing.assert_allclose(got[[0, 1]], want[[0, 1]], rtol=1e-3)
+            np.testing.assert_allclose(got[3], want[3], rtol=1e-2)    # feature-matching loss: tiny, chaotic along a trajectory
+            assert abs(got[2] - want[2]) <= 1.0 / ntr + 1e-6
+            # fp32 vs float64 after tens of steps: a borderline test sample may flip
+            assert abs(got[4] - fold_loop.eval_batches(m, f['Xte'].astype(np.float64), f['yte'], B=B)) <= 3.0 / nte + 1e-6
+        assert abs(fg.eval(0) - m.test_batch(f['Xte'].astype(np.float64), f['yte'])) <= 3.0 / nte + 1e-6
+        assert fg.counters(0) == (72, 72)
+
+
+def test_final_accuracy_tf32_vs_fp32_over_seed_set():
+    """north_star: final fold accuracy within +-0.5 pt over a fixed seed set.  Full-width folds (force+temperature,
+    D=1200, 6000/1200 rows, B=50) of the synthetic MREO-shape data, seeds {0..4} x 6 folds, 15 epochs each, trained
+    through the public drop-in API in both precisions with identical splits, initial weights, permutations and
+    noise keys; the fp32 path is tied to the oracle by the step / trajectory tests above."""
+    from mr_gan_b200.mr_gan import _kfold_jobs, dataset, train_gan_folds
+    acc = {}
+    for prec in ("tf32", "fp32"):
+        a = []
+        for seed in range(5):
+            X, y = dataset(modalities=2, seed=seed)
+            jobs = _kfold_jobs(X, y, seed, percentlabeled=8)
+            a += [1.0 - e for e in train_gan_folds(jobs, epochs=15, seed=seed, precision=prec)]
+        acc[prec] = np.array(a)
+    print("accuracy per fold tf32:", np.round(acc["tf32"], 4), "\nfp32:", np.round(acc["fp32"], 4))
+    print("mean accuracy tf32 %.4f fp32 %.4f" % (acc["tf32"].mean(), acc["fp32"].mean()))
+    assert 0.3 < acc["fp32"].mean() < 0.995                      # the task is neither chance nor trivial
+    assert abs(acc["tf32"].mean() - acc["fp32"].mean()) <= 0.005
+    # single folds are chaotic trajectories of a GAN at 8 % labels (one fold may differ by several points either
+    # way); the paired differences must not be biased
+    d = acc["tf32"] - acc["fp32"]
+    assert abs(np.median(d)) <= 0.01 and np.abs(d).mean() <= 0.04
