@@ -141,3 +141,41 @@ def test_product_never_imports_the_oracle():
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
     code = "import sys; import mr_gan_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_real_data_loader_and_librosa_free_logmel(tmp_path):
+    """dataset() on files in the processed-pickle format of processdata.py:91 (Python-2 protocol), and the numpy
+    restatement of librosa's melspectrogram / logamplitude (shape, scale and peak-position properties)."""
+    import pickle
+    from mr_gan_b200 import realdata
+    rng = np.random.default_rng(0)
+    fb = realdata.mel_filterbank()
+    assert fb.shape == (128, 1025) and (fb >= 0).all() and (fb.sum(axis=1) > 0).all()
+    centers = fb.argmax(axis=1)
+    assert (np.diff(centers) >= 0).all()                                  # monotone filter centres
+    sr, n = 48000, 9600                                                   # 0.2 s window, processdata.py:12
+    tone = np.sin(2 * np.pi * 3000.0 * np.arange(n) / sr)
+    S = realdata.melspectrogram(tone)
+    assert S.shape == (128, 1 + n // 512)                                 # 128 x 19 -> 2432 features (SURVEY.md 8)
+    peak_hz = (np.arange(1025) * sr / 2048.0)[fb[S[:, 9].argmax()].argmax()]
+    assert abs(peak_hz - 3000.0) < 150.0
+    L = realdata.logamplitude(S)
+    assert L.max() == 0.0 and L.min() >= -80.0
+    # tiny fake "MREO" set: 6 materials x 2 objects x 3 pokes, 0.1 s force/temperature, 0.05 s contact
+    for material in model.MATERIALS:
+        data = {}
+        for o in range(2):
+            data["%s_obj%d" % (material, o)] = {
+                'temperature': [list(rng.standard_normal(10)) for _ in range(3)],
+                'force0': [list(rng.standard_normal(10)) for _ in range(3)],
+                'force1': [list(rng.standard_normal(10)) for _ in range(3)],
+                'contact': [list(rng.standard_normal(2400)) for _ in range(3)]}
+        with open(realdata.processed_path(str(tmp_path), material, 0.1, 0.05), 'wb') as f:
+            pickle.dump(data, f, protocol=2)
+    widths = {0: 20, 1: 10, 2: 30, 3: 640, 4: 650, 5: 670, 6: 660}
+    for mod, w in widths.items():
+        X, y = mg.dataset(modalities=mod, forcetempTime=0.1, contactmicTime=0.05, data_dir=str(tmp_path))
+        assert X.shape == (36, w) and list(np.bincount(y)) == [6] * 6
+        assert w == synthetic.feature_width(mod, 0.1, 0.05)               # the synthetic generator has the same layout
+    objs = mg.dataset(modalities=2, forcetempTime=0.1, contactmicTime=0.05, leaveObjectOut=True, data_dir=str(tmp_path))
+    assert len(objs) == 12 and all(o['x'].shape == (3, 30) for o in objs.values())
