@@ -123,6 +123,16 @@ int  mrgan_epoch_result(mrgan_handle* h, mrgan_epoch_stats* stats);
 /* testerror on the full resident test set in one call, mr_gan.py:230 */
 int  mrgan_eval(mrgan_handle* h, int fold, float* err);
 
+/* Data-parallel large-batch mode (BASELINE.json config 5; the reference's batch is fixed at 50, mr_gan.py:78, so this
+ * is an extension): W processes, one GPU each, hold replicas of ONE set of folds; cfg.batch is the LOCAL batch, the
+ * global batch is W * cfg.batch.  After mrgan_dp_init every train call all-reduces (NCCL, in-stream, over
+ * NVLink / NVSwitch) the BatchNorm and feature-matching batch statistics and the flat gradient, so the W ranks
+ * compute exactly the single-GPU step at the global batch, including its noise stream.  Each rank passes its own
+ * slice of the global batch (rows [rank*batch, (rank+1)*batch) of every section).
+ *   mrgan_nccl_unique_id: 128 bytes from ncclGetUniqueId (call on rank 0, broadcast with any host transport). */
+int  mrgan_nccl_unique_id(void* id128);
+int  mrgan_dp_init(mrgan_handle* h, int rank, int world, const void* id128);
+
 /* mr_nn.py:114-118 twins (handle created with MRGAN_MODEL_NN):
  *   one model.fit batch: x[n,D], labels[n] -> {mse loss, accuracy}; n <= batch */
 int  mrnn_step(mrgan_handle* h, int fold, const float* x, const int32_t* labels, int n, float out[2]);

@@ -53,6 +53,8 @@ SYMBOLS = {
     "mrgan_train_epoch": (C.c_int, [_H, _ip, _ip, _ip, C.POINTER(EpochStats)]),
     "mrgan_epoch_result": (C.c_int, [_H, C.POINTER(EpochStats)]),
     "mrgan_eval": (C.c_int, [_H, C.c_int, _fp]),
+    "mrgan_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "mrgan_dp_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
     "mrnn_step": (C.c_int, [_H, C.c_int, _fp, _ip, C.c_int, _fp]),
     "mrnn_train_epoch": (C.c_int, [_H, _ip, C.c_int, _fp]),
     "mrnn_evaluate": (C.c_int, [_H, C.c_int, _fp]),

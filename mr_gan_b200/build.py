@@ -31,7 +31,7 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     flags = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-             "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
+             "-Xcompiler", "-fPIC", "-shared", "-ldl", "--use_fast_math=false"]
     flags = [f for f in flags if f != "--use_fast_math=false"]
     if os.path.exists(os.path.join(CSRC, "kernels_tc.cuh")):
         flags += ["-DMRGAN_WITH_TC", "-lcuda"]

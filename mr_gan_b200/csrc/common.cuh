@@ -49,7 +49,18 @@ struct GemmDesc {
   int rnd;                          // tf32 mode: bit 0 / bit 1 = round C / C2 to tf32 (they feed a tcgen05 MMA)
 };
 
-struct AdamHyper { float lr, b1, b2, eps; int shared_t; };
+// Per-step constants passed by value to the kernels: Adam hyper-parameters and, for the data-parallel mode, the
+// batch geometry (dp_bloc rows per section on this rank, dp_bg rows per section globally, this rank's index).
+struct AdamHyper { float lr, b1, b2, eps; int shared_t; int dp_bloc, dp_bg, dp_rank; };
+
+// Stacked-row index of this rank -> stacked-row index of the GLOBAL batch (identity unless data-parallel): sections
+// [labeled | unlabeled | fake] of dp_bg rows each, of which this rank holds rows [rank*bloc, (rank+1)*bloc).  The noise
+// stream is keyed by the global index, so W ranks draw exactly what one GPU would draw for the same global batch.
+__host__ __device__ inline int global_row(int L, const AdamHyper& hp) {
+  if (hp.dp_bg == hp.dp_bloc) return L;
+  const int sec = L / hp.dp_bloc;
+  return sec * hp.dp_bg + hp.dp_rank * hp.dp_bloc + (L - sec * hp.dp_bloc);
+}
 
 __host__ __device__ inline int pitch4(int w) { return (w + 3) & ~3; }
 

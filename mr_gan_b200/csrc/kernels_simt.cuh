@@ -17,7 +17,7 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 
 template <bool AT, bool BT>
 __global__ void __launch_bounds__(256)
-k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ folds, int rows_override) {
+k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ folds, int rows_override, AdamHyper hp) {
   const GemmDesc d = descs[blockIdx.z];
   int M = d.M, K = d.K;
   const int N = d.N;
@@ -133,10 +133,10 @@ k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ fo
     if (n >= N) continue;
     float nz[4] = {0.f, 0.f, 0.f, 0.f};
     if (noisy) {
-      if (((d.row0 + mb) & 3) == 0) {
-        normal4(k0, k1, (uint32_t)(d.row0 + mb) >> 2, (uint32_t)n, step, (uint32_t)d.tid, nz);
+      if (((d.row0 + mb) & 3) == 0 && (hp.dp_bg == hp.dp_bloc || (hp.dp_bloc & 3) == 0)) {
+        normal4(k0, k1, (uint32_t)global_row(d.row0 + mb, hp) >> 2, (uint32_t)n, step, (uint32_t)d.tid, nz);
       } else {
-        for (int i = 0; i < 4; ++i) nz[i] = normal1(k0, k1, (uint32_t)(d.row0 + mb + i), (uint32_t)n, step, (uint32_t)d.tid);
+        for (int i = 0; i < 4; ++i) nz[i] = normal1(k0, k1, (uint32_t)global_row(d.row0 + mb + i, hp), (uint32_t)n, step, (uint32_t)d.tid);
       }
     }
 #pragma unroll
@@ -182,9 +182,11 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
     }
   }
 
+  const bool aligned = (hp.dp_bloc & 3) == 0 || hp.dp_bg == hp.dp_bloc;   // 4-row noise groups stay inside one section
   if (c < D) {
     float nz[4];
-    normal4(fs.key0, fs.key1, (uint32_t)rg, (uint32_t)c, step, 0u, nz);
+    if (aligned) normal4(fs.key0, fs.key1, (uint32_t)global_row(rg * 4, hp) >> 2, (uint32_t)c, step, 0u, nz);
+    else for (int i = 0; i < 4; ++i) nz[i] = normal1(fs.key0, fs.key1, (uint32_t)global_row(rg * 4 + i, hp), (uint32_t)c, step, 0u);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = rg * 4 + i;
@@ -202,7 +204,10 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
   }
   if (mode != 2 && c < noise_dim) {       // generator input z (mr_gan.py:206,212)
     float nz[4] = {0.f, 0.f, 0.f, 0.f};
-    if (!from_stage) normal4(fs.key0, fs.key1, (uint32_t)rg, (uint32_t)c, step, MRGAN_TID_Z, nz);
+    if (!from_stage) {
+      if (aligned) normal4(fs.key0, fs.key1, (uint32_t)global_row(rg * 4, hp) >> 2, (uint32_t)c, step, MRGAN_TID_Z, nz);
+      else for (int i = 0; i < 4; ++i) nz[i] = normal1(fs.key0, fs.key1, (uint32_t)global_row(rg * 4 + i, hp), (uint32_t)c, step, MRGAN_TID_Z);
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = rg * 4 + i;
@@ -276,9 +281,9 @@ struct LossDesc {
 // (mr_gan.py:146-149,161) and their gradients.
 __global__ void __launch_bounds__(256)
 k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total,
-            int t, int B, int K, float w_unl, int tf32) {
+            int t, int B, int K, float w_unl, int tf32, int Bg) {
   __shared__ float sh[32];
-  const LossDesc d = descs[blockIdx.z];
+  const LossDesc d = descs[blockIdx.z];   // B rows per section on this rank, Bg in the global batch (means are over Bg)
   float s_lab = 0.f, s_unl = 0.f, s_err = 0.f;
   for (int r = threadIdx.x; r < 3 * B; r += blockDim.x) {
     const float* l = d.logits + (size_t)r * d.ld;
@@ -293,7 +298,7 @@ k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, 
       s_lab += lse - l[y];
       s_err += (am != y) ? 1.f : 0.f;
       for (int k = 0; k < K; ++k) {
-        const float g = (expf(l[k] - mx) * inv - (k == y ? 1.f : 0.f)) / B;
+        const float g = (expf(l[k] - mx) * inv - (k == y ? 1.f : 0.f)) / Bg;
         dl[k] = tf32 ? rna_tf32(g) : g;
       }
     } else {
@@ -301,7 +306,7 @@ k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, 
       float coef;
       if (r < 2 * B) { s_unl += 0.5f * (sp - lse); coef = 0.5f * (sg - 1.0f); }
       else           { s_unl += 0.5f * sp;         coef = 0.5f * sg; }
-      coef *= w_unl / B;
+      coef *= w_unl / Bg;
       for (int k = 0; k < K; ++k) {
         const float g = coef * expf(l[k] - mx) * inv;
         dl[k] = tf32 ? rna_tf32(g) : g;
@@ -313,7 +318,7 @@ k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, 
   s_err = block_sum(s_err, sh);
   if (threadIdx.x == 0) {
     float* st = step_stats + ((size_t)t * nf_total + fold_base + blockIdx.z) * 4;
-    st[0] = s_lab / B; st[1] = s_unl / B; st[2] = s_err / B;
+    st[0] = s_lab / Bg; st[1] = s_unl / Bg; st[2] = s_err / Bg;
   }
 }
 
@@ -370,6 +375,94 @@ k_loss_mse(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, i
     float* st = step_stats + ((size_t)t * nf_total + fold_base + blockIdx.z) * 4;
     st[0] = s_loss / n; st[1] = s_acc / n;
   }
+}
+
+
+// ------------------------------------------------------------------ data-parallel variants (statistics / apply split)
+// In the data-parallel mode the batch statistics that the reference takes over the whole batch (BatchNorm mean /
+// variance mr_gan.py:112, feature-matching means mr_gan.py:152-153) are summed locally, all-reduced over NVLink,
+// and applied by a second kernel, so that W ranks compute exactly the single-GPU large-batch step.
+struct DpBufs { float* bnf; float* bnb; float* fm; };   // per fold: [2*W] sums each (W = 500 / 500 / 250)
+
+__global__ void __launch_bounds__(128) k_bn_stats(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs) {
+  const BnDesc d = descs[blockIdx.z];
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= d.W) return;
+  float s = 0.f, q = 0.f;
+  for (int r = 0; r < d.B; ++r) { const float x = d.h1[(size_t)r * d.ld + j]; s += x; q = fmaf(x, x, q); }
+  bufs[blockIdx.z].bnf[j] = s; bufs[blockIdx.z].bnf[d.W + j] = q;
+}
+
+__global__ void __launch_bounds__(128) k_bn_apply(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs,
+                                                  float eps, int tf32, int Bg) {
+  const BnDesc d = descs[blockIdx.z];
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= d.W) return;
+  const float mu = bufs[blockIdx.z].bnf[j] / Bg;
+  const float var = fmaxf(bufs[blockIdx.z].bnf[d.W + j] / Bg - mu * mu, 0.f);
+  const float istd = rsqrtf(var + eps);
+  d.istd[j] = istd;
+  const float g = d.gamma[j], b = d.beta[j];
+  for (int r = 0; r < d.B; ++r) {
+    const float xh = (d.h1[(size_t)r * d.ld + j] - mu) * istd;
+    d.xhat[(size_t)r * d.ld + j] = xh;
+    const float u = fmaf(g, xh, b);
+    d.u[(size_t)r * d.ldu + j] = tf32 ? rna_tf32(u) : u;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_bn_bwd_stats(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs) {
+  const BnDesc d = descs[blockIdx.z];
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= d.W) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int r = 0; r < d.B; ++r) { const float du = d.du[(size_t)r * d.ld + j]; s1 += du; s2 = fmaf(du, d.xhat[(size_t)r * d.ld + j], s2); }
+  d.g_gamma[j] = s2; d.g_beta[j] = s1;        // LOCAL partial gradients: the flat gradient all-reduce completes them
+  bufs[blockIdx.z].bnb[j] = s1; bufs[blockIdx.z].bnb[d.W + j] = s2;
+}
+
+__global__ void __launch_bounds__(128) k_bn_bwd_apply(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs,
+                                                      int tf32, int Bg) {
+  const BnDesc d = descs[blockIdx.z];
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= d.W) return;
+  const float s1 = bufs[blockIdx.z].bnb[j], s2 = bufs[blockIdx.z].bnb[d.W + j];
+  const float g = d.gamma[j], istd = d.istd[j], invB = 1.0f / Bg;
+  for (int r = 0; r < d.B; ++r) {
+    const float xh = d.xhat[(size_t)r * d.ld + j];
+    const float dxh = d.du[(size_t)r * d.ld + j] * g;
+    const float dh1 = istd * (dxh - invB * g * s1 - xh * invB * g * s2);
+    const float dz = dh1 * (1.0f - expf(-d.h1[(size_t)r * d.ld + j]));
+    d.dz1[(size_t)r * d.ld + j] = tf32 ? rna_tf32(dz) : dz;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_fm_stats(const LossDesc* __restrict__ descs, const DpBufs* __restrict__ bufs, int B) {
+  const LossDesc d = descs[blockIdx.z];
+  for (int j = threadIdx.x; j < d.Wmid; j += blockDim.x) {
+    float mg = 0.f, mr = 0.f;
+    for (int r = 0; r < B; ++r) { mg += d.mid[(size_t)r * d.ldmid + j]; mr += d.mid[(size_t)(r + B) * d.ldmid + j]; }
+    bufs[blockIdx.z].fm[j] = mg; bufs[blockIdx.z].fm[d.Wmid + j] = mr;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_fm_apply(const LossDesc* __restrict__ descs, const DpBufs* __restrict__ bufs, float* __restrict__ step_stats, int fold_base,
+           int nf_total, int t, int B, int tf32, int Bg, int world) {
+  __shared__ float sh[32];
+  const LossDesc d = descs[blockIdx.z];
+  float s = 0.f;
+  for (int j = threadIdx.x; j < d.Wmid; j += blockDim.x) {
+    const float diff = (bufs[blockIdx.z].fm[j] - bufs[blockIdx.z].fm[d.Wmid + j]) / Bg;
+    s = fmaf(diff, diff, s);
+    float g = 2.0f * diff / ((float)d.Wmid * Bg);
+    if (tf32) g = rna_tf32(g);
+    for (int r = 0; r < B; ++r)
+      d.dmid[(size_t)r * d.lddmid + j] = (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : 0.f;
+  }
+  s = block_sum(s, sh);
+  // every rank holds the same global loss; the statistics block is summed over ranks afterwards -> store 1/world of it
+  if (threadIdx.x == 0) step_stats[((size_t)t * nf_total + fold_base + blockIdx.z) * 4 + 3] = s / d.Wmid / world;
 }
 
 // ------------------------------------------------------------------ evaluation

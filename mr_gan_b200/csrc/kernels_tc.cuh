@@ -320,8 +320,10 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
             if (r0 >= NE) break;
             float nz[4] = {0.f, 0.f, 0.f, 0.f};
             if (noisy) {
-              if (((g.row0 + r0) & 3) == 0) normal4(key0, key1, (uint32_t)(g.row0 + r0) >> 2, (uint32_t)f, step, (uint32_t)g.tid, nz);
-              else for (int i = 0; i < 4; ++i) nz[i] = normal1(key0, key1, (uint32_t)(g.row0 + r0 + i), (uint32_t)f, step, (uint32_t)g.tid);
+              if (((g.row0 + r0) & 3) == 0 && (hp.dp_bg == hp.dp_bloc || (hp.dp_bloc & 3) == 0))
+                normal4(key0, key1, (uint32_t)global_row(g.row0 + r0, hp) >> 2, (uint32_t)f, step, (uint32_t)g.tid, nz);
+              else
+                for (int i = 0; i < 4; ++i) nz[i] = normal1(key0, key1, (uint32_t)global_row(g.row0 + r0 + i, hp), (uint32_t)f, step, (uint32_t)g.tid);
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {

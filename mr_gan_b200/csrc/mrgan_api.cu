@@ -2,6 +2,7 @@
 // declared in include/mrgan.h.  Reference interface replaced: the K.function callables of
 // mr_gan.py:169-171, the epoch loop mr_gan.py:183-230 and mr_nn.py:114-118.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
@@ -99,6 +100,11 @@ struct mrgan_handle {
   long long launches = 0;
   std::string err;
   AdamHyper hp;
+  // data-parallel mode (mrgan_dp_init): NCCL communicator + buffers of the all-reduced batch statistics
+  int dp_world = 1, dp_rank = 0;
+  void* nccl_comm = nullptr;
+  float* d_dpmem = nullptr; DpBufs* d_dpbufs = nullptr;
+  float *dp_bnf = nullptr, *dp_bnb = nullptr, *dp_fm = nullptr;   // [nf][2*500], [nf][2*500], [nf][2*250]
 #ifdef MRGAN_WITH_TC
   TcOp* d_tcops = nullptr;            // [NUM_OPS][nf] tensor maps + epilogue descriptors
   int tc_bn[NUM_OPS] = {0}, tc_maxME[NUM_OPS] = {0}, tc_maxNE[NUM_OPS] = {0};
@@ -373,6 +379,48 @@ void init_ones(mrgan_handle* h) {
   }
 }
 
+
+// ------------------------------------------------------------------ NCCL (resolved at run time: no link dependency)
+struct NcclId { char b[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+
+bool nccl_load() {
+  if (g_nccl.lib) return true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return false;
+  g_nccl.GetUniqueId = (int (*)(NcclId*))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) return false;
+  g_nccl.lib = lib;
+  return true;
+}
+
+// in-stream sum all-reduce of fp32 (ncclFloat32 = 7, ncclSum = 0); no-op outside the data-parallel mode
+void dp_allreduce(mrgan_handle* h, float* buf, size_t n) {
+  if (h->dp_world <= 1 || n == 0) return;
+  const int rc = g_nccl.AllReduce(buf, buf, n, 7, 0, h->nccl_comm, h->stream);
+  if (rc != 0) h->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+}
+
+void dp_allreduce_grads(mrgan_handle* h, int net) {
+  if (h->dp_world <= 1) return;
+  long long n = 0;
+  for (int f = 0; f < h->nf; ++f) n += h->net[net][f].n;
+  dp_allreduce(h, h->Gr + h->net[net][0].off, (size_t)n);      // the nets of all folds are contiguous in the flat buffer
+}
+
 // ------------------------------------------------------------------ launch sequences
 void launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override, cudaStream_t st = nullptr) {
   if (!st) st = h->stream;
@@ -384,9 +432,9 @@ void launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override, cu
   if (h->cfg.precision == MRGAN_PREC_TF32 && tc_launch_gemm(h, op, f0, nfl, rows_override, st)) return;
 #endif
   dim3 grid((oi.maxN + 63) / 64, (M + 63) / 64, nfl);
-  if (!oi.at && !oi.bt) k_gemm_simt<false, false><<<grid, 256, 0, st>>>(d, h->d_folds, rows_override);
-  else if (!oi.at && oi.bt) k_gemm_simt<false, true><<<grid, 256, 0, st>>>(d, h->d_folds, rows_override);
-  else k_gemm_simt<true, false><<<grid, 256, 0, st>>>(d, h->d_folds, rows_override);
+  if (!oi.at && !oi.bt) k_gemm_simt<false, false><<<grid, 256, 0, st>>>(d, h->d_folds, rows_override, h->hp);
+  else if (!oi.at && oi.bt) k_gemm_simt<false, true><<<grid, 256, 0, st>>>(d, h->d_folds, rows_override, h->hp);
+  else k_gemm_simt<true, false><<<grid, 256, 0, st>>>(d, h->d_folds, rows_override, h->hp);
   h->launches++;
 }
 
@@ -435,8 +483,17 @@ void launch_adam(mrgan_handle* h, int f0, int nfl, int net) {
 
 void enqueue_gen_fwd(mrgan_handle* h, int f0, int nfl, int op_g3) {
   launch_gemm(h, OP_G1, f0, nfl, 0);
-  k_bn_fwd<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, h->cfg.bn_eps, h->cfg.precision == MRGAN_PREC_TF32);
-  h->launches++;
+  const dim3 bng((kGH + 127) / 128, 1, nfl);
+  const int tf32 = h->cfg.precision == MRGAN_PREC_TF32;
+  if (h->dp_world > 1) {      // batch statistics over the GLOBAL batch: local sums -> NVLink all-reduce -> apply
+    k_bn_stats<<<bng, 128, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0);
+    dp_allreduce(h, h->dp_bnf + (size_t)f0 * 2 * kGH, (size_t)nfl * 2 * kGH);
+    k_bn_apply<<<bng, 128, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, h->cfg.bn_eps, tf32, h->hp.dp_bg);
+    h->launches += 2;
+  } else {
+    k_bn_fwd<<<bng, 128, 0, h->stream>>>(h->d_bn + f0, h->cfg.bn_eps, tf32);
+    h->launches++;
+  }
   launch_gemm(h, OP_G2, f0, nfl, 0);
   launch_gemm(h, op_g3, f0, nfl, 0);
 }
@@ -449,7 +506,7 @@ void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) 
   enqueue_gen_fwd(h, f0, nfl, OP_G3D);
   for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 0);
   k_loss_disc<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B, c.n_classes, c.unlabeled_weight,
-                                                         c.precision == MRGAN_PREC_TF32);
+                                                         c.precision == MRGAN_PREC_TF32, h->hp.dp_bg);
   h->launches++;
   for (int l = 6; l >= 1; --l) {      // dX first: it reads W_l, which the fused-Adam dW epilogue overwrites
     if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
@@ -457,7 +514,9 @@ void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) 
     launch_gemm(h, OP_DW1 + l - 1, f0, nfl, 0, h->side);
   }
   join_side(h);
+  dp_allreduce_grads(h, 0);
   launch_adam(h, f0, nfl, 0);
+  if (from_stage) dp_allreduce(h, h->d_step_stats + ((size_t)t * h->nf + f0) * 4, (size_t)nfl * 4);
 }
 
 // train_batch_gen (mr_gan.py:170)
@@ -467,8 +526,16 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   launch_prep(h, f0, nfl, 1, from_stage, t, 2 * B);
   enqueue_gen_fwd(h, f0, nfl, OP_G3G);
   for (int l = 0; l < 5; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 2 * B);
-  k_fm<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B, c.precision == MRGAN_PREC_TF32);
-  h->launches++;
+  if (h->dp_world > 1) {
+    k_fm_stats<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, B);
+    dp_allreduce(h, h->dp_fm + (size_t)f0 * 2 * kDW[4], (size_t)nfl * 2 * kDW[4]);
+    k_fm_apply<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, h->d_step_stats, f0, h->nf, t, B,
+                                                       c.precision == MRGAN_PREC_TF32, h->hp.dp_bg, h->dp_world);
+    h->launches += 2;
+  } else {
+    k_fm<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B, c.precision == MRGAN_PREC_TF32);
+    h->launches++;
+  }
   for (int l = 5; l >= 2; --l) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, B);
   launch_gemm(h, OP_DX1G, f0, nfl, 0);
   launch_gemm(h, OP_GX3, f0, nfl, 0);
@@ -477,12 +544,21 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   launch_gemm(h, OP_GX2, f0, nfl, 0);
   fork_side(h);
   launch_gemm(h, OP_GW2, f0, nfl, 0, h->side);
-  k_bn_bwd<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, c.precision == MRGAN_PREC_TF32);
-  h->launches++;
+  if (h->dp_world > 1) {
+    k_bn_bwd_stats<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0);
+    dp_allreduce(h, h->dp_bnb + (size_t)f0 * 2 * kGH, (size_t)nfl * 2 * kGH);
+    k_bn_bwd_apply<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, c.precision == MRGAN_PREC_TF32, h->hp.dp_bg);
+    h->launches += 2;
+  } else {
+    k_bn_bwd<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, c.precision == MRGAN_PREC_TF32);
+    h->launches++;
+  }
   fork_side(h);
   launch_gemm(h, OP_GW1, f0, nfl, 0, h->side);
   join_side(h);
+  dp_allreduce_grads(h, 1);
   launch_adam(h, f0, nfl, 1);
+  dp_allreduce(h, h->d_step_stats + ((size_t)t * h->nf + f0) * 4, (size_t)nfl * 4);
 }
 
 // one model.fit batch of mr_nn (mr_nn.py:117)
@@ -761,7 +837,9 @@ int tc_setup(mrgan_handle* h) {
 void tc_teardown(mrgan_handle* h) {
   if (h->d_tcops) cudaFree(h->d_tcops);
   if (h->d_tcadam) cudaFree(h->d_tcadam);
-  for (int n = 0; n < 2; ++n) if (h->d_ranges_tc[n]) cudaFree(h->d_ranges_tc[n]);
+  for (int n = 0; n < 2; ++n) { if (h->d_ranges_tc[n]) cudaFree(h->d_ranges_tc[n]); h->d_ranges_tc[n] = nullptr; }
+  for (int i = 0; i < NUM_OPS; ++i) { h->tc_bn[i] = 0; h->tc_maxME[i] = 0; h->tc_maxNE[i] = 0; }
+  h->d_tcadam = nullptr;
   h->d_tcops = nullptr;
 }
 
@@ -817,7 +895,7 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   if (cfg->n_folds < 1 || cfg->batch < 1 || cfg->n_classes < 2 || cfg->n_classes > 64 || cfg->noise_dim < 1)
     return fail(nullptr, MRGAN_ERR_ARG, "bad config (n_folds/batch/n_classes/noise_dim)");
   if (cfg->model != MRGAN_MODEL_GAN && cfg->model != MRGAN_MODEL_NN) return fail(nullptr, MRGAN_ERR_ARG, "bad model");
-  if (cfg->model == MRGAN_MODEL_GAN && 3 * cfg->batch > 4096) return fail(nullptr, MRGAN_ERR_ARG, "batch too large");
+  if (cfg->batch > (1 << 16)) return fail(nullptr, MRGAN_ERR_ARG, "batch too large");
   for (int f = 0; f < cfg->n_folds; ++f) {
     if (folds[f].D < 1 || folds[f].n_train < cfg->batch || folds[f].n_test < 1)
       return fail(nullptr, MRGAN_ERR_ARG, "bad fold shape");
@@ -840,7 +918,7 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   h->n_train = folds[0].n_train;
   h->shapes.assign(folds, folds + h->nf);
   h->fb.resize(h->nf);
-  h->hp = AdamHyper{cfg->lr, cfg->beta1, cfg->beta2, cfg->adam_eps, cfg->shared_t};
+  h->hp = AdamHyper{cfg->lr, cfg->beta1, cfg->beta2, cfg->adam_eps, cfg->shared_t, cfg->batch, cfg->batch, 0};
   int ne = h->R;
   for (int f = 0; f < h->nf; ++f) ne = folds[f].n_test > ne ? folds[f].n_test : ne;
   h->NE = ne;
@@ -899,6 +977,9 @@ int mrgan_destroy(mrgan_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+  if (h->d_dpmem) cudaFree(h->d_dpmem);
+  if (h->d_dpbufs) cudaFree(h->d_dpbufs);
 #ifdef MRGAN_WITH_TC
   tc_teardown(h);
 #endif
@@ -1124,13 +1205,22 @@ int mrgan_train_epoch(mrgan_handle* h, const int32_t* idx_lab, const int32_t* id
       return fail(h, MRGAN_ERR_ARG, "train_epoch: row index out of range");
   CK(cudaSetDevice(h->cfg.device));
   int rc = finish_pending(h); if (rc) return rc;
-  rc = build_graph(h, nb, nb, 0); if (rc) return rc;
+  const bool eager = h->dp_world > 1;      // data-parallel epochs interleave NCCL collectives: enqueue step by step
+  if (!eager) { rc = build_graph(h, nb, nb, 0); if (rc) return rc; }
   const int32_t* streams[3] = {idx_lab, idx_unl, idx_unl2};
   rc = upload_indices(h, streams, 3, h->n_train); if (rc) return rc;
   CK(cudaEventRecord(h->ev0, h->stream));
-  CK(cudaGraphLaunch(h->graphs[nb], h->stream));
+  if (eager) {
+    for (int t = 0; t < nb; ++t) { enqueue_disc_step(h, 0, h->nf, t, 0); enqueue_gen_step(h, 0, h->nf, t, 0); }
+    if (h->cfg.eval_each_epoch) enqueue_eval(h, 0, h->nf, false, 0);
+    k_epoch_reduce<<<h->nf, 32, 0, h->stream>>>(h->d_step_stats, h->d_eval, h->d_epoch_stats, h->nf, nb, h->cfg.eval_each_epoch);
+    h->launches++;
+    CK(cudaMemcpyAsync(h->h_epoch_stats, h->d_epoch_stats, (size_t)h->nf * 8 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    CK(cudaGraphLaunch(h->graphs[nb], h->stream));
+    h->launches += h->graph_nodes[nb];
+  }
   CK(cudaEventRecord(h->ev1, h->stream));
-  h->launches += h->graph_nodes[nb];
   h->epoch_pending = true;
   if (stats) return mrgan_epoch_result(h, stats);
   return MRGAN_OK;
@@ -1280,6 +1370,53 @@ int mrgan_time_op(mrgan_handle* h, int which, int reps, float* ms_avg) {
   return MRGAN_OK;
 }
 
+int mrgan_nccl_unique_id(void* id128) {
+  if (!id128) return fail(nullptr, MRGAN_ERR_ARG, "nccl_unique_id: null pointer");
+  if (!nccl_load()) return fail(nullptr, MRGAN_ERR_STATE, "libnccl.so.2 not found");
+  NcclId id;
+  const int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) return fail(nullptr, MRGAN_ERR_CUDA, "ncclGetUniqueId failed");
+  memcpy(id128, id.b, 128);
+  return MRGAN_OK;
+}
+
+int mrgan_dp_init(mrgan_handle* h, int rank, int world, const void* id128) {
+  if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
+  if (world < 1 || rank < 0 || rank >= world || !id128) return fail(h, MRGAN_ERR_ARG, "dp_init: bad rank / world / id");
+  if (h->cfg.model != MRGAN_MODEL_GAN) return fail(h, MRGAN_ERR_STATE, "dp_init: data-parallel mode is implemented for the GAN model");
+  if (h->dp_world > 1 || h->nccl_comm) return fail(h, MRGAN_ERR_STATE, "dp_init called twice");
+  if (world == 1) return MRGAN_OK;
+  if (h->cfg.batch % 4) return fail(h, MRGAN_ERR_ARG, "dp_init: the local batch must be a multiple of 4 (noise row groups)");
+  if (!nccl_load()) return fail(h, MRGAN_ERR_STATE, "libnccl.so.2 not found");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = finish_pending(h); if (rc) return rc;
+  NcclId id; memcpy(id.b, id128, 128);
+  const int nrc = g_nccl.CommInitRank(&h->nccl_comm, world, id, rank);
+  if (nrc != 0) return fail(h, MRGAN_ERR_CUDA, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error"));
+  const int nf = h->nf;
+  const size_t per = 2 * kGH + 2 * kGH + 2 * kDW[4];
+  CK(cudaMalloc(&h->d_dpmem, per * nf * sizeof(float)));
+  CK(cudaMemset(h->d_dpmem, 0, per * nf * sizeof(float)));
+  h->dp_bnf = h->d_dpmem; h->dp_bnb = h->dp_bnf + (size_t)nf * 2 * kGH; h->dp_fm = h->dp_bnb + (size_t)nf * 2 * kGH;
+  std::vector<DpBufs> bufs(nf);
+  for (int f = 0; f < nf; ++f) bufs[f] = DpBufs{h->dp_bnf + (size_t)f * 2 * kGH, h->dp_bnb + (size_t)f * 2 * kGH, h->dp_fm + (size_t)f * 2 * kDW[4]};
+  CK(cudaMalloc(&h->d_dpbufs, nf * sizeof(DpBufs)));
+  CK(cudaMemcpy(h->d_dpbufs, bufs.data(), nf * sizeof(DpBufs), cudaMemcpyHostToDevice));
+  h->dp_world = world; h->dp_rank = rank;
+  h->hp.dp_bloc = h->cfg.batch; h->hp.dp_bg = h->cfg.batch * world; h->hp.dp_rank = rank;
+#ifdef MRGAN_WITH_TC
+  if (h->cfg.precision == MRGAN_PREC_TF32) {   // gradients must be all-reduced before Adam: dW stores them, k_adam applies
+    tc_teardown(h);
+    h->tc_fused_adam = false;
+    rc = tc_setup(h); if (rc) return rc;
+  }
+#endif
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  h->graphs.clear(); h->graph_nodes.clear();
+  CK(cudaDeviceSynchronize());
+  return MRGAN_OK;
+}
+
 int mrgan_debug_buffer(mrgan_handle* h, int fold, int which, float* dst, int rows, int cols) {
   int rc = check_fold(h, fold); if (rc) return rc;
   if (!dst || rows < 1 || cols < 1) return fail(h, MRGAN_ERR_ARG, "debug_buffer: bad argument");
@@ -1338,9 +1475,9 @@ int mrgan_debug_gemm(mrgan_handle* h, int mode, int M, int N, int K, const float
   if (use_tc && !done) return fail(h, MRGAN_ERR_ARG, "library built without the tcgen05 kernels");
   if (!done) {
     dim3 grid((N + 63) / 64, (M + 63) / 64, 1);
-    if (mode == 0) k_gemm_simt<false, false><<<grid, 256, 0, h->stream>>>(dd, h->d_folds, 0);
-    else if (mode == 1) k_gemm_simt<false, true><<<grid, 256, 0, h->stream>>>(dd, h->d_folds, 0);
-    else k_gemm_simt<true, false><<<grid, 256, 0, h->stream>>>(dd, h->d_folds, 0);
+    if (mode == 0) k_gemm_simt<false, false><<<grid, 256, 0, h->stream>>>(dd, h->d_folds, 0, h->hp);
+    else if (mode == 1) k_gemm_simt<false, true><<<grid, 256, 0, h->stream>>>(dd, h->d_folds, 0, h->hp);
+    else k_gemm_simt<true, false><<<grid, 256, 0, h->stream>>>(dd, h->d_folds, 0, h->hp);
     h->launches++;
   }
   cudaError_t e = cudaMemcpy2DAsync(C, (size_t)N * 4, dC, (size_t)ldc * 4, (size_t)N * 4, M, cudaMemcpyDeviceToHost, h->stream);

@@ -65,6 +65,22 @@ class FoldGroup:
         self.noise_dim = cfg.noise_dim
         self.n_train = self.shapes[0][1]
 
+    # ------------------------------------------------------------------ data-parallel large-batch mode
+    @staticmethod
+    def nccl_unique_id():
+        """128-byte NCCL id (rank 0 creates it, every rank passes it to dp_init)."""
+        buf = C.create_string_buffer(128)
+        lib = _lib.load()
+        if lib.mrgan_nccl_unique_id(buf) != 0:
+            raise MrganError("mrgan_nccl_unique_id: %s" % lib.mrgan_last_error(None).decode())
+        return buf.raw
+
+    def dp_init(self, rank, world, unique_id):
+        """Join a data-parallel group: this handle's `batch` becomes the LOCAL batch (global = world * batch)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._chk(self.lib.mrgan_dp_init(self._h, int(rank), int(world), buf))
+        self.dp_rank, self.dp_world = int(rank), int(world)
+
     # ------------------------------------------------------------------ plumbing
     def _chk(self, rc, h="self"):
         if rc != 0:
