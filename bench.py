@@ -157,6 +157,75 @@ def run_reference(args, rank):
     return 0
 
 
+def run_dp(args, rank, world, local, barrier):
+    """BASELINE.json config 5: one fold at a large global batch, batch rows split over the ranks, BN / feature-matching
+    statistics and the flat gradient all-reduced with NCCL over NVLink (strong scaling: the global batch is fixed)."""
+    import torch
+    import torch.distributed as dist
+    from mr_gan_b200.engine import FoldGroup
+    from mr_gan_b200.model import init_disc, init_gen
+    D, Bg = args.dp_width, args.dp_batch
+    Bl, nb = Bg // world, 4
+    W, K = max(args.warmup, 3), args.steps
+    rng = np.random.default_rng(0)
+    pD, pG = init_disc(D, rng), init_gen(D, rng)
+    ntr = nb * Bl
+    X = np.random.default_rng(100 + rank).standard_normal((ntr, D)).astype(np.float32)
+    y = (np.arange(ntr) % 6).astype(np.int32)
+    fg = FoldGroup([(D, ntr, 600, 4242)], precision=args.precision, batch=Bl, device=local, eval_each_epoch=False)
+    if world > 1:
+        uid = [FoldGroup.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        fg.dp_init(rank, world, uid[0])
+    fg.set_params(0, 1, pG)
+    fg.set_params(0, 0, pD)
+    fg.load_fold(0, X, y, X[:600], y[:600])
+    idx = np.arange(ntr, dtype=np.int32)[None, :]
+    sampler = ClockSampler(local)
+    for w in range(W):
+        fg.train_epoch(idx, idx, idx)
+    sampler.start()
+    barrier()
+    l0 = fg.kernel_launches
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for k in range(K):
+        st = fg.train_epoch(idx, idx, idx)
+        dev_ms += fg.last_device_ms
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = (float(x) for x in t.tolist())
+    pairs = K * nb
+    flops, nbytes, N_D, N_G = algo_work(D, Bg)
+    hbm, tf, how = peaks()
+    value = pairs / (dev_ms * 1e-3)
+    ach = flops * value / 1e12
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
+            "data": "synthetic",
+            "config": {"workload": "mr_gan.py table-5 fold at large batch, data-parallel: D=%d (1 s contact mic), global batch %d "
+                                   "(%d per GPU); 1 step = %d D+G step-pairs" % (D, Bg, Bl, nb),
+                       "parallelism": "dp%d, NCCL all-reduce of BN/FM statistics and flat gradients (%.0f MB D + %.0f MB G per pair)"
+                                      % (world, 4e-6 * N_D, 4e-6 * N_G), "precision": args.precision},
+            "e2e": {"value": pairs / (wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(3 * 4 * ntr),
+                    "d2h_bytes_per_step": 32, "wall_ms": wall_ms},
+            "gpu_launches": int(fg.kernel_launches - l0),
+            "roofline": {"kernel": "whole step pair (tcgen05 GEMMs dominate at this batch)", "bound": "tensor", "achieved": ach,
+                         "peak": tf * world, "unit": "TFLOP/s", "frac": ach / (tf * world), "traffic": None, "peak_source": how,
+                         "note": "tf32 operands: the tf32 tensor peak is half the bf16 figure used as denominator"},
+            "clocks": clocks, "sanity": {"last_loss_lab": float(st[0, 0]), "last_loss_gen": float(st[0, 3])}}
+    fg.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -169,6 +238,10 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=12)
     ap.add_argument("--cpu-pairs", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "dp"],
+                    help="sweep: fold-sharded table-1 group (headline); dp: ONE fold at large batch, data-parallel (config 5)")
+    ap.add_argument("--dp-batch", type=int, default=8192, help="global batch of the dp workload")
+    ap.add_argument("--dp-width", type=int, default=12032, help="input width of the dp workload (1 s contact mic, table 5)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,6 +267,9 @@ def main():
     from mr_gan_b200 import foldprep
     from mr_gan_b200.engine import FoldGroup
     from mr_gan_b200.model import fold_key, init_disc, init_gen
+
+    if args.workload == "dp":
+        return run_dp(args, rank, world, local, barrier)
 
     D, B, G = args.width, 50, args.folds
     W, K = max(args.warmup, 3), args.steps
