@@ -375,7 +375,7 @@ struct alignas(64) TcAdamOp {
 };
 
 #define TCA_KC 8
-#define TCA_NB 3
+#define TCA_NB 4
 
 namespace tc {
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {

@@ -5,6 +5,7 @@
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <string>
@@ -83,6 +84,10 @@ struct mrgan_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;        // dW (+Adam) kernels run here, concurrently with the latency-bound dX chain
   cudaEvent_t ev_pool[16] = {nullptr}; int ev_next = 0;
+  // the folds of a group are independent, so an epoch is captured as `nchains` parallel chains of kernels (disjoint fold
+  // ranges, own main + side stream): one chain's latency-bound small kernels fill the SMs another chain leaves idle
+  int nchains = 1;
+  cudaStream_t cmain[4] = {nullptr}, cside[4] = {nullptr};
   char* arena = nullptr; size_t arena_bytes = 0;
   float *P = nullptr, *Mo = nullptr, *Vo = nullptr, *Gr = nullptr; long long n_flat = 0;
   FoldState* d_folds = nullptr; std::vector<FoldState> h_folds;
@@ -637,14 +642,32 @@ int build_graph(mrgan_handle* h, int key, int nb, int n_idx_nn) {
   const long long before = h->launches;
   cudaGraph_t g = nullptr;
   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-  if (c.model == MRGAN_MODEL_GAN) {
-    for (int t = 0; t < nb; ++t) {
-      enqueue_disc_step(h, 0, h->nf, t, 0);
-      enqueue_gen_step(h, 0, h->nf, t, 0);
+  {
+    cudaStream_t origin = h->stream, origin_side = h->side;
+    const int nch = h->nchains;
+    cudaEvent_t e = h->ev_pool[h->ev_next++ & 15];
+    cudaEventRecord(e, origin);
+    for (int ch = 1; ch < nch; ++ch) cudaStreamWaitEvent(h->cmain[ch], e, 0);
+    for (int ch = 0; ch < nch; ++ch) {
+      const int f0 = (int)((long long)h->nf * ch / nch), f1 = (int)((long long)h->nf * (ch + 1) / nch);
+      if (f1 <= f0) continue;
+      h->stream = h->cmain[ch]; h->side = h->cside[ch];
+      if (c.model == MRGAN_MODEL_GAN) {
+        for (int t = 0; t < nb; ++t) {
+          enqueue_disc_step(h, f0, f1 - f0, t, 0);
+          enqueue_gen_step(h, f0, f1 - f0, t, 0);
+        }
+        if (c.eval_each_epoch) enqueue_eval(h, f0, f1 - f0, false, 0);
+      } else {
+        for (int t = 0; t < nb; ++t) enqueue_nn_step(h, f0, f1 - f0, t, 0, c.batch);
+      }
     }
-    if (c.eval_each_epoch) enqueue_eval(h, 0, h->nf, false, 0);
-  } else {
-    for (int t = 0; t < nb; ++t) enqueue_nn_step(h, 0, h->nf, t, 0, c.batch);
+    h->stream = origin; h->side = origin_side;
+    for (int ch = 1; ch < nch; ++ch) {
+      cudaEvent_t j = h->ev_pool[h->ev_next++ & 15];
+      cudaEventRecord(j, h->cmain[ch]);
+      cudaStreamWaitEvent(origin, j, 0);
+    }
   }
   k_epoch_reduce<<<h->nf, 32, 0, h->stream>>>(h->d_step_stats, h->d_eval, h->d_epoch_stats, h->nf, nb,
                                               c.model == MRGAN_MODEL_GAN && c.eval_each_epoch);
@@ -949,6 +972,19 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 16 && ok; ++i) ok = cudaEventCreateWithFlags(&h->ev_pool[i], cudaEventDisableTiming) == cudaSuccess;
+  {
+    const char* env = getenv("MRGAN_CHAINS");
+    int nch = env ? atoi(env) : (h->nf >= 32 ? 4 : (h->nf >= 8 ? 2 : 1));
+    if (nch < 1) nch = 1;
+    if (nch > 4) nch = 4;
+    if (nch > h->nf) nch = h->nf;
+    h->nchains = nch;
+    h->cmain[0] = h->stream; h->cside[0] = h->side;
+    for (int ch = 1; ch < nch && ok; ++ch) {
+      ok = cudaStreamCreateWithFlags(&h->cmain[ch], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaStreamCreateWithFlags(&h->cside[ch], cudaStreamNonBlocking) == cudaSuccess;
+    }
+  }
   ok = ok && cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess;
   ok = ok && cudaMallocHost(&h->h_epoch_stats, (size_t)h->nf * 8 * sizeof(float)) == cudaSuccess;
   ok = ok && cudaMallocHost(&h->h_scratch, 64 * sizeof(float)) == cudaSuccess;
@@ -993,6 +1029,7 @@ int mrgan_destroy(mrgan_handle* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int i = 0; i < 16; ++i) if (h->ev_pool[i]) cudaEventDestroy(h->ev_pool[i]);
+  for (int ch = 1; ch < 4; ++ch) { if (h->cmain[ch]) cudaStreamDestroy(h->cmain[ch]); if (h->cside[ch]) cudaStreamDestroy(h->cside[ch]); }
   if (h->side) cudaStreamDestroy(h->side);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;

@@ -337,12 +337,15 @@ def test_fp32_path_tracks_oracle_over_epochs_at_reference_batch():
             got = fg.train_epoch(*[a[None, :] for a in idx[e]])[0]
             st, step = fold_loop.train_epoch(m, f['Xtr'].astype(np.float64), f['ytr'], *idx[e], key, step, B=B)
             want = st.mean(axis=0)
-            np.testing.assert_allclose(got[[0, 1]], want[[0, 1]], rtol=1e-3)
-            np.testing.assert_allclose(got[3], want[3], rtol=1e-2)    # feature-matching loss: tiny, chaotic along a trajectory
-            assert abs(got[2] - want[2]) <= 1.0 / ntr + 1e-6
-            # fp32 vs float64 after tens of steps: a borderline test sample may flip
-            assert abs(got[4] - fold_loop.eval_batches(m, f['Xte'].astype(np.float64), f['yte'], B=B)) <= 3.0 / nte + 1e-6
-        assert abs(fg.eval(0) - m.test_batch(f['Xte'].astype(np.float64), f['yte'])) <= 3.0 / nte + 1e-6
+            # Adam's near-sign updates (eps = 1e-8) turn fp32-vs-float64 rounding of near-zero gradients into
+            # parameter differences of 2*lr within a few steps, so epoch means agree to ~1e-3 at first and drift
+            tol = 1e-3 if e == 0 else 5e-3
+            np.testing.assert_allclose(got[[0, 1]], want[[0, 1]], rtol=tol)
+            np.testing.assert_allclose(got[3], want[3], rtol=10 * tol)    # feature-matching loss: tiny squared difference of means
+            # argmax statistics: exact while the trajectories coincide (first epoch), a few borderline samples later
+            assert abs(got[2] - want[2]) <= (1.0 / ntr + 1e-6 if e == 0 else 0.03)
+            assert abs(got[4] - fold_loop.eval_batches(m, f['Xte'].astype(np.float64), f['yte'], B=B)) <= (1.0 / nte + 1e-6 if e == 0 else 0.04)
+        assert abs(fg.eval(0) - m.test_batch(f['Xte'].astype(np.float64), f['yte'])) <= 0.04
         assert fg.counters(0) == (72, 72)
 
 
