@@ -344,7 +344,7 @@ def test_fp32_path_tracks_oracle_over_epochs_at_reference_batch():
             np.testing.assert_allclose(got[3], want[3], rtol=10 * tol)    # feature-matching loss: tiny squared difference of means
             # argmax statistics: exact while the trajectories coincide (first epoch), a few borderline samples later
             assert abs(got[2] - want[2]) <= (1.0 / ntr + 1e-6 if e == 0 else 0.03)
-            assert abs(got[4] - fold_loop.eval_batches(m, f['Xte'].astype(np.float64), f['yte'], B=B)) <= (1.0 / nte + 1e-6 if e == 0 else 0.04)
+            assert abs(got[4] - fold_loop.eval_batches(m, f['Xte'].astype(np.float64), f['yte'], B=B)) <= (3.0 / nte + 1e-6 if e == 0 else 0.04)
         assert abs(fg.eval(0) - m.test_batch(f['Xte'].astype(np.float64), f['yte'])) <= 0.04
         assert fg.counters(0) == (72, 72)
 
