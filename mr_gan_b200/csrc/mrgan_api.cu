@@ -28,6 +28,8 @@ enum Op {
   OP_DW1, OP_DW2, OP_DW3, OP_DW4, OP_DW5, OP_DW6,
   OP_DX2, OP_DX3, OP_DX4, OP_DX5, OP_DX6,     // OP_DXl: dZ[l] -> dZ[l-1]
   OP_DX1G,                                     // dZ[1] -> dFake (G step only)
+  OP_D1G, OP_D2G, OP_D3G, OP_D4G, OP_D5G,      // G step: D forward over 2B rows [fake | real] (own TMA boxes / MMA-N)
+  OP_DX2G, OP_DX3G, OP_DX4G, OP_DX5G,          // G step: dX chain over the B fake rows
   OP_GW1, OP_GW2, OP_GW3, OP_GX2, OP_GX3,
   OP_E1, OP_E1S, OP_E2, OP_E3, OP_E4, OP_E5, OP_E6,
   NUM_OPS
@@ -284,6 +286,7 @@ void build_descs(mrgan_handle* h) {
                              EPI_FWD, l <= 5 ? ACT_RELU : ACT_NONE, f);
       if (l <= 4) { d.C2 = b.a[l]; d.ldc2 = b.lda[l]; d.sigma = sig[l]; d.tid = l; d.row0 = 0; }
       setop(OP_D1 + l - 1, f, d, false, false, (l == 5 ? 1 : 0) | 2);
+      if (gan && l <= 5) { GemmDesc dg = d; dg.M = 2 * B; setop(OP_D1G + l - 1, f, dg, false, false, (l == 5 ? 1 : 0) | 2); }
       // eval twin: no noise, reads the clean activations
       const float* EA = (l == 1) ? b.xte : b.eh[l - 1];
       float* EC = (l <= 5) ? b.eh[l] : b.elg;
@@ -303,6 +306,7 @@ void build_descs(mrgan_handle* h) {
                                EPI_DX, ACT_RELU, f);
         x.aux = b.hb[l - 1]; x.ldaux = b.lda[l - 1];
         setop(OP_DX2 + l - 2, f, x, false, true, 1);
+        if (gan && l <= 5) { GemmDesc xg = x; xg.M = B; setop(OP_DX2G + l - 2, f, xg, false, true, 1); }
       }
     }
     rg0[f] = AdamRange{LD.off, LD.n};
@@ -530,7 +534,7 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   const int B = c.batch;
   launch_prep(h, f0, nfl, 1, from_stage, t, 2 * B);
   enqueue_gen_fwd(h, f0, nfl, OP_G3G);
-  for (int l = 0; l < 5; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 2 * B);
+  for (int l = 0; l < 5; ++l) launch_gemm(h, OP_D1G + l, f0, nfl, 0);
   if (h->dp_world > 1) {
     k_fm_stats<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, B);
     dp_allreduce(h, h->dp_fm + (size_t)f0 * 2 * kDW[4], (size_t)nfl * 2 * kDW[4]);
@@ -541,7 +545,7 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
     k_fm<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B, c.precision == MRGAN_PREC_TF32);
     h->launches++;
   }
-  for (int l = 5; l >= 2; --l) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, B);
+  for (int l = 5; l >= 2; --l) launch_gemm(h, OP_DX2G + l - 2, f0, nfl, 0);
   launch_gemm(h, OP_DX1G, f0, nfl, 0);
   launch_gemm(h, OP_GX3, f0, nfl, 0);
   fork_side(h);
