@@ -227,19 +227,36 @@ struct BnDesc {
 };
 
 // mr_gan.py:112 BatchNormalization(epsilon=2e-5) in training phase: biased batch variance.
-__global__ void __launch_bounds__(128) k_bn_fwd(const BnDesc* __restrict__ descs, float eps, int tf32) {
+// Block = 32 columns x 8 row slices (256 threads): the batch loop is split 8 ways and reduced through shared memory,
+// so the dependent-load chain per thread is B/8 rows instead of B.
+#define BN_COLS 32
+#define BN_SLICES 8
+__global__ void __launch_bounds__(256) k_bn_fwd(const BnDesc* __restrict__ descs, float eps, int tf32) {
+  __shared__ float red[2][BN_SLICES][BN_COLS];
   const BnDesc d = descs[blockIdx.z];
-  const int j = blockIdx.x * 128 + threadIdx.x;
-  if (j >= d.W) return;
+  const int cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
+  const int j = blockIdx.x * BN_COLS + cx;
+  const bool ok = j < d.W;
   float s = 0.f;
-  for (int r = 0; r < d.B; ++r) s += d.h1[(size_t)r * d.ld + j];
-  const float mu = s / d.B;
+  if (ok) for (int r = sl; r < d.B; r += BN_SLICES) s += d.h1[(size_t)r * d.ld + j];
+  red[0][sl][cx] = s;
+  __syncthreads();
+  float mu = 0.f;
+#pragma unroll
+  for (int i = 0; i < BN_SLICES; ++i) mu += red[0][i][cx];
+  mu /= d.B;
   float q = 0.f;
-  for (int r = 0; r < d.B; ++r) { const float x = d.h1[(size_t)r * d.ld + j] - mu; q = fmaf(x, x, q); }
-  const float istd = rsqrtf(q / d.B + eps);
-  d.istd[j] = istd;
+  if (ok) for (int r = sl; r < d.B; r += BN_SLICES) { const float x = d.h1[(size_t)r * d.ld + j] - mu; q = fmaf(x, x, q); }
+  red[1][sl][cx] = q;
+  __syncthreads();
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < BN_SLICES; ++i) var += red[1][i][cx];
+  if (!ok) return;
+  const float istd = rsqrtf(var / d.B + eps);
+  if (sl == 0) d.istd[j] = istd;
   const float g = d.gamma[j], b = d.beta[j];
-  for (int r = 0; r < d.B; ++r) {
+  for (int r = sl; r < d.B; r += BN_SLICES) {
     const float xh = (d.h1[(size_t)r * d.ld + j] - mu) * istd;
     d.xhat[(size_t)r * d.ld + j] = xh;
     const float u = fmaf(g, xh, b);
@@ -248,20 +265,27 @@ __global__ void __launch_bounds__(128) k_bn_fwd(const BnDesc* __restrict__ descs
 }
 
 // BN backward + softplus' of the layer in front of it (G layer 1): du -> dgamma, dbeta, dz1.
-__global__ void __launch_bounds__(128) k_bn_bwd(const BnDesc* __restrict__ descs, int tf32) {
+__global__ void __launch_bounds__(256) k_bn_bwd(const BnDesc* __restrict__ descs, int tf32) {
+  __shared__ float red[2][BN_SLICES][BN_COLS];
   const BnDesc d = descs[blockIdx.z];
-  const int j = blockIdx.x * 128 + threadIdx.x;
-  if (j >= d.W) return;
-  float s1 = 0.f, s2 = 0.f;
-  for (int r = 0; r < d.B; ++r) {
+  const int cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
+  const int j = blockIdx.x * BN_COLS + cx;
+  const bool ok = j < d.W;
+  float p1 = 0.f, p2 = 0.f;
+  if (ok) for (int r = sl; r < d.B; r += BN_SLICES) {
     const float du = d.du[(size_t)r * d.ld + j];
-    s1 += du;
-    s2 = fmaf(du, d.xhat[(size_t)r * d.ld + j], s2);
+    p1 += du;
+    p2 = fmaf(du, d.xhat[(size_t)r * d.ld + j], p2);
   }
-  d.g_gamma[j] = s2;
-  d.g_beta[j] = s1;
+  red[0][sl][cx] = p1; red[1][sl][cx] = p2;
+  __syncthreads();
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < BN_SLICES; ++i) { s1 += red[0][i][cx]; s2 += red[1][i][cx]; }
+  if (!ok) return;
+  if (sl == 0) { d.g_gamma[j] = s2; d.g_beta[j] = s1; }
   const float g = d.gamma[j], istd = d.istd[j], invB = 1.0f / d.B;
-  for (int r = 0; r < d.B; ++r) {
+  for (int r = sl; r < d.B; r += BN_SLICES) {
     const float xh = d.xhat[(size_t)r * d.ld + j];
     const float dxh = d.du[(size_t)r * d.ld + j] * g;
     const float dh1 = istd * (dxh - invB * g * s1 - xh * invB * g * s2);
@@ -323,21 +347,31 @@ k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, 
 }
 
 // Feature matching (mr_gan.py:152-154): rows [0,B) = fake, [B,2B) = real mid activations.
-// Writes dZ5 (already multiplied by ReLU') for the fake rows.
-__global__ void __launch_bounds__(256)
+// Writes dZ5 (already multiplied by ReLU') for the fake rows.  1024 threads = 256 columns x 4 row slices.
+__global__ void __launch_bounds__(1024)
 k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total, int t, int B,
      int tf32) {
   __shared__ float sh[32];
+  __shared__ float red[2][4][256];
   const LossDesc d = descs[blockIdx.z];
+  const int cx = threadIdx.x & 255, sl = threadIdx.x >> 8;
   float s = 0.f;
-  for (int j = threadIdx.x; j < d.Wmid; j += blockDim.x) {
+  for (int j0 = 0; j0 < d.Wmid; j0 += 256) {
+    const int j = j0 + cx;
+    const bool ok = j < d.Wmid;
     float mg = 0.f, mr = 0.f;
-    for (int r = 0; r < B; ++r) { mg += d.mid[(size_t)r * d.ldmid + j]; mr += d.mid[(size_t)(r + B) * d.ldmid + j]; }
+    if (ok) for (int r = sl; r < B; r += 4) { mg += d.mid[(size_t)r * d.ldmid + j]; mr += d.mid[(size_t)(r + B) * d.ldmid + j]; }
+    __syncthreads();
+    red[0][sl][cx] = mg; red[1][sl][cx] = mr;
+    __syncthreads();
+    if (!ok) continue;
+    mg = red[0][0][cx] + red[0][1][cx] + red[0][2][cx] + red[0][3][cx];
+    mr = red[1][0][cx] + red[1][1][cx] + red[1][2][cx] + red[1][3][cx];
     const float diff = (mg - mr) / B;
-    s = fmaf(diff, diff, s);
+    if (sl == 0) s = fmaf(diff, diff, s);
     float g = 2.0f * diff / ((float)d.Wmid * B);
     if (tf32) g = rna_tf32(g);
-    for (int r = 0; r < B; ++r)
+    for (int r = sl; r < B; r += 4)
       d.dmid[(size_t)r * d.lddmid + j] = (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : 0.f;
   }
   s = block_sum(s, sh);

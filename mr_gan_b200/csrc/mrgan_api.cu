@@ -492,7 +492,7 @@ void launch_adam(mrgan_handle* h, int f0, int nfl, int net) {
 
 void enqueue_gen_fwd(mrgan_handle* h, int f0, int nfl, int op_g3) {
   launch_gemm(h, OP_G1, f0, nfl, 0);
-  const dim3 bng((kGH + 127) / 128, 1, nfl);
+  const dim3 bng((kGH + 127) / 128, 1, nfl), bnf((kGH + BN_COLS - 1) / BN_COLS, 1, nfl);
   const int tf32 = h->cfg.precision == MRGAN_PREC_TF32;
   if (h->dp_world > 1) {      // batch statistics over the GLOBAL batch: local sums -> NVLink all-reduce -> apply
     k_bn_stats<<<bng, 128, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0);
@@ -500,7 +500,7 @@ void enqueue_gen_fwd(mrgan_handle* h, int f0, int nfl, int op_g3) {
     k_bn_apply<<<bng, 128, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, h->cfg.bn_eps, tf32, h->hp.dp_bg);
     h->launches += 2;
   } else {
-    k_bn_fwd<<<bng, 128, 0, h->stream>>>(h->d_bn + f0, h->cfg.bn_eps, tf32);
+    k_bn_fwd<<<bnf, 256, 0, h->stream>>>(h->d_bn + f0, h->cfg.bn_eps, tf32);
     h->launches++;
   }
   launch_gemm(h, OP_G2, f0, nfl, 0);
@@ -542,7 +542,7 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
                                                        c.precision == MRGAN_PREC_TF32, h->hp.dp_bg, h->dp_world);
     h->launches += 2;
   } else {
-    k_fm<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B, c.precision == MRGAN_PREC_TF32);
+    k_fm<<<dim3(1, 1, nfl), 1024, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B, c.precision == MRGAN_PREC_TF32);
     h->launches++;
   }
   for (int l = 5; l >= 2; --l) launch_gemm(h, OP_DX2G + l - 2, f0, nfl, 0);
@@ -559,7 +559,7 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
     k_bn_bwd_apply<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, c.precision == MRGAN_PREC_TF32, h->hp.dp_bg);
     h->launches += 2;
   } else {
-    k_bn_bwd<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, c.precision == MRGAN_PREC_TF32);
+    k_bn_bwd<<<dim3((kGH + BN_COLS - 1) / BN_COLS, 1, nfl), 256, 0, h->stream>>>(h->d_bn + f0, c.precision == MRGAN_PREC_TF32);
     h->launches++;
   }
   fork_side(h);
