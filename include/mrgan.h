@@ -102,6 +102,14 @@ int  mrgan_load_fold(mrgan_handle* h, int fold,
                      const float* x_train, const int32_t* y_train,
                      const float* x_test, const int32_t* y_test);
 
+/* Device-side fold preparation (replaces the host work of mr_gan.py:96-101 and the per-fold upload):
+ * the raw feature matrix of a sweep is uploaded ONCE per handle (all folds of a table share it, mr_gan.py:250-257);
+ * a fold is then cut on the device from row indices: StandardScaler statistics over its training rows (float64
+ * accumulation, population variance, zero-variance guard, like sklearn), scaled X_train in the given (already shuffled)
+ * order, scaled X_test, gathered labels.  slot < 8. */
+int  mrgan_load_dataset(mrgan_handle* h, int slot, const float* x, const int32_t* y, int n_rows, int D);
+int  mrgan_prepare_fold(mrgan_handle* h, int fold, int slot, const int32_t* train_rows, const int32_t* test_rows);
+
 /* The three K.function callables, one fold at a time, HOST buffers:
  *   train_batch_disc([1, x_lab, labels, x_unl, noise]) -> [loss_lab, loss_unl, train_err]  mr_gan.py:169
  *   train_batch_gen ([1, x_unl, noise])               -> loss_gen                          mr_gan.py:170
@@ -155,7 +163,7 @@ int  mrgan_time_op(mrgan_handle* h, int which, int reps, float* ms_avg);
 /* Debug/test hook: copy an intermediate buffer of the last step of one fold to the host
  * (dst is [rows, cols] dense).  which: 0..5 = noisy layer inputs a[l], 10+l = post-ReLU h[l],
  * 20+l = dZ[l], 30 = logits, 31 = dlogits, 32 = dFake, 40 = z, 41 = G h1, 42 = G BN out,
- * 43 = G h2, 44 = G dZ2, 45 = G dU, 46 = G dZ1. */
+ * 43 = G h2, 44 = G dZ2, 45 = G dU, 46 = G dZ1, 50 = resident X_train, 51 = resident X_test. */
 int  mrgan_debug_buffer(mrgan_handle* h, int fold, int which, float* dst, int rows, int cols);
 /* Test hook: one stand-alone GEMM through the step's kernels (use_tc = 1: tcgen05 path, 0: fp32 path).
  * mode 0: C[M,N] = A[M,K] B[K,N]   mode 1: C[M,N] = A[M,K] B[N,K]^T   mode 2: C[M,N] = A[K,M]^T B[K,N]

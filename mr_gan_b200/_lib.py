@@ -47,6 +47,8 @@ SYMBOLS = {
     "mrgan_get_adam": (C.c_int, [_H, C.c_int, C.c_int, _fp, _fp, C.c_int64]),
     "mrgan_get_counters": (C.c_int, [_H, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mrgan_load_fold": (C.c_int, [_H, C.c_int, _fp, _ip, _fp, _ip]),
+    "mrgan_load_dataset": (C.c_int, [_H, C.c_int, _fp, _ip, C.c_int, C.c_int]),
+    "mrgan_prepare_fold": (C.c_int, [_H, C.c_int, C.c_int, _ip, _ip]),
     "mrgan_disc_step": (C.c_int, [_H, C.c_int, _fp, _ip, _fp, _fp, _fp]),
     "mrgan_gen_step": (C.c_int, [_H, C.c_int, _fp, _fp, _fp]),
     "mrgan_test_batch": (C.c_int, [_H, C.c_int, _fp, _ip, C.c_int, _fp]),

@@ -598,3 +598,37 @@ __global__ void k_fill_normal(float* __restrict__ dst, const FoldState* __restri
   const FoldState& fs = folds[fold];
   dst[i] = normal1(fs.key0, fs.key1, (uint32_t)(row0 + r), (uint32_t)c, (uint32_t)step, (uint32_t)tid);
 }
+
+
+// ------------------------------------------------------------------ device-side fold preparation (mr_gan.py:96-101)
+// StandardScaler.fit over the training rows of a fold: per-column sum and sum of squares in float64.
+__global__ void __launch_bounds__(128)
+k_col_stats(const float* __restrict__ X, int ldx, const int* __restrict__ rows, int n_rows, int D, double* __restrict__ stats) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= D) return;
+  double s = 0.0, q = 0.0;
+  for (int i = blockIdx.y; i < n_rows; i += gridDim.y) {
+    const double x = (double)X[(size_t)rows[i] * ldx + c];
+    s += x; q += x * x;
+  }
+  atomicAdd(&stats[c], s);
+  atomicAdd(&stats[D + c], q);
+}
+
+// StandardScaler.transform + row gather: out[i, c] = float((X[rows[i], c] - mean_c) / std_c), std 0 -> 1 (sklearn).
+__global__ void __launch_bounds__(128)
+k_scale_gather(const float* __restrict__ X, int ldx, const int* __restrict__ rows, int n_rows, int D, const double* __restrict__ stats,
+               int n_fit, float* __restrict__ out, int ldo, const int* __restrict__ y_src, int* __restrict__ y_out, int tf32) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= D) return;
+  const double mean = stats[c] / n_fit;
+  double var = stats[D + c] / n_fit - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double sd = sqrt(var);
+  if (sd < 1e-300 || var <= 10.0 * 2.220446049250313e-16 * fabs(mean) * fabs(mean)) sd = 1.0;   // constant column
+  for (int i = blockIdx.y; i < n_rows; i += gridDim.y) {
+    const float v = (float)(((double)X[(size_t)rows[i] * ldx + c] - mean) / sd);
+    out[(size_t)i * ldo + c] = tf32 ? rna_tf32(v) : v;
+    if (c == 0 && y_out) y_out[i] = y_src[rows[i]];
+  }
+}

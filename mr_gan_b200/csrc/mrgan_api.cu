@@ -108,6 +108,9 @@ struct mrgan_handle {
   std::string err;
   AdamHyper hp;
   // data-parallel mode (mrgan_dp_init): NCCL communicator + buffers of the all-reduced batch statistics
+  // device-resident raw datasets (mrgan_load_dataset) and scratch of the device-side fold preparation
+  struct Dataset { float* x = nullptr; int* y = nullptr; int n = 0, D = 0, ld = 0; } datasets[8];
+  double* d_prep_stats = nullptr; int* d_prep_rows = nullptr; int prep_rows_cap = 0, prep_stats_cap = 0;
   int dp_world = 1, dp_rank = 0;
   void* nccl_comm = nullptr;
   float* d_dpmem = nullptr; DpBufs* d_dpbufs = nullptr;
@@ -1017,6 +1020,9 @@ int mrgan_destroy(mrgan_handle* h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& ds : h->datasets) { if (ds.x) cudaFree(ds.x); if (ds.y) cudaFree(ds.y); }
+  if (h->d_prep_stats) cudaFree(h->d_prep_stats);
+  if (h->d_prep_rows) cudaFree(h->d_prep_rows);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   if (h->d_dpmem) cudaFree(h->d_dpmem);
   if (h->d_dpbufs) cudaFree(h->d_dpbufs);
@@ -1132,6 +1138,64 @@ int mrgan_load_fold(mrgan_handle* h, int fold, const float* x_train, const int32
     h->launches++;
   }
   CK(cudaStreamSynchronize(h->stream));
+  b.loaded = true;
+  return MRGAN_OK;
+}
+
+int mrgan_load_dataset(mrgan_handle* h, int slot, const float* x, const int32_t* y, int n_rows, int D) {
+  if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
+  if (slot < 0 || slot >= 8 || !x || !y || n_rows < 1 || D < 1) return fail(h, MRGAN_ERR_ARG, "load_dataset: bad argument");
+  for (int i = 0; i < n_rows; ++i)
+    if (y[i] < 0 || y[i] >= h->cfg.n_classes) return fail(h, MRGAN_ERR_ARG, "load_dataset: label out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = finish_pending(h); if (rc) return rc;
+  mrgan_handle::Dataset& ds = h->datasets[slot];
+  if (ds.x) { cudaFree(ds.x); cudaFree(ds.y); ds.x = nullptr; ds.y = nullptr; }
+  ds.n = n_rows; ds.D = D; ds.ld = pitch4(D);
+  CK(cudaMalloc(&ds.x, (size_t)n_rows * ds.ld * sizeof(float)));
+  CK(cudaMalloc(&ds.y, (size_t)n_rows * sizeof(int)));
+  CK(cudaMemcpy2DAsync(ds.x, (size_t)ds.ld * sizeof(float), x, (size_t)D * sizeof(float), (size_t)D * sizeof(float), n_rows,
+                       cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(ds.y, y, (size_t)n_rows * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MRGAN_OK;
+}
+
+int mrgan_prepare_fold(mrgan_handle* h, int fold, int slot, const int32_t* train_rows, const int32_t* test_rows) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (slot < 0 || slot >= 8 || !h->datasets[slot].x) return fail(h, MRGAN_ERR_STATE, "prepare_fold: dataset slot is empty");
+  if (!train_rows || !test_rows) return fail(h, MRGAN_ERR_ARG, "prepare_fold: null pointer");
+  const mrgan_handle::Dataset& ds = h->datasets[slot];
+  const mrgan_fold_shape& s = h->shapes[fold];
+  if (ds.D != s.D) return fail(h, MRGAN_ERR_ARG, "prepare_fold: dataset width differs from the fold's D");
+  for (int i = 0; i < s.n_train; ++i) if ((unsigned)train_rows[i] >= (unsigned)ds.n) return fail(h, MRGAN_ERR_ARG, "prepare_fold: train row out of range");
+  for (int i = 0; i < s.n_test; ++i) if ((unsigned)test_rows[i] >= (unsigned)ds.n) return fail(h, MRGAN_ERR_ARG, "prepare_fold: test row out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  const int nrows = s.n_train + s.n_test;
+  if (nrows > h->prep_rows_cap) {
+    if (h->d_prep_rows) cudaFree(h->d_prep_rows);
+    CK(cudaMalloc(&h->d_prep_rows, (size_t)nrows * sizeof(int)));
+    h->prep_rows_cap = nrows;
+  }
+  if (2 * s.D > h->prep_stats_cap) {
+    if (h->d_prep_stats) cudaFree(h->d_prep_stats);
+    CK(cudaMalloc(&h->d_prep_stats, (size_t)2 * s.D * sizeof(double)));
+    h->prep_stats_cap = 2 * s.D;
+  }
+  FoldBuffers& b = h->fb[fold];
+  CK(cudaMemcpyAsync(h->d_prep_rows, train_rows, (size_t)s.n_train * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->d_prep_rows + s.n_train, test_rows, (size_t)s.n_test * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->d_prep_stats, 0, (size_t)2 * s.D * sizeof(double), h->stream));
+  const int gx = (s.D + 127) / 128;
+  k_col_stats<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows, s.n_train, s.D, h->d_prep_stats);
+  k_scale_gather<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows, s.n_train, s.D, h->d_prep_stats, s.n_train,
+                                                     b.xtr, pitch4(s.D), ds.y, b.ytr, 0);
+  k_scale_gather<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows + s.n_train, s.n_test, s.D, h->d_prep_stats, s.n_train,
+                                                     b.xte, b.lda[0], ds.y, b.yte, h->cfg.precision == MRGAN_PREC_TF32);
+  h->launches += 3;
+  CK(cudaStreamSynchronize(h->stream));     // the pageable index arrays are borrowed only for the call
+  CK(cudaGetLastError());
   b.loaded = true;
   return MRGAN_OK;
 }
@@ -1472,6 +1536,8 @@ int mrgan_debug_buffer(mrgan_handle* h, int fold, int which, float* dst, int row
   else if (which >= 21 && which <= 25) { src = b.dz[which - 20]; ld = b.ldz[which - 20]; }
   else if (which == 30) { src = b.lg; ld = pitch4(K); }
   else if (which == 31) { src = b.dlg; ld = pitch4(K); }
+  else if (which == 50) { src = b.xtr; ld = pitch4(D); }
+  else if (which == 51) { src = b.xte; ld = b.lda[0]; }
   else if (gan && which == 32) { src = b.dfake; ld = pitch4(D); }
   else if (gan && which == 40) { src = b.zb; ld = pitch4(nd + 1); }
   else if (gan && which == 41) { src = b.h1g; ld = kGH; }

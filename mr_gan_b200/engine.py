@@ -162,6 +162,22 @@ class FoldGroup:
         self._chk(self.lib.mrgan_load_fold(self._h, fold, _lib.fptr(x_train), _lib.iptr(y_train),
                                            _lib.fptr(x_test), _lib.iptr(y_test)))
 
+    def load_dataset(self, slot, x, y):
+        """Upload the raw feature matrix of a sweep once; folds are then cut on the device (prepare_fold)."""
+        x, y = _f32(x), _i32(y)
+        if x.ndim != 2 or y.shape != (x.shape[0],):
+            raise ValueError("load_dataset: x must be [n, D] and y [n]")
+        self._chk(self.lib.mrgan_load_dataset(self._h, int(slot), _lib.fptr(x), _lib.iptr(y), x.shape[0], x.shape[1]))
+
+    def prepare_fold(self, fold, slot, train_rows, test_rows):
+        """Device-side mr_gan.py:96-101: scaler statistics over train_rows, scaled + gathered X_train (in the given,
+        already shuffled order) / X_test, gathered labels."""
+        D, ntr, nte, _ = self.shapes[fold]
+        tr, te = _i32(train_rows), _i32(test_rows)
+        if tr.shape != (ntr,) or te.shape != (nte,):
+            raise ValueError("prepare_fold: expected %d train and %d test rows" % (ntr, nte))
+        self._chk(self.lib.mrgan_prepare_fold(self._h, int(fold), int(slot), _lib.iptr(tr), _lib.iptr(te)))
+
     # ------------------------------------------------------------------ the K.function callables
     def train_batch_disc(self, fold, x_lab, labels, x_unl, noise):
         """mr_gan.py:169 ``train_batch_disc([1, x_lab, labels, x_unl, noise])``."""

@@ -56,3 +56,26 @@ def epoch_indices(rng, n_train, lab_rows, unl_rows=None):
     else:
         u1, u2, _ = (unl_rows[tiled_perm(rng, n_train, len(unl_rows))] for _ in range(3))
     return idx_lab.astype(np.int32), np.asarray(u1, np.int32), np.asarray(u2, np.int32)
+
+
+FoldIndex = namedtuple("FoldIndex", "train_rows test_rows y_train y_test lab_rows unl_rows")
+
+
+def prepare_fold_indices(y, train_idx, test_idx, percentlabeled, percentunlabeled=None, rng=None, n_classes=6):
+    """Index-only version of ``prepare_fold`` for the device-side fold preparation (``FoldGroup.prepare_fold``):
+    the same shuffle and labeled / unlabeled subset selection (mr_gan.py:101-107), but X never leaves the GPU.
+    Draws from ``rng`` exactly like ``prepare_fold(trainTestSets=...)`` does, so both paths pick identical rows."""
+    rng = rng if rng is not None else np.random.default_rng()
+    y = np.asarray(y)
+    train_idx, test_idx = np.asarray(train_idx), np.asarray(test_idx)
+    perm = rng.permutation(len(train_idx))
+    train_rows = train_idx[perm]
+    y_train = y[train_rows]
+    num_labeled = int(10 * percentlabeled)
+    lab_rows = np.concatenate([np.nonzero(y_train == j)[0][:num_labeled] for j in range(n_classes)])
+    unl_rows = None
+    if percentunlabeled is not None:
+        n_unl = num_labeled + int(10 * percentunlabeled)
+        unl_rows = np.concatenate([np.nonzero(y_train == j)[0][:n_unl] for j in range(n_classes)])
+    return FoldIndex(train_rows.astype(np.int32), test_idx.astype(np.int32), y_train.astype(np.int32),
+                     y[test_idx].astype(np.int32), lab_rows, unl_rows)

@@ -40,25 +40,42 @@ def train_gan_folds(jobs, epochs=100, verbose=False, *, seed=0, precision='fp32'
     jobs: list of dicts with keys ``trainTestSets`` (or ``X``, ``y``), ``percentlabeled``,
     ``percentunlabeled`` (optional), ``job_id`` (optional, seeds the fold's streams).
     Returns the list of test errors (mr_gan.py:230,234), one per job."""
-    folds, rngs = [], []
+    folds, rngs, slots = [], [], {}
     for i, job in enumerate(jobs):
         rng = np.random.default_rng([int(seed), int(job.get('job_id', i))])
-        folds.append(foldprep.prepare_fold(job.get('X'), job.get('y'), job['percentlabeled'],
-                                           job.get('percentunlabeled'), job.get('trainTestSets'), rng))
+        if 'train_idx' in job:      # index job: the fold is cut on the device from the resident dataset
+            folds.append(foldprep.prepare_fold_indices(job['y'], job['train_idx'], job['test_idx'], job['percentlabeled'],
+                                                       job.get('percentunlabeled'), rng))
+            slots.setdefault(id(job['X']), (len(slots), job['X'], job['y']))
+        else:
+            folds.append(foldprep.prepare_fold(job.get('X'), job.get('y'), job['percentlabeled'],
+                                               job.get('percentunlabeled'), job.get('trainTestSets'), rng))
         rngs.append(rng)
-    shapes = [(f.x_train.shape[1], f.x_train.shape[0], f.x_test.shape[0], fold_key(seed, job.get('job_id', i)))
-              for i, (f, job) in enumerate(zip(folds, jobs))]
+    if len(slots) > 8:
+        raise ValueError("a fold group may draw from at most 8 datasets")
+
+    def dims(f, job):
+        if isinstance(f, foldprep.FoldIndex):
+            return job['X'].shape[1], len(f.train_rows), len(f.test_rows)
+        return f.x_train.shape[1], f.x_train.shape[0], f.x_test.shape[0]
+
+    shapes = [dims(f, job) + (fold_key(seed, job.get('job_id', i)),) for i, (f, job) in enumerate(zip(folds, jobs))]
     fg = FoldGroup(shapes, model='gan', precision=precision, device=device, batch=batch,
                    eval_each_epoch=eval_each_epoch, shared_t=shared_t)
-    for i, (f, rng) in enumerate(zip(folds, rngs)):
-        D = f.x_train.shape[1]
+    for slot, X, y in slots.values():
+        fg.load_dataset(slot, X, y)            # one upload per dataset; every fold of the group reuses it
+    for i, (f, rng, job) in enumerate(zip(folds, rngs, jobs)):
+        D, ntr, nte = shapes[i][:3]
         if verbose:
             print('Num of class examples in test set:', [int(np.sum(f.y_test == c)) for c in range(len(MATERIALS))])
-            print('X_train:', f.x_train.shape, 'y_train:', f.y_train.shape, 'X_test:', f.x_test.shape, 'y_test:', f.y_test.shape)
+            print('X_train:', (ntr, D), 'y_train:', (ntr,), 'X_test:', (nte, D), 'y_test:', (nte,))
             print('x_labeled:', (len(f.lab_rows), D), 'y_labeled:', (len(f.lab_rows),))
         fg.set_params(i, 1, init_gen(D, rng))       # generator first, as mr_gan.py:110-114 builds it first
         fg.set_params(i, 0, init_disc(D, rng))
-        fg.load_fold(i, f.x_train, f.y_train, f.x_test, f.y_test)
+        if isinstance(f, foldprep.FoldIndex):
+            fg.prepare_fold(i, slots[id(job['X'])][0], f.train_rows, f.test_rows)
+        else:
+            fg.load_fold(i, f.x_train, f.y_train, f.x_test, f.y_test)
     n_train = shapes[0][1]
     if verbose:
         print('Epochs:', epochs)
@@ -105,18 +122,39 @@ def mr_gan(X, y, percentlabeled=50, percentunlabeled=None, epochs=100, trainTest
 
 # ------------------------------------------------------------------ CLI (mr_gan.py:236-341)
 def _kfold_jobs(X, y, seed, **kw):
+    """mr_gan.py:255-257 as index jobs: the split is expressed as row indices into the shared X."""
     skf = StratifiedKFold(n_splits=6, shuffle=True, random_state=seed)            # mr_gan.py:255
-    return [dict(trainTestSets=[X[tr], X[te], y[tr], y[te]], **kw) for tr, te in skf.split(X, y)]
+    return [dict(X=X, y=y, train_idx=tr, test_idx=te, **kw) for tr, te in skf.split(X, y)]
+
+
+def stack_objects(objects):
+    """Leave-one-object-out data as one matrix + per-object row ranges (mr_gan.py:274-278 concatenates per fold)."""
+    names = list(objects)
+    X = np.concatenate([np.asarray(objects[n]['x']) for n in names])
+    y = np.concatenate([np.asarray(objects[n]['y']) for n in names])
+    ends = np.cumsum([len(objects[n]['y']) for n in names])
+    return X, y, {n: (e - len(objects[n]['y']), e) for n, e in zip(names, ends)}
 
 
 def _loo_jobs(objects, **kw):
     """mr_gan.py:274-279: one job per held-out object."""
+    X, y, spans = stack_objects(objects)
+    rows = np.arange(len(y))
     jobs = []
-    for name, data in objects.items():
-        Xtr = np.concatenate([d['x'] for n, d in objects.items() if n != name])
-        ytr = np.concatenate([d['y'] for n, d in objects.items() if n != name])
-        jobs.append(dict(trainTestSets=[Xtr, np.asarray(data['x']), ytr, np.asarray(data['y'])], name=name, **kw))
+    for name, (a, b) in spans.items():
+        jobs.append(dict(X=X, y=y, train_idx=np.concatenate([rows[:a], rows[b:]]), test_idx=rows[a:b], name=name, **kw))
     return jobs
+
+
+def job_rows(j):
+    """(n_train, n_test) of a job in either format."""
+    if 'train_idx' in j:
+        return len(j['train_idx']), len(j['test_idx'])
+    return len(j['trainTestSets'][0]), len(j['trainTestSets'][1])
+
+
+def job_width(j):
+    return j['X'].shape[1] if 'train_idx' in j else j['trainTestSets'][0].shape[1]
 
 
 def main(argv=None):
@@ -142,8 +180,7 @@ def main(argv=None):
         res = sweep.run_sharded(
             jobs, lambda js, dev: train_gan_folds(js, epochs=args.epochs, verbose=args.verbose, seed=seed,
                                                   precision=args.precision, device=dev),
-            group_size=args.group, key=lambda j: (len(j['trainTestSets'][0]), len(j['trainTestSets'][1])),
-            cost=lambda j: j['trainTestSets'][0].shape[1])
+            group_size=args.group, key=job_rows, cost=job_width)
         return res
 
     def report(errors, label='Average error:'):

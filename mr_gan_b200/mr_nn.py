@@ -9,32 +9,47 @@ import numpy as np
 from . import foldprep, sweep
 from .engine import FoldGroup
 from .model import MATERIALS, fold_key, init_disc
-from .mr_gan import MODALITIES, _kfold_jobs, _loo_jobs, dataset
+from .mr_gan import MODALITIES, _kfold_jobs, _loo_jobs, dataset, job_rows, job_width
 
 
 def train_nn_folds(jobs, epochs=100, verbose=False, *, seed=0, precision='fp32', device=0, batch=20):
     """Train a group of independent mr_nn folds side by side; returns test errors (mr_nn.py:118-119)."""
-    folds, rngs = [], []
+    folds, rngs, slots = [], [], {}
     for i, job in enumerate(jobs):
         rng = np.random.default_rng([int(seed), int(job.get('job_id', i))])
-        folds.append(foldprep.prepare_fold(job.get('X'), job.get('y'), job['percentlabeled'], None,
-                                           job.get('trainTestSets'), rng))
+        if 'train_idx' in job:
+            folds.append(foldprep.prepare_fold_indices(job['y'], job['train_idx'], job['test_idx'], job['percentlabeled'], None, rng))
+            slots.setdefault(id(job['X']), (len(slots), job['X'], job['y']))
+        else:
+            folds.append(foldprep.prepare_fold(job.get('X'), job.get('y'), job['percentlabeled'], None,
+                                               job.get('trainTestSets'), rng))
         rngs.append(rng)
     n_lab = len(folds[0].lab_rows)
     if any(len(f.lab_rows) != n_lab for f in folds):
         raise ValueError("folds of one group must have the same number of labeled rows")
     if n_lab % batch:
         raise ValueError("labeled rows (%d) must be a multiple of the batch size (%d)" % (n_lab, batch))
-    shapes = [(f.x_train.shape[1], f.x_train.shape[0], f.x_test.shape[0], fold_key(seed, job.get('job_id', i)))
-              for i, (f, job) in enumerate(zip(folds, jobs))]
+
+    def dims(f, job):
+        if isinstance(f, foldprep.FoldIndex):
+            return job['X'].shape[1], len(f.train_rows), len(f.test_rows)
+        return f.x_train.shape[1], f.x_train.shape[0], f.x_test.shape[0]
+
+    shapes = [dims(f, job) + (fold_key(seed, job.get('job_id', i)),) for i, (f, job) in enumerate(zip(folds, jobs))]
     fg = FoldGroup(shapes, model='nn', precision=precision, device=device, batch=batch)
-    for i, (f, rng) in enumerate(zip(folds, rngs)):
+    for slot, X, y in slots.values():
+        fg.load_dataset(slot, X, y)
+    for i, (f, rng, job) in enumerate(zip(folds, rngs, jobs)):
+        D, ntr, nte = shapes[i][:3]
         if verbose:
             print('Num of class examples in test set:', [int(np.sum(f.y_test == c)) for c in range(len(MATERIALS))])
-            print('X_train:', f.x_train.shape, 'y_train:', f.y_train.shape, 'X_test:', f.x_test.shape, 'y_test:', f.y_test.shape)
-            print('x_labeled:', (n_lab, f.x_train.shape[1]), 'y_labeled:', (n_lab,))
-        fg.set_params(i, 0, init_disc(f.x_train.shape[1], rng))
-        fg.load_fold(i, f.x_train, f.y_train, f.x_test, f.y_test)
+            print('X_train:', (ntr, D), 'y_train:', (ntr,), 'X_test:', (nte, D), 'y_test:', (nte,))
+            print('x_labeled:', (n_lab, D), 'y_labeled:', (n_lab,))
+        fg.set_params(i, 0, init_disc(D, rng))
+        if isinstance(f, foldprep.FoldIndex):
+            fg.prepare_fold(i, slots[id(job['X'])][0], f.train_rows, f.test_rows)
+        else:
+            fg.load_fold(i, f.x_train, f.y_train, f.x_test, f.y_test)
 
     def draw():   # model.fit(shuffle=True): one permutation of the labeled rows per epoch (mr_nn.py:117)
         return np.stack([f.lab_rows[rng.permutation(n_lab)] for f, rng in zip(folds, rngs)]).astype(np.int32)
@@ -81,8 +96,8 @@ def main(argv=None):
             jobs, lambda js, dev: train_nn_folds(js, epochs=args.epochs, verbose=args.verbose, seed=seed,
                                                  precision=args.precision, device=dev),
             group_size=args.group,
-            key=lambda j: (len(j['trainTestSets'][0]), len(j['trainTestSets'][1]), j['percentlabeled']),
-            cost=lambda j: j['trainTestSets'][0].shape[1] * j['percentlabeled'])
+            key=lambda j: job_rows(j) + (j['percentlabeled'],),
+            cost=lambda j: job_width(j) * j['percentlabeled'])
 
     if '2' in args.tables:                      # mr_nn.py:129-146
         say('\n', '-' * 25, 'Testing various amounts of labeled training data', '-' * 25)

@@ -371,3 +371,34 @@ def test_final_accuracy_tf32_vs_fp32_over_seed_set():
     # way); the paired differences must not be biased
     d = acc["tf32"] - acc["fp32"]
     assert abs(np.median(d)) <= 0.01 and np.abs(d).mean() <= 0.04
+
+
+def test_device_side_fold_preparation_matches_host_path():
+    """mrgan_load_dataset + mrgan_prepare_fold (scaler statistics, scaling, gather on the device) == the host's
+    StandardScaler path (mr_gan.py:96-101) followed by mrgan_load_fold; a zero-variance column stays finite."""
+    from mr_gan_b200 import foldprep, synthetic
+    X, y = synthetic.synthetic_dataset(1, forcetempTime=0.3, pokes=5, seed=2)          # [360, 30]
+    X = X.astype(np.float32)
+    X[:, 7] = 3.25                                                                       # constant column
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(360)
+    tr, te = np.sort(perm[:300]), np.sort(perm[300:])
+    fi = foldprep.prepare_fold_indices(y, tr, te, 1, None, np.random.default_rng(9))
+    fh = foldprep.prepare_fold(None, None, 1, None, [X[tr], X[te], y[tr], y[te]], np.random.default_rng(9))
+    for prec in ("fp32", "tf32"):
+        with FoldGroup([(30, 300, 60, 1), (30, 300, 60, 1)], precision=prec, batch=10) as fg:     # same noise key
+            fg.load_dataset(0, X, y)
+            fg.prepare_fold(0, 0, fi.train_rows, fi.test_rows)
+            fg.load_fold(1, fh.x_train, fh.y_train, fh.x_test, fh.y_test)
+            a, b = fg.debug_buffer(0, 50, 300, 30), fg.debug_buffer(1, 50, 300, 30)
+            np.testing.assert_allclose(a, b, rtol=2e-6, atol=2e-6)
+            np.testing.assert_allclose(a, fh.x_train, rtol=2e-6, atol=2e-6)
+            assert np.isfinite(a).all() and np.abs(a[:, 7]).max() == 0.0
+            np.testing.assert_allclose(fg.debug_buffer(0, 51, 60, 30), fg.debug_buffer(1, 51, 60, 30), rtol=2e-6, atol=2e-6)
+            # same labels: one epoch on identical weights/indices gives the same supervised statistics
+            pD, pG = model.init_disc(30, rng), model.init_gen(30, rng)
+            for f in (0, 1):
+                fg.set_params(f, 0, pD); fg.set_params(f, 1, pG)
+            idx = foldprep.epoch_indices(np.random.default_rng(3), 300, fi.lab_rows)
+            st = fg.train_epoch(*[np.stack([a_, a_]) for a_ in idx])
+            assert abs(st[0, 2] - st[1, 2]) <= 2.0 / 300 and abs(st[0, 0] - st[1, 0]) <= 5e-3 * abs(st[1, 0])

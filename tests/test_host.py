@@ -96,9 +96,20 @@ def test_cli_surface_matches_reference_flags():
             mod.main([])                                       # --tables is required (mr_gan.py:240)
     assert mg.MODALITIES[5] == 'Force, Temperature, and Contact Mic'
     jobs = mg._kfold_jobs(*synthetic.synthetic_dataset(1, forcetempTime=0.1, pokes=2, seed=0), 0, percentlabeled=1)
-    assert len(jobs) == 6 and jobs[0]['trainTestSets'][0].shape == (120, 10)
+    assert len(jobs) == 6 and mg.job_rows(jobs[0]) == (120, 24) and mg.job_width(jobs[0]) == 10
     loo = mg._loo_jobs(synthetic.synthetic_dataset(1, forcetempTime=0.1, pokes=2, seed=0, leaveObjectOut=True), percentlabeled=1)
-    assert len(loo) == 72 and loo[0]['trainTestSets'][0].shape == (142, 10) and loo[0]['trainTestSets'][1].shape == (2, 10)
+    assert len(loo) == 72 and mg.job_rows(loo[0]) == (142, 2) and mg.job_width(loo[0]) == 10
+    assert sorted(np.concatenate([loo[5]['train_idx'], loo[5]['test_idx']])) == list(range(144))
+    # index-only fold prep draws from the generator exactly like the host path and picks the same rows
+    X, y = synthetic.synthetic_dataset(1, forcetempTime=0.1, pokes=2, seed=0)
+    j = jobs[0]
+    fi = foldprep.prepare_fold_indices(y, j['train_idx'], j['test_idx'], 0.1, 0.1, np.random.default_rng(5))
+    fh = foldprep.prepare_fold(None, None, 0.1, 0.1, [X[j['train_idx']], X[j['test_idx']], y[j['train_idx']], y[j['test_idx']]],
+                               np.random.default_rng(5))
+    np.testing.assert_array_equal(fi.y_train, fh.y_train)
+    np.testing.assert_array_equal(fi.lab_rows, fh.lab_rows)
+    np.testing.assert_array_equal(fi.unl_rows, fh.unl_rows)
+    np.testing.assert_array_equal(y[fi.train_rows], fh.y_train)
 
 
 # ------------------------------------------------------------------ C-ABI surface (no compute)
