@@ -23,7 +23,8 @@ struct FoldState {
   int iterations;        // Keras `adam.iterations`, shared by D and G (mr_gan.py:165-167)
   int it_net[2];         // per-net counters used when shared_t == 0
   int rng_step;          // number of executed train steps = Philox `step` word
-  float lr_t;            // lr * sqrt(1-b2^t) / (1-b1^t) of the step in flight
+  float lr_t[2];         // lr * sqrt(1-b2^t) / (1-b1^t) of the D step / G step in flight (per net: the D net's
+                         // dW+Adam kernels may still run while the next G step's batch assembly writes its own value)
   int D, n_train, n_test;
   int ldx;               // pitch of x_train
   const float* x_train;  // [n_train, ldx] scaled features (device-resident fold data)

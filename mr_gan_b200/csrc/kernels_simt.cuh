@@ -174,7 +174,7 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
       const int net = (mode == 1) ? 1 : 0;
       const int tt = (hp.shared_t ? fs.iterations : fs.it_net[net]) + 1;
       const double b1t = pow((double)hp.b1, (double)tt), b2t = pow((double)hp.b2, (double)tt);
-      fs.lr_t = (float)((double)hp.lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+      fs.lr_t[net] = (float)((double)hp.lr * sqrt(1.0 - b2t) / (1.0 - b1t));
     }
     if (mode != 1) {
       for (int r = threadIdx.x; r < (mode == 2 ? nrows : B); r += 128)
@@ -553,7 +553,7 @@ k_adam(float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ Vo, co
   const int f = fold_base + blockIdx.y;
   const AdamRange rg = ranges[f];
   FoldState& fs = folds[f];
-  const float lr_t = fs.lr_t;
+  const float lr_t = fs.lr_t[net];
   const float b1 = hp.b1, b2 = hp.b2, eps = hp.eps, c1 = 1.0f - hp.b1, c2 = 1.0f - hp.b2;
   const long long n4 = rg.n >> 2;
   float4* p4 = reinterpret_cast<float4*>(P + rg.off);

@@ -30,7 +30,8 @@ struct alignas(64) TcOp {
   int ME, NE, KE;             // extents: MMA-M (features), MMA-N, contraction
   int bn;                     // MMA-N per tile (multiple of 16, <= 256; multiple of 32 when B is MN-major)
   int epi;                    // EPI_FWD / EPI_DX / EPI_STORE / EPI_ADAM
-  int pad_[3];
+  int net;                    // 0 = discriminator, 1 = generator (which lr_t the fused Adam uses)
+  int pad_[2];
 };
 
 #define TC_KBLK 32            // contraction elements per stage (one 128-byte swizzle row of fp32)
@@ -226,7 +227,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
     const bool noisy = (epi == EPI_FWD) && g.C2 != nullptr && g.sigma != 0.f;
     if (noisy || epi == EPI_ADAM) {
       const FoldState& fs = folds[g.fold];
-      key0 = fs.key0; key1 = fs.key1; step = (uint32_t)fs.rng_step; lr_t = fs.lr_t;
+      key0 = fs.key0; key1 = fs.key1; step = (uint32_t)fs.rng_step; lr_t = fs.lr_t[op.net];
     }
 
     if (epi == EPI_ADAM) {
@@ -372,6 +373,7 @@ struct alignas(64) TcAdamOp {
   CUtensorMap mapP, mapM, mapV;    // Waug, m, v as [rows k, cols n], box = 128 cols x KC rows, no swizzle
   int ME, NE, KE;                  // out-features n, in-features(+1) k, contraction rows r
   int fold;
+  int net;
 };
 
 #define TCA_KC 8
@@ -494,7 +496,7 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
     const int lane_base = 32 * (warp & 3);
     const int nl = lane_base + lane;
     const uint32_t trow = tmem_base + ((uint32_t)lane_base << 16);
-    const float lr_t = folds[op.fold].lr_t;
+    const float lr_t = folds[op.fold].lr_t[op.net];
     const float b1 = hp.b1, b2 = hp.b2, c1 = 1.0f - hp.b1, c2 = 1.0f - hp.b2, eps = hp.eps;
     mbar_wait(tmem_full, 0);
     fence_after();

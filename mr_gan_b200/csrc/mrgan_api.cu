@@ -86,6 +86,7 @@ struct mrgan_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;        // dW (+Adam) kernels run here, concurrently with the latency-bound dX chain
   cudaEvent_t ev_pool[16] = {nullptr}; int ev_next = 0;
+  bool side_open = false;             // work forked to `side` since the last join (joins are no-ops otherwise)
   // the folds of a group are independent, so an epoch is captured as `nchains` parallel chains of kernels (disjoint fold
   // ranges, own main + side stream): one chain's latency-bound small kernels fill the SMs another chain leaves idle
   int nchains = 1;
@@ -456,8 +457,11 @@ void fork_side(mrgan_handle* h) {
   cudaEvent_t e = h->ev_pool[h->ev_next++ & 15];
   cudaEventRecord(e, h->stream);
   cudaStreamWaitEvent(h->side, e, 0);
+  h->side_open = true;
 }
 void join_side(mrgan_handle* h) {
+  if (!h->side_open) return;
+  h->side_open = false;
   cudaEvent_t e = h->ev_pool[h->ev_next++ & 15];
   cudaEventRecord(e, h->side);
   cudaStreamWaitEvent(h->stream, e, 0);
@@ -493,7 +497,14 @@ void launch_adam(mrgan_handle* h, int f0, int nfl, int net) {
   h->launches++;
 }
 
+// The side stream's dW kernels read the step's activation buffers (a[l], dZ[l]), which the NEXT step's batch assembly
+// and forward pass overwrite: every step therefore joins the side stream before it ends (measured: deferring the join
+// past the next step's generator forward gains nothing once several fold chains run concurrently, and would need
+// double-buffered activations).
+bool deferred_join(const mrgan_handle*) { return false; }
+
 void enqueue_gen_fwd(mrgan_handle* h, int f0, int nfl, int op_g3) {
+  if (deferred_join(h)) join_side(h);          // generator weights of the previous G step (GW1..3 on the side stream)
   launch_gemm(h, OP_G1, f0, nfl, 0);
   const dim3 bng((kGH + 127) / 128, 1, nfl), bnf((kGH + BN_COLS - 1) / BN_COLS, 1, nfl);
   const int tf32 = h->cfg.precision == MRGAN_PREC_TF32;
@@ -525,7 +536,7 @@ void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) 
     fork_side(h);                     // dW_l (+Adam) streams HBM on the side while main continues the dX chain
     launch_gemm(h, OP_DW1 + l - 1, f0, nfl, 0, h->side);
   }
-  join_side(h);
+  if (!deferred_join(h) || from_stage) join_side(h);   // deferred: dW1+Adam overlaps the next G step's generator forward
   dp_allreduce_grads(h, 0);
   launch_adam(h, f0, nfl, 0);
   if (from_stage) dp_allreduce(h, h->d_step_stats + ((size_t)t * h->nf + f0) * 4, (size_t)nfl * 4);
@@ -537,6 +548,7 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   const int B = c.batch;
   launch_prep(h, f0, nfl, 1, from_stage, t, 2 * B);
   enqueue_gen_fwd(h, f0, nfl, OP_G3G);
+  if (deferred_join(h)) join_side(h);          // discriminator weights updated by the D step's dW+Adam kernels
   for (int l = 0; l < 5; ++l) launch_gemm(h, OP_D1G + l, f0, nfl, 0);
   if (h->dp_world > 1) {
     k_fm_stats<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, B);
@@ -567,7 +579,7 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   }
   fork_side(h);
   launch_gemm(h, OP_GW1, f0, nfl, 0, h->side);
-  join_side(h);
+  if (!deferred_join(h) || from_stage) join_side(h);
   dp_allreduce_grads(h, 1);
   launch_adam(h, f0, nfl, 1);
   dp_allreduce(h, h->d_step_stats + ((size_t)t * h->nf + f0) * 4, (size_t)nfl * 4);
@@ -594,6 +606,7 @@ void enqueue_nn_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage, in
 
 // test_batch (mr_gan.py:171): phase 0, no noise
 void enqueue_eval(mrgan_handle* h, int f0, int nfl, bool staged, int n_override) {
+  join_side(h);
   launch_gemm(h, staged ? OP_E1S : OP_E1, f0, nfl, n_override);
   for (int l = 1; l < 6; ++l) launch_gemm(h, OP_E2 + l - 1, f0, nfl, n_override);
   k_argmax_err<<<dim3(1, 1, nfl), 256, 0, h->stream>>>((staged ? h->d_eval_s : h->d_eval) + f0, n_override, h->cfg.n_classes);
@@ -659,14 +672,17 @@ int build_graph(mrgan_handle* h, int key, int nb, int n_idx_nn) {
       const int f0 = (int)((long long)h->nf * ch / nch), f1 = (int)((long long)h->nf * (ch + 1) / nch);
       if (f1 <= f0) continue;
       h->stream = h->cmain[ch]; h->side = h->cside[ch];
+      h->side_open = false;
       if (c.model == MRGAN_MODEL_GAN) {
         for (int t = 0; t < nb; ++t) {
           enqueue_disc_step(h, f0, f1 - f0, t, 0);
           enqueue_gen_step(h, f0, f1 - f0, t, 0);
         }
         if (c.eval_each_epoch) enqueue_eval(h, f0, f1 - f0, false, 0);
+        join_side(h);                             // every forked stream must rejoin before the capture ends
       } else {
         for (int t = 0; t < nb; ++t) enqueue_nn_step(h, f0, f1 - f0, t, 0, c.batch);
+        join_side(h);
       }
     }
     h->stream = origin; h->side = origin_side;
@@ -815,6 +831,7 @@ int tc_setup(mrgan_handle* h) {
       TcOp& t = ops[(size_t)op * nf + f];
       const int mode = (!oi.at && !oi.bt) ? 0 : ((!oi.at && oi.bt) ? 1 : 2);
       if (!tc_fill_op(fn, t, g, mode)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+      t.net = (op == OP_GW1 || op == OP_GW2 || op == OP_GW3) ? 1 : 0;
       if (mode == 2) {
         if (h->tc_fused_adam) t.epi = EPI_ADAM;
         const size_t off = (size_t)(g.C - h->Gr);
@@ -836,7 +853,7 @@ int tc_setup(mrgan_handle* h) {
       for (int f = 0; f < nf; ++f) {
         const TcOp& t = ops[(size_t)op * nf + f];
         TcAdamOp& a = aops[(size_t)op * nf + f];
-        a.mapA = t.mapA; a.mapB = t.mapB; a.ME = t.ME; a.NE = t.NE; a.KE = t.KE; a.fold = t.g.fold;
+        a.mapA = t.mapA; a.mapB = t.mapB; a.ME = t.ME; a.NE = t.NE; a.KE = t.KE; a.fold = t.g.fold; a.net = t.net;
         // W / m / v as [rows = in+1, cols = out] with the tensor's pitch; box 128 cols x KC rows, clipped at the logical extents
         if (!make_map(fn, &a.mapP, t.P, t.ME, t.NE, t.g.ldc, TCA_KC, false, 128) ||
             !make_map(fn, &a.mapM, t.Mo, t.ME, t.NE, t.g.ldc, TCA_KC, false, 128) ||
