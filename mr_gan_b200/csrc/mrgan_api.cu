@@ -1167,10 +1167,12 @@ int mrgan_load_dataset(mrgan_handle* h, int slot, const float* x, const int32_t*
   CK(cudaSetDevice(h->cfg.device));
   int rc = finish_pending(h); if (rc) return rc;
   mrgan_handle::Dataset& ds = h->datasets[slot];
-  if (ds.x) { cudaFree(ds.x); cudaFree(ds.y); ds.x = nullptr; ds.y = nullptr; }
+  if (ds.x && (ds.n != n_rows || ds.D != D)) { cudaFree(ds.x); cudaFree(ds.y); ds.x = nullptr; ds.y = nullptr; }
   ds.n = n_rows; ds.D = D; ds.ld = pitch4(D);
-  CK(cudaMalloc(&ds.x, (size_t)n_rows * ds.ld * sizeof(float)));
-  CK(cudaMalloc(&ds.y, (size_t)n_rows * sizeof(int)));
+  if (!ds.x) {       // a re-upload of the same shape reuses the buffers (cudaFree / cudaMalloc synchronise the device)
+    CK(cudaMalloc(&ds.x, (size_t)n_rows * ds.ld * sizeof(float)));
+    CK(cudaMalloc(&ds.y, (size_t)n_rows * sizeof(int)));
+  }
   CK(cudaMemcpy2DAsync(ds.x, (size_t)ds.ld * sizeof(float), x, (size_t)D * sizeof(float), (size_t)D * sizeof(float), n_rows,
                        cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(ds.y, y, (size_t)n_rows * sizeof(int), cudaMemcpyHostToDevice, h->stream));
