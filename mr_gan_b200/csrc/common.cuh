@@ -63,6 +63,13 @@ __host__ __device__ inline int global_row(int L, const AdamHyper& hp) {
   return sec * hp.dp_bg + hp.dp_rank * hp.dp_bloc + (L - sec * hp.dp_bloc);
 }
 
+// Programmatic dependent launch: every kernel of the step chain lets its successor be scheduled as soon as all of its own
+// CTAs are running (launch_dependents at the top) and orders itself after its predecessor with griddepcontrol.wait, which
+// returns once the predecessor grid has completed and its writes are visible.  What a kernel does BEFORE the wait (barrier
+// init, TMEM allocation, descriptor fetch) overlaps the predecessor's tail.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __host__ __device__ inline int pitch4(int w) { return (w + 3) & ~3; }
 
 // ---------------------------------------------------------------- Philox4x32-10

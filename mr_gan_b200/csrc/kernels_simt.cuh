@@ -18,6 +18,8 @@ __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpre
 template <bool AT, bool BT>
 __global__ void __launch_bounds__(256)
 k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ folds, int rows_override, AdamHyper hp) {
+  pdl_launch_dependents();
+  pdl_wait();
   const GemmDesc d = descs[blockIdx.z];
   int M = d.M, K = d.K;
   const int N = d.N;
@@ -163,6 +165,8 @@ k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ fo
 __global__ void __launch_bounds__(128)
 k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, int t, int B, int nrows,
        int noise_dim, float sigma_in, AdamHyper hp, int tf32) {
+  pdl_launch_dependents();
+  pdl_wait();
   FoldState& fs = folds[fold_base + blockIdx.z];
   const int c = blockIdx.x * 128 + threadIdx.x;
   const int rg = blockIdx.y;
@@ -232,6 +236,8 @@ struct BnDesc {
 #define BN_COLS 32
 #define BN_SLICES 8
 __global__ void __launch_bounds__(256) k_bn_fwd(const BnDesc* __restrict__ descs, float eps, int tf32) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[2][BN_SLICES][BN_COLS];
   const BnDesc d = descs[blockIdx.z];
   const int cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
@@ -266,6 +272,8 @@ __global__ void __launch_bounds__(256) k_bn_fwd(const BnDesc* __restrict__ descs
 
 // BN backward + softplus' of the layer in front of it (G layer 1): du -> dgamma, dbeta, dz1.
 __global__ void __launch_bounds__(256) k_bn_bwd(const BnDesc* __restrict__ descs, int tf32) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[2][BN_SLICES][BN_COLS];
   const BnDesc d = descs[blockIdx.z];
   const int cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
@@ -306,6 +314,8 @@ struct LossDesc {
 __global__ void __launch_bounds__(256)
 k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total,
             int t, int B, int K, float w_unl, int tf32, int Bg) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sh[32];
   const LossDesc d = descs[blockIdx.z];   // B rows per section on this rank, Bg in the global batch (means are over Bg)
   float s_lab = 0.f, s_unl = 0.f, s_err = 0.f;
@@ -351,6 +361,8 @@ k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, 
 __global__ void __launch_bounds__(1024)
 k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total, int t, int B,
      int tf32) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sh[32];
   __shared__ float red[2][4][256];
   const LossDesc d = descs[blockIdx.z];
@@ -382,6 +394,8 @@ k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fol
 __global__ void __launch_bounds__(256)
 k_loss_mse(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total,
            int t, int n, int rows_total, int K, int tf32) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sh[32];
   const LossDesc d = descs[blockIdx.z];
   float s_loss = 0.f, s_acc = 0.f;
@@ -507,6 +521,8 @@ struct EvalDesc { const float* logits; int ld; const int* y; int n; int n_batche
 // out[2] = mse vs one-hot over all rows (mr_nn.py:118 evaluate()[0]).
 __global__ void __launch_bounds__(256)
 k_argmax_err(const EvalDesc* __restrict__ descs, int n_override, int K) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sh[32];
   const EvalDesc d = descs[blockIdx.z];
   const int n = n_override > 0 ? n_override : d.n;
@@ -531,6 +547,8 @@ k_argmax_err(const EvalDesc* __restrict__ descs, int n_override, int K) {
 // Means over the epoch's batches (mr_gan.py:215-217) -> epoch_stats[f][0..3]; [4] = batch-wise test error.
 __global__ void k_epoch_reduce(const float* __restrict__ step_stats, const EvalDesc* __restrict__ evals,
                                float* __restrict__ epoch_stats, int nf, int nb, int with_eval) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int f = blockIdx.x, j = threadIdx.x;
   if (j < 4) {
     float s = 0.f;
@@ -550,6 +568,8 @@ struct AdamRange { long long off; long long n; };   // n multiple of 4, off 16B 
 __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ Vo, const float* __restrict__ G,
        const AdamRange* __restrict__ ranges, FoldState* __restrict__ folds, int fold_base, int net, AdamHyper hp) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int f = fold_base + blockIdx.y;
   const AdamRange rg = ranges[f];
   FoldState& fs = folds[f];

@@ -126,7 +126,8 @@ template <bool A_MN, bool B_MN, int STAGES, int TMEM_COLS, int MINB, int EPW>
 __global__ void __launch_bounds__(64 + 32 * EPW, MINB)
 k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_override, AdamHyper hp) {
   using namespace tc;
-  const TcOp& op = ops[blockIdx.z];
+  pdl_launch_dependents();
+  const TcOp& op = ops[blockIdx.z];      // descriptor tables are written once at handle creation: safe before pdl_wait()
   const int ME = op.ME, KE = op.KE, bn = op.bn;
   int NE = op.NE;
   if (rows_override > 0 && !B_MN) NE = rows_override;      // fewer batch rows (G step)
@@ -160,6 +161,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();                             // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -395,6 +397,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __global__ void __launch_bounds__(192, 2)
 k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, AdamHyper hp) {
   using namespace tc;
+  pdl_launch_dependents();
   constexpr int STAGES = 2, KC = TCA_KC, NB = TCA_NB;
   constexpr uint32_t STAGE_BYTES = 2 * 128 * 128;            // A (4 x 4 KB blocks) + B (4 x 4 KB blocks)
   constexpr uint32_t ARR_BYTES = KC * 128 * 4;               // one array (W, m or v) of one chunk
@@ -435,6 +438,7 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {

@@ -86,6 +86,8 @@ struct mrgan_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;        // dW (+Adam) kernels run here, concurrently with the latency-bound dX chain
   cudaEvent_t ev_pool[16] = {nullptr}; int ev_next = 0;
+  bool use_pdl = false;               // programmatic dependent launch between the kernels of a step: opt-in (MRGAN_PDL=1);
+                                      // measured neutral at 74 folds/GPU and -17 % at 12 (early-resident dependents hold SM resources)
   bool side_open = false;             // work forked to `side` since the last join (joins are no-ops otherwise)
   // the folds of a group are independent, so an epoch is captured as `nchains` parallel chains of kernels (disjoint fold
   // ranges, own main + side stream): one chain's latency-bound small kernels fill the SMs another chain leaves idle
@@ -393,6 +395,21 @@ void init_ones(mrgan_handle* h) {
 }
 
 
+// ------------------------------------------------------------------ kernel launch with programmatic stream serialization
+template <typename... KArgs, typename... Args>
+void launch_k(mrgan_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = h->use_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  h->launches++;
+}
+
 // ------------------------------------------------------------------ NCCL (resolved at run time: no link dependency)
 struct NcclId { char b[128]; };
 struct NcclApi {
@@ -445,10 +462,9 @@ void launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override, cu
   if (h->cfg.precision == MRGAN_PREC_TF32 && tc_launch_gemm(h, op, f0, nfl, rows_override, st)) return;
 #endif
   dim3 grid((oi.maxN + 63) / 64, (M + 63) / 64, nfl);
-  if (!oi.at && !oi.bt) k_gemm_simt<false, false><<<grid, 256, 0, st>>>(d, h->d_folds, rows_override, h->hp);
-  else if (!oi.at && oi.bt) k_gemm_simt<false, true><<<grid, 256, 0, st>>>(d, h->d_folds, rows_override, h->hp);
-  else k_gemm_simt<true, false><<<grid, 256, 0, st>>>(d, h->d_folds, rows_override, h->hp);
-  h->launches++;
+  if (!oi.at && !oi.bt) launch_k(h, k_gemm_simt<false, false>, grid, dim3(256), 0, st, d, (const FoldState*)h->d_folds, rows_override, h->hp);
+  else if (!oi.at && oi.bt) launch_k(h, k_gemm_simt<false, true>, grid, dim3(256), 0, st, d, (const FoldState*)h->d_folds, rows_override, h->hp);
+  else launch_k(h, k_gemm_simt<true, false>, grid, dim3(256), 0, st, d, (const FoldState*)h->d_folds, rows_override, h->hp);
 }
 
 // side stream: fork = "side waits for everything enqueued on main so far", join = the reverse.
@@ -478,9 +494,8 @@ void launch_prep(mrgan_handle* h, int f0, int nfl, int mode, int from_stage, int
   int cols = max_D(h, f0, nfl);
   if (c.noise_dim > cols) cols = c.noise_dim;
   dim3 grid((cols + 127) / 128, (nrows + 3) / 4, nfl);
-  k_prep<<<grid, 128, 0, h->stream>>>(h->d_folds, f0, mode, from_stage, t, c.batch, nrows, c.noise_dim, c.sigma_in, h->hp,
-                                             c.precision == MRGAN_PREC_TF32);
-  h->launches++;
+  launch_k(h, k_prep, grid, dim3(128), 0, h->stream, h->d_folds, f0, mode, from_stage, t, c.batch, nrows, c.noise_dim, c.sigma_in, h->hp,
+           (int)(c.precision == MRGAN_PREC_TF32));
 }
 
 void launch_adam(mrgan_handle* h, int f0, int nfl, int net) {
@@ -493,8 +508,7 @@ void launch_adam(mrgan_handle* h, int f0, int nfl, int net) {
 #ifdef MRGAN_WITH_TC
   if (h->cfg.precision == MRGAN_PREC_TF32 && h->tc_fused_adam) { ranges = h->d_ranges_tc[net]; blocks = 1; }
 #endif
-  k_adam<<<dim3(blocks, nfl), 256, 0, h->stream>>>(h->P, h->Mo, h->Vo, h->Gr, ranges, h->d_folds, f0, net, h->hp);
-  h->launches++;
+  launch_k(h, k_adam, dim3(blocks, nfl), dim3(256), 0, h->stream, h->P, h->Mo, h->Vo, (const float*)h->Gr, ranges, h->d_folds, f0, net, h->hp);
 }
 
 // The side stream's dW kernels read the step's activation buffers (a[l], dZ[l]), which the NEXT step's batch assembly
@@ -514,8 +528,7 @@ void enqueue_gen_fwd(mrgan_handle* h, int f0, int nfl, int op_g3) {
     k_bn_apply<<<bng, 128, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, h->cfg.bn_eps, tf32, h->hp.dp_bg);
     h->launches += 2;
   } else {
-    k_bn_fwd<<<bnf, 256, 0, h->stream>>>(h->d_bn + f0, h->cfg.bn_eps, tf32);
-    h->launches++;
+    launch_k(h, k_bn_fwd, bnf, dim3(256), 0, h->stream, (const BnDesc*)(h->d_bn + f0), h->cfg.bn_eps, tf32);
   }
   launch_gemm(h, OP_G2, f0, nfl, 0);
   launch_gemm(h, op_g3, f0, nfl, 0);
@@ -528,9 +541,8 @@ void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) 
   launch_prep(h, f0, nfl, 0, from_stage, t, 2 * B);
   enqueue_gen_fwd(h, f0, nfl, OP_G3D);
   for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 0);
-  k_loss_disc<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B, c.n_classes, c.unlabeled_weight,
-                                                         c.precision == MRGAN_PREC_TF32, h->hp.dp_bg);
-  h->launches++;
+  launch_k(h, k_loss_disc, dim3(1, 1, nfl), dim3(256), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, B,
+           c.n_classes, c.unlabeled_weight, (int)(c.precision == MRGAN_PREC_TF32), h->hp.dp_bg);
   for (int l = 6; l >= 1; --l) {      // dX first: it reads W_l, which the fused-Adam dW epilogue overwrites
     if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
     fork_side(h);                     // dW_l (+Adam) streams HBM on the side while main continues the dX chain
@@ -557,8 +569,8 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
                                                        c.precision == MRGAN_PREC_TF32, h->hp.dp_bg, h->dp_world);
     h->launches += 2;
   } else {
-    k_fm<<<dim3(1, 1, nfl), 1024, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, B, c.precision == MRGAN_PREC_TF32);
-    h->launches++;
+    launch_k(h, k_fm, dim3(1, 1, nfl), dim3(1024), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, B,
+             (int)(c.precision == MRGAN_PREC_TF32));
   }
   for (int l = 5; l >= 2; --l) launch_gemm(h, OP_DX2G + l - 2, f0, nfl, 0);
   launch_gemm(h, OP_DX1G, f0, nfl, 0);
@@ -574,8 +586,8 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
     k_bn_bwd_apply<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, c.precision == MRGAN_PREC_TF32, h->hp.dp_bg);
     h->launches += 2;
   } else {
-    k_bn_bwd<<<dim3((kGH + BN_COLS - 1) / BN_COLS, 1, nfl), 256, 0, h->stream>>>(h->d_bn + f0, c.precision == MRGAN_PREC_TF32);
-    h->launches++;
+    launch_k(h, k_bn_bwd, dim3((kGH + BN_COLS - 1) / BN_COLS, 1, nfl), dim3(256), 0, h->stream, (const BnDesc*)(h->d_bn + f0),
+             (int)(c.precision == MRGAN_PREC_TF32));
   }
   fork_side(h);
   launch_gemm(h, OP_GW1, f0, nfl, 0, h->side);
@@ -592,9 +604,8 @@ void enqueue_nn_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage, in
   // stale rows contribute nothing to dW/db and every GEMM keeps its static shape
   launch_prep(h, f0, nfl, 2, from_stage, t, n);
   for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 0);
-  k_loss_mse<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_step_stats, f0, h->nf, t, n, h->R, c.n_classes,
-                                                        c.precision == MRGAN_PREC_TF32);
-  h->launches++;
+  launch_k(h, k_loss_mse, dim3(1, 1, nfl), dim3(256), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, n, h->R,
+           c.n_classes, (int)(c.precision == MRGAN_PREC_TF32));
   for (int l = 6; l >= 1; --l) {
     if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
     fork_side(h);
@@ -609,8 +620,8 @@ void enqueue_eval(mrgan_handle* h, int f0, int nfl, bool staged, int n_override)
   join_side(h);
   launch_gemm(h, staged ? OP_E1S : OP_E1, f0, nfl, n_override);
   for (int l = 1; l < 6; ++l) launch_gemm(h, OP_E2 + l - 1, f0, nfl, n_override);
-  k_argmax_err<<<dim3(1, 1, nfl), 256, 0, h->stream>>>((staged ? h->d_eval_s : h->d_eval) + f0, n_override, h->cfg.n_classes);
-  h->launches++;
+  launch_k(h, k_argmax_err, dim3(1, 1, nfl), dim3(256), 0, h->stream, (const EvalDesc*)((staged ? h->d_eval_s : h->d_eval) + f0), n_override,
+           h->cfg.n_classes);
 }
 
 int check_fold(mrgan_handle* h, int fold) {
@@ -899,11 +910,10 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
   if (rows_override > 0 && !oi.at) NE = rows_override;
   dim3 grid((h->tc_maxME[op] + 127) / 128, (NE + bn - 1) / bn, nfl);
   const TcOp* d = h->d_tcops + (size_t)op * h->nf + f0;
-  if (!oi.at && !oi.bt) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(bn, TC_FWD_STAGES), st>>>(d, h->d_folds, rows_override, h->hp);
-  else if (!oi.at && oi.bt) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(bn, TC_FWD_STAGES), st>>>(d, h->d_folds, rows_override, h->hp);
-  else if (h->d_tcadam) k_dw_adam_tc<<<grid, 192, TCA_SMEM_BYTES, st>>>(h->d_tcadam + (size_t)op * h->nf + f0, h->d_folds, h->hp);
-  else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(bn, TC_DW_STAGES), st>>>(d, h->d_folds, 0, h->hp);
-  h->launches++;
+  if (!oi.at && !oi.bt) launch_k(h, K_TC_FWD, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp);
+  else if (!oi.at && oi.bt) launch_k(h, K_TC_DX, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp);
+  else if (h->d_tcadam) launch_k(h, k_dw_adam_tc, grid, dim3(192), (size_t)TCA_SMEM_BYTES, st, (const TcAdamOp*)(h->d_tcadam + (size_t)op * h->nf + f0), h->d_folds, h->hp);
+  else launch_k(h, K_TC_DW, grid, dim3(TC_DW_THREADS), tc_smem_bytes(bn, TC_DW_STAGES), st, d, h->d_folds, 0, h->hp);
   return true;
 }
 
@@ -997,6 +1007,8 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   ok = ok && cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 16 && ok; ++i) ok = cudaEventCreateWithFlags(&h->ev_pool[i], cudaEventDisableTiming) == cudaSuccess;
   {
+    const char* pdl = getenv("MRGAN_PDL");
+    if (pdl) h->use_pdl = atoi(pdl) != 0;
     const char* env = getenv("MRGAN_CHAINS");
     int nch = env ? atoi(env) : (h->nf >= 32 ? 4 : (h->nf >= 8 ? 2 : 1));
     if (nch < 1) nch = 1;
