@@ -80,7 +80,7 @@ def main(argv=None):
     parser.add_argument('--seed', type=int, default=None)
     parser.add_argument('--epochs', type=int, default=100)
     parser.add_argument('--precision', choices=['fp32', 'tf32'], default='fp32')
-    parser.add_argument('--group', type=int, default=12)
+    parser.add_argument('--group', type=int, default=42)
     parser.add_argument('--data-dir', default='data_processed')
     args = parser.parse_args(argv)
     seed = args.seed if args.seed is not None else int(np.random.SeedSequence().entropy % (2 ** 31))
