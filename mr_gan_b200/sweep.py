@@ -4,7 +4,7 @@ mr_gan.py:244-341 / mr_nn.py:129-168) grouped per GPU and sharded over the GPUs 
 Each (modality, labeled %, fold) call of ``mr_gan()`` is independent (fresh models per call,
 mr_gan.py:109-171), so the sweep shards by fold with NO collective: under ``torchrun`` rank r
 takes the job groups r, r+W, r+2W, ... and rank 0 gathers one float per fold through
-``torch.distributed`` (gloo/nccl object gather) and prints in the reference's loop order."""
+``torch.distributed`` (gloo object gather on the host) and prints in the reference's loop order."""
 import os
 
 import numpy as np
@@ -60,8 +60,7 @@ def run_sharded(jobs, train_group, group_size=6, key=lambda j: 0, cost=lambda j:
     if world > 1:
         import torch.distributed as dist
         if not dist.is_initialized() and init_dist:
-            import torch
-            dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+            dist.init_process_group("gloo")      # host-side gather of one float per fold: no GPU collective on this path
         parts = [None] * world
         dist.all_gather_object(parts, mine)
         mine = {}
