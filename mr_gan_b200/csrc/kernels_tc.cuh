@@ -122,7 +122,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
 // MINB: CTAs per SM the register allocation must allow (dW uses 2 so that one CTA's Adam epilogue
 // streams HBM while the other loads operands and runs its MMAs).
 // EPW: epilogue warps (4 or 8; with 8 the accumulator columns are split between two warp groups).
-template <bool A_MN, bool B_MN, int STAGES, int TMEM_COLS, int MINB, int EPW>
+// MT: feature sub-tiles of 128 per CTA (1 or 2).  With MT = 2 the CTA computes 256 features against ONE copy of the
+// batch-side operand tile (two accumulators in TMEM, 2 x 4 MMAs per stage), which halves the activation bytes every
+// SM has to ingest -- the forward / dX mainloops are bound by L2->SM traffic, not by HBM or the tensor pipe -- and each
+// warp group of the epilogue owns one sub-tile.  MT = 2 requires EPW = 8 and TMEM_COLS = 512.
+template <bool A_MN, bool B_MN, int STAGES, int TMEM_COLS, int MINB, int EPW, int MT>
 __global__ void __launch_bounds__(64 + 32 * EPW, MINB)
 k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_override, AdamHyper hp) {
   using namespace tc;
@@ -131,12 +135,12 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   const int ME = op.ME, KE = op.KE, bn = op.bn;
   int NE = op.NE;
   if (rows_override > 0 && !B_MN) NE = rows_override;      // fewer batch rows (G step)
-  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * bn;
+  const int m0 = blockIdx.x * 128 * MT, n0 = blockIdx.y * bn;
   if (m0 >= ME || n0 >= NE) return;                         // uniform per CTA: nothing allocated yet
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)bn * 128, stage_bytes = a_bytes + b_bytes;
+  const uint32_t a_bytes = MT * 128 * 128, b_bytes = (uint32_t)bn * 128, stage_bytes = a_bytes + b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
   uint64_t* full = bars;                    // [STAGES]
   uint64_t* empty = bars + STAGES;          // [STAGES]
@@ -176,9 +180,10 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         const int k0 = kb * TC_KBLK;
         if (A_MN) {
 #pragma unroll
-          for (int b = 0; b < 4; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * 4096, m0 + 32 * b, k0);
+          for (int b = 0; b < 4 * MT; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * 4096, m0 + 32 * b, k0);
         } else {
-          tma_load_2d(&op.mapA, &full[s], sa, k0, m0);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) tma_load_2d(&op.mapA, &full[s], sa + mt * 16384, k0, m0 + 128 * mt);
         }
         if (B_MN) {
           for (int b = 0; b < bn / 32; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * 4096, n0 + 32 * b, k0);
@@ -204,9 +209,12 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
 #pragma unroll
         for (int k = 0; k < TC_KBLK / 8; ++k) {
-          const uint64_t da = smem_desc(sa + k * stepA, lboA, sboA, layA);
           const uint64_t db = smem_desc(sb + k * stepB, lboB, sboB, layB);
-          mma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {      // sub-tile mt: A block at +16 KB, accumulator at TMEM column 256 * mt
+            const uint64_t da = smem_desc(sa + mt * 16384u + k * stepA, lboA, sboA, layA);
+            mma_tf32(tmem_base + 256u * mt, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
         }
         mma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
       }
@@ -215,15 +223,17 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   } else {
     // ===================== epilogue (EPW warps; a warp may only touch TMEM lanes 32*(warp%4)..+31) =====================
     const int lane_base = 32 * (warp & 3);
-    const int chalf = (EPW == 8) ? (((min(bn, NE - n0) + 1) / 2 + 15) & ~15) : bn;   // columns per warp group
-    const int cbeg = (EPW == 8) ? ((warp - 2) >> 2) * chalf : 0;
-    const int f = m0 + lane_base + lane;                  // this thread's feature index (MMA-M)
+    const int wg = (warp - 2) >> 2;                       // epilogue warp group (0 or 1 when EPW == 8)
+    const int sub = (MT == 2) ? wg : 0;                   // MT == 2: one feature sub-tile per warp group
+    const int chalf = (EPW == 8 && MT == 1) ? (((min(bn, NE - n0) + 1) / 2 + 15) & ~15) : bn;   // columns per warp group
+    const int cbeg = (EPW == 8 && MT == 1) ? wg * chalf : 0;
+    const int f = m0 + 128 * sub + lane_base + lane;      // this thread's feature index (MMA-M)
     const bool f_ok = f < ME;
     const GemmDesc g = op.g;             // by value: descriptor fields must not be re-read from HBM around every store
     const int epi = op.epi;
     float* const adamP = op.P; float* const adamM = op.Mo; float* const adamV = op.Vo;
     const int ncols = min(min(bn, NE - n0), cbeg + chalf);      // this warp's column range is [cbeg, ncols)
-    const uint32_t trow = tmem_base + ((uint32_t)lane_base << 16);
+    const uint32_t trow = tmem_base + 256u * sub + ((uint32_t)lane_base << 16);
     uint32_t key0 = 0, key1 = 0, step = 0;
     float lr_t = 0.f;
     const bool noisy = (epi == EPI_FWD) && g.C2 != nullptr && g.sigma != 0.f;

@@ -122,6 +122,7 @@ struct mrgan_handle {
   TcOp* d_tcops = nullptr;            // [NUM_OPS][nf] tensor maps + epilogue descriptors
   int tc_bn[NUM_OPS] = {0}, tc_maxME[NUM_OPS] = {0}, tc_maxNE[NUM_OPS] = {0};
   bool tc_fused_adam = true;          // dW epilogue applies Adam in place (no gradient round trip)
+  bool tc_mt2 = true;                 // forward / dX: 256 features per CTA where the layer is wide enough (MRGAN_MT2=0 disables)
   bool tc_adam_tma = true;            // ... with W/m/v staged through smem by TMA (k_dw_adam_tc) instead of the LSU
   TcAdamOp* d_tcadam = nullptr;       // [NUM_OPS][nf]
   AdamRange* d_ranges_tc[2] = {nullptr, nullptr};   // what is left for k_adam: BN gamma/beta (G), nothing (D)
@@ -767,11 +768,15 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 #define TC_DW_STAGES 2
 #define TC_FWD_THREADS (64 + 32 * 8)
 #define TC_DW_THREADS (64 + 32 * 4)
-#define K_TC_FWD k_gemm_tc<true, false, TC_FWD_STAGES, 256, 1, 8>
-#define K_TC_DX k_gemm_tc<false, false, TC_FWD_STAGES, 256, 1, 8>
-#define K_TC_DW k_gemm_tc<true, true, TC_DW_STAGES, 128, 2, 4>
+#define K_TC_FWD k_gemm_tc<true, false, TC_FWD_STAGES, 256, 1, 8, 1>
+#define K_TC_DX k_gemm_tc<false, false, TC_FWD_STAGES, 256, 1, 8, 1>
+#define K_TC_FWD2 k_gemm_tc<true, false, TC_FWD_STAGES, 512, 1, 8, 2>     // 256 features per CTA (layers >= 500 wide)
+#define K_TC_DX2 k_gemm_tc<false, false, TC_FWD_STAGES, 512, 1, 8, 2>
+#define K_TC_DW k_gemm_tc<true, true, TC_DW_STAGES, 128, 2, 4, 1>
 #define TCA_SMEM_BYTES (2 * 2 * 128 * 128 + TCA_NB * 3 * TCA_KC * 128 * 4 + 256)
-size_t tc_smem_bytes(int bn, int stages) { return 1024 + (size_t)stages * (128 * 128 + (size_t)bn * 128) + 256; }
+size_t tc_smem_bytes(int bn, int stages, int mt = 1) { return 1024 + (size_t)stages * ((size_t)mt * 128 * 128 + (size_t)bn * 128) + 256; }
+// two feature sub-tiles per CTA when the layer is wide enough and the 4-stage ring still fits in 227 KB
+bool tc_use_mt2(int maxME, int bn) { return maxME >= 500 && tc_smem_bytes(bn, TC_FWD_STAGES, 2) <= 227 * 1024; }
 
 int tc_setup(mrgan_handle* h);
 
@@ -786,6 +791,8 @@ EncodeTiledFn tc_encoder() {
 void tc_set_smem_attr() {
   cudaFuncSetAttribute(K_TC_FWD, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
   cudaFuncSetAttribute(K_TC_DX, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
+  cudaFuncSetAttribute(K_TC_FWD2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(K_TC_DX2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(K_TC_DW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(128, TC_DW_STAGES));
   cudaFuncSetAttribute(k_dw_adam_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCA_SMEM_BYTES);
 }
@@ -910,6 +917,13 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
   if (rows_override > 0 && !oi.at) NE = rows_override;
   dim3 grid((h->tc_maxME[op] + 127) / 128, (NE + bn - 1) / bn, nfl);
   const TcOp* d = h->d_tcops + (size_t)op * h->nf + f0;
+  if (!oi.at && h->tc_mt2 && tc_use_mt2(h->tc_maxME[op], bn)) {
+    grid.x = (h->tc_maxME[op] + 255) / 256;
+    const size_t smem = tc_smem_bytes(bn, TC_FWD_STAGES, 2);
+    if (!oi.bt) launch_k(h, K_TC_FWD2, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp);
+    else launch_k(h, K_TC_DX2, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp);
+    return true;
+  }
   if (!oi.at && !oi.bt) launch_k(h, K_TC_FWD, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp);
   else if (!oi.at && oi.bt) launch_k(h, K_TC_DX, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp);
   else if (h->d_tcadam) launch_k(h, k_dw_adam_tc, grid, dim3(192), (size_t)TCA_SMEM_BYTES, st, (const TcAdamOp*)(h->d_tcadam + (size_t)op * h->nf + f0), h->d_folds, h->hp);
@@ -1007,6 +1021,9 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   ok = ok && cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 16 && ok; ++i) ok = cudaEventCreateWithFlags(&h->ev_pool[i], cudaEventDisableTiming) == cudaSuccess;
   {
+#ifdef MRGAN_WITH_TC
+    if (const char* mt2 = getenv("MRGAN_MT2")) h->tc_mt2 = atoi(mt2) != 0;
+#endif
     const char* pdl = getenv("MRGAN_PDL");
     if (pdl) h->use_pdl = atoi(pdl) != 0;
     const char* env = getenv("MRGAN_CHAINS");
