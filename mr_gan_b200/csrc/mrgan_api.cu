@@ -747,6 +747,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2D fp32 tensor [rows, cols] with `pitch` floats per row; box = 32 columns (one 128B swizzle row) x box_rows
+// L2 promotion of the TMA loads: every box row is one 128-byte line of a row-major matrix, so neighbouring boxes /
+// k-blocks touch the adjacent 128 bytes of the same DRAM page; fetching 256 B per miss halves the DRAM activations.
+CUtensorMapL2promotion g_l2_promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+
 bool make_map(EncodeTiledFn fn, CUtensorMap* m, const float* base, int cols, int rows, int pitch, int box_rows,
               bool mn_major, int box_cols = 32) {
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -756,7 +760,7 @@ bool make_map(EncodeTiledFn fn, CUtensorMap* m, const float* base, int cols, int
   return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
             CU_TENSOR_MAP_INTERLEAVE_NONE,
             box_cols != 32 ? CU_TENSOR_MAP_SWIZZLE_NONE : (mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
-            CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            g_l2_promo,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -838,6 +842,9 @@ int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g) {
 int tc_setup(mrgan_handle* h) {
   EncodeTiledFn fn = tc_encoder();
   if (!fn) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if (const char* pr = getenv("MRGAN_L2PROMO"))
+    g_l2_promo = atoi(pr) == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (atoi(pr) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                 : (atoi(pr) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
   const int nf = h->nf;
   std::vector<TcOp> ops((size_t)NUM_OPS * nf);
   memset(ops.data(), 0, ops.size() * sizeof(TcOp));
