@@ -402,3 +402,19 @@ def test_device_side_fold_preparation_matches_host_path():
             idx = foldprep.epoch_indices(np.random.default_rng(3), 300, fi.lab_rows)
             st = fg.train_epoch(*[np.stack([a_, a_]) for a_ in idx])
             assert abs(st[0, 2] - st[1, 2]) <= 2.0 / 300 and abs(st[0, 0] - st[1, 0]) <= 5e-3 * abs(st[1, 0])
+
+
+def test_data_parallel_mode_matches_single_gpu_large_batch():
+    """BASELINE config 5: W ranks x local batch B/W == one GPU at batch B (same weights, global batch and noise stream),
+    replicas bit-identical across ranks.  Needs >= 2 GPUs (tools/dp_check.py under torchrun); skipped on a 1-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for prec in ("fp32", "tf32"):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                            "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "dp_check.py"), "--precision", prec],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "DP PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
