@@ -418,3 +418,27 @@ def test_data_parallel_mode_matches_single_gpu_large_batch():
                             "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "dp_check.py"), "--precision", prec],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "DP PARITY OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("D", [10, 3632, 12032])
+def test_extreme_widths_single_step_pair(precision, D):
+    """Smallest (0.1 s temperature, table 5), widest compact (force+temperature+contact mic) and widest table-5 input
+    (1 s contact mic, 12 032 features): one D step and one G step, EACH from the oracle's exact initial state."""
+    B = 50
+    key = philox.fold_key(6, 2)
+    pD, pG, steps = make_golden.case_inputs(D, B, 40 + D % 7, 1)
+    s = steps[0]
+    want_d = O.GanOracle(pD, pG).disc_step(s['x_lab'], s['labels'], s['x_unl'], s['z_d'], fold_loop.d_noise(key, 0, B, D, 0),
+                                           fold_loop.d_noise(key, 0, B, D, B), fold_loop.d_noise(key, 0, B, D, 2 * B))
+    want_g = O.GanOracle(pD, pG).gen_step(s['x_unl2'], s['z_g'], fold_loop.d_noise(key, 0, B, D, 0), fold_loop.d_noise(key, 0, B, D, B))
+    got = []
+    for which in ("d", "g"):
+        with FoldGroup([(D, 100, 100, _key64(key))], precision=precision) as fg:    # n_test = 100: a leave-one-object-out fold
+            fg.set_params(0, 0, pD)
+            fg.set_params(0, 1, pG)
+            got.append(fg.train_batch_disc(0, s['x_lab'], s['labels'], s['x_unl'], s['z_d']) if which == "d"
+                       else fg.train_batch_gen(0, s['x_unl2'], s['z_g']))
+    np.testing.assert_allclose(got[0][:2], want_d[:2], rtol=LOSS_RTOL[precision])
+    assert abs(got[0][2] - want_d[2]) < 1e-6
+    np.testing.assert_allclose(got[1], want_g, rtol=LOSS_RTOL[precision] if D >= 100 else GEN_RTOL_SMALL_BATCH[precision])
