@@ -1030,6 +1030,7 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   {
 #ifdef MRGAN_WITH_TC
     if (const char* mt2 = getenv("MRGAN_MT2")) h->tc_mt2 = atoi(mt2) != 0;
+    if (const char* at = getenv("MRGAN_ADAM_TMA")) h->tc_adam_tma = atoi(at) != 0;    // 0: LSU epilogue of k_gemm_tc (A/B switch)
 #endif
     const char* pdl = getenv("MRGAN_PDL");
     if (pdl) h->use_pdl = atoi(pdl) != 0;
