@@ -411,6 +411,10 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
   constexpr int STAGES = 2, KC = TCA_KC, NB = TCA_NB;
   constexpr uint32_t STAGE_BYTES = 2 * 128 * 128;            // A (4 x 4 KB blocks) + B (4 x 4 KB blocks)
   constexpr uint32_t ARR_BYTES = KC * 128 * 4;               // one array (W, m or v) of one chunk
+  constexpr uint32_t CHUNK_BYTES = 3 * ARR_BYTES;
+  // chunk buffers: NB dedicated ones + NX carved out of the operand stages once the MMAs have consumed them
+  constexpr int NX = (STAGES * STAGE_BYTES) / CHUNK_BYTES;
+  constexpr int NBUF = NB + NX;
   const TcAdamOp& op = ops[blockIdx.z];
   const int ME = op.ME, NE = op.NE, KE = op.KE;
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;     // n-feature tile (lanes), k-feature tile (columns)
@@ -419,14 +423,15 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
   extern __shared__ __align__(1024) uint8_t smem_dyn[];
   uint8_t* smem = smem_dyn;
   if ((smem_u32(smem) & 1023u) != 0) __trap();                // swizzled TMA tiles need 1024-byte alignment
-  uint8_t* cbuf = smem + STAGES * STAGE_BYTES;                // [NB][3][KC][128] floats
-  uint64_t* bars = reinterpret_cast<uint64_t*>(cbuf + NB * 3 * ARR_BYTES);
+  uint8_t* cbuf = smem + STAGES * STAGE_BYTES;                // NB dedicated chunk buffers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cbuf + NB * CHUNK_BYTES);
   uint64_t* full = bars;                       // [STAGES]   operands landed
   uint64_t* empty = bars + STAGES;             // [STAGES]   operands consumed
-  uint64_t* tmem_full = bars + 2 * STAGES;     //            accumulator complete
-  uint64_t* cfull = bars + 2 * STAGES + 1;     // [NB]       optimizer-state chunk landed
-  uint64_t* cdone = cfull + NB;                // [NB]       chunk updated in smem (128 arrivals)
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(cdone + NB);
+  uint64_t* tmem_full = bars + 2 * STAGES;     //            accumulator complete (2 waiters: epilogue, DMA thread)
+  uint64_t* cfull = bars + 2 * STAGES + 1;     // [NBUF]     optimizer-state chunk landed
+  uint64_t* cdone = cfull + NBUF;              // [NBUF]     chunk updated in smem (128 arrivals)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(cdone + NBUF);
+  auto buf_ptr = [&](int b) -> uint8_t* { return b < NB ? cbuf + (size_t)b * CHUNK_BYTES : smem + (size_t)(b - NB) * CHUNK_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (KE + TC_KBLK - 1) / TC_KBLK;
@@ -437,7 +442,7 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
     prefetch_map(&op.mapA); prefetch_map(&op.mapB); prefetch_map(&op.mapP); prefetch_map(&op.mapM); prefetch_map(&op.mapV);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
-    for (int b = 0; b < NB; ++b) { mbar_init(&cfull[b], 1); mbar_init(&cdone[b], 128); }
+    for (int b = 0; b < NBUF; ++b) { mbar_init(&cfull[b], 1); mbar_init(&cdone[b], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -454,9 +459,9 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
     if (lane == 0) {
       // ---- DMA thread: optimizer-state chunks first (they do not depend on the MMA), then the operands ----
       auto load_chunk = [&](int c) {
-        const int b = c % NB;
-        uint8_t* dst = cbuf + (size_t)b * 3 * ARR_BYTES;
-        mbar_expect_tx(&cfull[b], 3 * ARR_BYTES);
+        const int b = c % NBUF;
+        uint8_t* dst = buf_ptr(b);
+        mbar_expect_tx(&cfull[b], CHUNK_BYTES);
         tma_load_2d(&op.mapP, &cfull[b], dst, m0, n0 + c * KC);
         tma_load_2d(&op.mapM, &cfull[b], dst + ARR_BYTES, m0, n0 + c * KC);
         tma_load_2d(&op.mapV, &cfull[b], dst + 2 * ARR_BYTES, m0, n0 + c * KC);
@@ -475,16 +480,24 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
 #pragma unroll
         for (int b = 0; b < 4; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * 4096, n0 + 32 * b, k0);
       }
-      // ---- write-back of updated chunks and refill of the freed buffers ----
+      // the MMAs have consumed every operand stage once the accumulator is complete: the operand region now takes
+      // NX more chunks in flight
+      mbar_wait(tmem_full, 0);
+      for (int c = NB; c < NBUF && c < nch; ++c) load_chunk(c);
+      // ---- write-back of updated chunks; a buffer is refilled one chunk late so that the store which is reading it has
+      //      had a whole chunk period to drain (wait_group.read 1 instead of a full stall per chunk) ----
       for (int c = 0; c < nch; ++c) {
-        const int b = c % NB;
-        mbar_wait(&cdone[b], (uint32_t)(c / NB) & 1u);
-        const uint8_t* src = cbuf + (size_t)b * 3 * ARR_BYTES;
+        const int b = c % NBUF;
+        mbar_wait(&cdone[b], (uint32_t)(c / NBUF) & 1u);
+        const uint8_t* src = buf_ptr(b);
         tma_store_2d(&op.mapP, src, m0, n0 + c * KC);
         tma_store_2d(&op.mapM, src + ARR_BYTES, m0, n0 + c * KC);
         tma_store_2d(&op.mapV, src + 2 * ARR_BYTES, m0, n0 + c * KC);
         bulk_commit();
-        if (c + NB < nch) { bulk_wait_read0(); load_chunk(c + NB); }
+        if (c >= 1 && c - 1 + NBUF < nch) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          load_chunk(c - 1 + NBUF);
+        }
       }
       bulk_wait_read0();
     }
@@ -515,13 +528,13 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
     mbar_wait(tmem_full, 0);
     fence_after();
     for (int c = 0; c < nch; ++c) {
-      const int b = c % NB;
-      float* sP = reinterpret_cast<float*>(cbuf + (size_t)b * 3 * ARR_BYTES);
+      const int b = c % NBUF;
+      float* sP = reinterpret_cast<float*>(buf_ptr(b));
       float* sM = sP + KC * 128;
       float* sV = sM + KC * 128;
       float g[KC];
       tmem_ld8(trow + (uint32_t)(c * KC), g);
-      mbar_wait(&cfull[b], (uint32_t)(c / NB) & 1u);
+      mbar_wait(&cfull[b], (uint32_t)(c / NBUF) & 1u);
 #pragma unroll
       for (int j = 0; j < KC; ++j) {
         const int i = j * 128 + nl;
