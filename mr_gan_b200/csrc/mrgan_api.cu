@@ -777,6 +777,11 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 #define K_TC_FWD2 k_gemm_tc<true, false, TC_FWD_STAGES, 512, 1, 8, 2>     // 256 features per CTA (layers >= 500 wide)
 #define K_TC_DX2 k_gemm_tc<false, false, TC_FWD_STAGES, 512, 1, 8, 2>
 #define K_TC_DW k_gemm_tc<true, true, TC_DW_STAGES, 128, 2, 4, 1>
+// large-batch regime (more than 256 batch rows: data-parallel config 5): 256 x 256 tiles, 3-stage ring of 64 KB stages
+#define TC_BIG_STAGES 3
+#define K_TC_FWD_BIG k_gemm_tc<true, false, TC_BIG_STAGES, 512, 1, 8, 2>
+#define K_TC_DX_BIG k_gemm_tc<false, false, TC_BIG_STAGES, 512, 1, 8, 2>
+#define K_TC_DW_BIG k_gemm_tc<true, true, TC_BIG_STAGES, 512, 1, 8, 2>
 #define TCA_SMEM_BYTES (2 * 2 * 128 * 128 + TCA_NB * 3 * TCA_KC * 128 * 4 + 256)
 size_t tc_smem_bytes(int bn, int stages, int mt = 1) { return 1024 + (size_t)stages * ((size_t)mt * 128 * 128 + (size_t)bn * 128) + 256; }
 // two feature sub-tiles per CTA when the layer is wide enough and the 4-stage ring still fits in 227 KB
@@ -795,6 +800,9 @@ EncodeTiledFn tc_encoder() {
 void tc_set_smem_attr() {
   cudaFuncSetAttribute(K_TC_FWD, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
   cudaFuncSetAttribute(K_TC_DX, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
+  cudaFuncSetAttribute(K_TC_FWD_BIG, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(K_TC_DX_BIG, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(K_TC_DW_BIG, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(K_TC_FWD2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(K_TC_DX2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(K_TC_DW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(128, TC_DW_STAGES));
@@ -807,16 +815,16 @@ bool tc_fill_op(EncodeTiledFn fn, TcOp& t, const GemmDesc& g, int mode) {
   t.ME = g.N; t.NE = g.M; t.KE = g.K;
   if (mode == 0) {            // forward: C[M rows, N feats] = act[M, K] @ W[K, N]
     t.epi = EPI_FWD;
-    t.bn = g.M <= 256 ? round_up(g.M, 16) : 160;
+    t.bn = g.M <= 256 ? round_up(g.M, 16) : 256;
     return make_map(fn, &t.mapA, g.B, g.N, g.K, g.ldb, 32, true) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false);
   }
   if (mode == 1) {            // dX: C[M rows, N in-feats] = dZ[M, K] @ W[N, K]^T
     t.epi = EPI_DX;
-    t.bn = g.M <= 256 ? round_up(g.M, 16) : 160;
+    t.bn = g.M <= 256 ? round_up(g.M, 16) : 256;
     return make_map(fn, &t.mapA, g.B, g.K, g.N, g.ldb, 128, false) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false);
   }
   t.epi = EPI_STORE;          // dW: C[M in-feats(+1), N out-feats] = act[K rows, M]^T @ dZ[K rows, N]
-  t.bn = 128;
+  t.bn = g.K > 512 ? 256 : 128;   // a long contraction (large batch) is a regular big GEMM: 256 x 256 tiles
   return make_map(fn, &t.mapA, g.B, g.N, g.K, g.ldb, 32, true) && make_map(fn, &t.mapB, g.A, g.M, g.K, g.lda, 32, true);
 }
 
@@ -842,6 +850,7 @@ int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g) {
 int tc_setup(mrgan_handle* h) {
   EncodeTiledFn fn = tc_encoder();
   if (!fn) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  if (h->R > 512) h->tc_fused_adam = false;   // large batch: dW is tensor-bound -> big-tile GEMM + flat Adam instead of the fused kernel
   if (const char* pr = getenv("MRGAN_L2PROMO"))
     g_l2_promo = atoi(pr) == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (atoi(pr) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                  : (atoi(pr) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
@@ -924,6 +933,14 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
   if (rows_override > 0 && !oi.at) NE = rows_override;
   dim3 grid((h->tc_maxME[op] + 127) / 128, (NE + bn - 1) / bn, nfl);
   const TcOp* d = h->d_tcops + (size_t)op * h->nf + f0;
+  if (bn == 256 && (oi.at || h->tc_maxME[op] >= 500)) {     // large-batch regime
+    grid.x = (h->tc_maxME[op] + 255) / 256;
+    const size_t smem = tc_smem_bytes(256, TC_BIG_STAGES, 2);
+    if (oi.at) launch_k(h, K_TC_DW_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, 0, h->hp);
+    else if (!oi.bt) launch_k(h, K_TC_FWD_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp);
+    else launch_k(h, K_TC_DX_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp);
+    return true;
+  }
   if (!oi.at && h->tc_mt2 && tc_use_mt2(h->tc_maxME[op], bn)) {
     grid.x = (h->tc_maxME[op] + 255) / 256;
     const size_t smem = tc_smem_bytes(bn, TC_FWD_STAGES, 2);

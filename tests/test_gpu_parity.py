@@ -442,3 +442,29 @@ def test_extreme_widths_single_step_pair(precision, D):
     np.testing.assert_allclose(got[0][:2], want_d[:2], rtol=LOSS_RTOL[precision])
     assert abs(got[0][2] - want_d[2]) < 1e-6
     np.testing.assert_allclose(got[1], want_g, rtol=LOSS_RTOL[precision] if D >= 100 else GEN_RTOL_SMALL_BATCH[precision])
+
+
+@pytest.mark.parametrize("precision", PRECISIONS)
+def test_large_batch_step_pair_against_oracle(precision):
+    """Large-batch regime of BASELINE config 5 on one GPU (B=192 -> 576 stacked rows: 256x256-tile GEMMs, dW stored and
+    applied by the flat Adam kernel instead of the fused epilogue): one D and one G step from identical state."""
+    D, B = 300, 192
+    key = philox.fold_key(8, 0)
+    pD, pG, steps = make_golden.case_inputs(D, B, 77, 1)
+    s = steps[0]
+    want_d = O.GanOracle(pD, pG).disc_step(s['x_lab'], s['labels'], s['x_unl'], s['z_d'], fold_loop.d_noise(key, 0, B, D, 0),
+                                           fold_loop.d_noise(key, 0, B, D, B), fold_loop.d_noise(key, 0, B, D, 2 * B))
+    m = O.GanOracle(pD, pG)
+    want_g = m.gen_step(s['x_unl2'], s['z_g'], fold_loop.d_noise(key, 0, B, D, 0), fold_loop.d_noise(key, 0, B, D, B))
+    with FoldGroup([(D, 2 * B, 64, _key64(key))], precision=precision, batch=B) as fg:
+        fg.set_params(0, 0, pD)
+        fg.set_params(0, 1, pG)
+        got_d = fg.train_batch_disc(0, s['x_lab'], s['labels'], s['x_unl'], s['z_d'])
+    with FoldGroup([(D, 2 * B, 64, _key64(key))], precision=precision, batch=B) as fg:
+        fg.set_params(0, 0, pD)
+        fg.set_params(0, 1, pG)
+        got_g = fg.train_batch_gen(0, s['x_unl2'], s['z_g'])
+        _param_close(fg.get_params(0, 1), m.pG, pG, PARAM_TOL[precision])
+    np.testing.assert_allclose(got_d[:2], want_d[:2], rtol=LOSS_RTOL[precision])
+    assert abs(got_d[2] - want_d[2]) < 1e-6
+    np.testing.assert_allclose(got_g, want_g, rtol=LOSS_RTOL[precision])
