@@ -233,13 +233,15 @@ struct BnDesc {
 // mr_gan.py:112 BatchNormalization(epsilon=2e-5) in training phase: biased batch variance.
 // Block = 32 columns x 8 row slices (256 threads): the batch loop is split 8 ways and reduced through shared memory,
 // so the dependent-load chain per thread is B/8 rows instead of B.
+// The slice count is blockDim.x / 32: 8 at the reference batch, 32 in the large-batch regime.
 #define BN_COLS 32
-#define BN_SLICES 8
-__global__ void __launch_bounds__(256) k_bn_fwd(const BnDesc* __restrict__ descs, float eps, int tf32) {
+#define BN_MAX_SLICES 32
+__global__ void __launch_bounds__(1024) k_bn_fwd(const BnDesc* __restrict__ descs, float eps, int tf32) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float red[2][BN_SLICES][BN_COLS];
+  __shared__ float red[2][BN_MAX_SLICES][BN_COLS];
   const BnDesc d = descs[blockIdx.z];
+  const int BN_SLICES = blockDim.x / BN_COLS;
   const int cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
   const int j = blockIdx.x * BN_COLS + cx;
   const bool ok = j < d.W;
@@ -248,7 +250,6 @@ __global__ void __launch_bounds__(256) k_bn_fwd(const BnDesc* __restrict__ descs
   red[0][sl][cx] = s;
   __syncthreads();
   float mu = 0.f;
-#pragma unroll
   for (int i = 0; i < BN_SLICES; ++i) mu += red[0][i][cx];
   mu /= d.B;
   float q = 0.f;
@@ -256,7 +257,6 @@ __global__ void __launch_bounds__(256) k_bn_fwd(const BnDesc* __restrict__ descs
   red[1][sl][cx] = q;
   __syncthreads();
   float var = 0.f;
-#pragma unroll
   for (int i = 0; i < BN_SLICES; ++i) var += red[1][i][cx];
   if (!ok) return;
   const float istd = rsqrtf(var / d.B + eps);
@@ -271,11 +271,12 @@ __global__ void __launch_bounds__(256) k_bn_fwd(const BnDesc* __restrict__ descs
 }
 
 // BN backward + softplus' of the layer in front of it (G layer 1): du -> dgamma, dbeta, dz1.
-__global__ void __launch_bounds__(256) k_bn_bwd(const BnDesc* __restrict__ descs, int tf32) {
+__global__ void __launch_bounds__(1024) k_bn_bwd(const BnDesc* __restrict__ descs, int tf32) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float red[2][BN_SLICES][BN_COLS];
+  __shared__ float red[2][BN_MAX_SLICES][BN_COLS];
   const BnDesc d = descs[blockIdx.z];
+  const int BN_SLICES = blockDim.x / BN_COLS;
   const int cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
   const int j = blockIdx.x * BN_COLS + cx;
   const bool ok = j < d.W;
@@ -288,7 +289,6 @@ __global__ void __launch_bounds__(256) k_bn_bwd(const BnDesc* __restrict__ descs
   red[0][sl][cx] = p1; red[1][sl][cx] = p2;
   __syncthreads();
   float s1 = 0.f, s2 = 0.f;
-#pragma unroll
   for (int i = 0; i < BN_SLICES; ++i) { s1 += red[0][i][cx]; s2 += red[1][i][cx]; }
   if (!ok) return;
   if (sl == 0) { d.g_gamma[j] = s2; d.g_beta[j] = s1; }
@@ -432,26 +432,34 @@ k_loss_mse(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, i
 // and applied by a second kernel, so that W ranks compute exactly the single-GPU large-batch step.
 struct DpBufs { float* bnf; float* bnb; float* fm; };   // per fold: [2*W] sums each (W = 500 / 500 / 250)
 
-__global__ void __launch_bounds__(128) k_bn_stats(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs) {
+__global__ void __launch_bounds__(1024) k_bn_stats(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs) {
+  __shared__ float red[2][BN_MAX_SLICES][BN_COLS];
   const BnDesc d = descs[blockIdx.z];
-  const int j = blockIdx.x * 128 + threadIdx.x;
-  if (j >= d.W) return;
+  const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
+  const int j = blockIdx.x * BN_COLS + cx;
   float s = 0.f, q = 0.f;
-  for (int r = 0; r < d.B; ++r) { const float x = d.h1[(size_t)r * d.ld + j]; s += x; q = fmaf(x, x, q); }
-  bufs[blockIdx.z].bnf[j] = s; bufs[blockIdx.z].bnf[d.W + j] = q;
+  if (j < d.W) for (int r = sl; r < d.B; r += nsl) { const float x = d.h1[(size_t)r * d.ld + j]; s += x; q = fmaf(x, x, q); }
+  red[0][sl][cx] = s; red[1][sl][cx] = q;
+  __syncthreads();
+  if (sl == 0 && j < d.W) {
+    s = 0.f; q = 0.f;
+    for (int i = 0; i < nsl; ++i) { s += red[0][i][cx]; q += red[1][i][cx]; }
+    bufs[blockIdx.z].bnf[j] = s; bufs[blockIdx.z].bnf[d.W + j] = q;
+  }
 }
 
-__global__ void __launch_bounds__(128) k_bn_apply(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs,
-                                                  float eps, int tf32, int Bg) {
+__global__ void __launch_bounds__(1024) k_bn_apply(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs,
+                                                   float eps, int tf32, int Bg) {
   const BnDesc d = descs[blockIdx.z];
-  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
+  const int j = blockIdx.x * BN_COLS + cx;
   if (j >= d.W) return;
   const float mu = bufs[blockIdx.z].bnf[j] / Bg;
   const float var = fmaxf(bufs[blockIdx.z].bnf[d.W + j] / Bg - mu * mu, 0.f);
   const float istd = rsqrtf(var + eps);
-  d.istd[j] = istd;
+  if (sl == 0) d.istd[j] = istd;
   const float g = d.gamma[j], b = d.beta[j];
-  for (int r = 0; r < d.B; ++r) {
+  for (int r = sl; r < d.B; r += nsl) {
     const float xh = (d.h1[(size_t)r * d.ld + j] - mu) * istd;
     d.xhat[(size_t)r * d.ld + j] = xh;
     const float u = fmaf(g, xh, b);
@@ -459,24 +467,32 @@ __global__ void __launch_bounds__(128) k_bn_apply(const BnDesc* __restrict__ des
   }
 }
 
-__global__ void __launch_bounds__(128) k_bn_bwd_stats(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs) {
+__global__ void __launch_bounds__(1024) k_bn_bwd_stats(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs) {
+  __shared__ float red[2][BN_MAX_SLICES][BN_COLS];
   const BnDesc d = descs[blockIdx.z];
-  const int j = blockIdx.x * 128 + threadIdx.x;
-  if (j >= d.W) return;
+  const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
+  const int j = blockIdx.x * BN_COLS + cx;
   float s1 = 0.f, s2 = 0.f;
-  for (int r = 0; r < d.B; ++r) { const float du = d.du[(size_t)r * d.ld + j]; s1 += du; s2 = fmaf(du, d.xhat[(size_t)r * d.ld + j], s2); }
-  d.g_gamma[j] = s2; d.g_beta[j] = s1;        // LOCAL partial gradients: the flat gradient all-reduce completes them
-  bufs[blockIdx.z].bnb[j] = s1; bufs[blockIdx.z].bnb[d.W + j] = s2;
+  if (j < d.W) for (int r = sl; r < d.B; r += nsl) { const float du = d.du[(size_t)r * d.ld + j]; s1 += du; s2 = fmaf(du, d.xhat[(size_t)r * d.ld + j], s2); }
+  red[0][sl][cx] = s1; red[1][sl][cx] = s2;
+  __syncthreads();
+  if (sl == 0 && j < d.W) {
+    s1 = 0.f; s2 = 0.f;
+    for (int i = 0; i < nsl; ++i) { s1 += red[0][i][cx]; s2 += red[1][i][cx]; }
+    d.g_gamma[j] = s2; d.g_beta[j] = s1;        // LOCAL partial gradients: the flat gradient all-reduce completes them
+    bufs[blockIdx.z].bnb[j] = s1; bufs[blockIdx.z].bnb[d.W + j] = s2;
+  }
 }
 
-__global__ void __launch_bounds__(128) k_bn_bwd_apply(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs,
-                                                      int tf32, int Bg) {
+__global__ void __launch_bounds__(1024) k_bn_bwd_apply(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs,
+                                                       int tf32, int Bg) {
   const BnDesc d = descs[blockIdx.z];
-  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
+  const int j = blockIdx.x * BN_COLS + cx;
   if (j >= d.W) return;
   const float s1 = bufs[blockIdx.z].bnb[j], s2 = bufs[blockIdx.z].bnb[d.W + j];
   const float g = d.gamma[j], istd = d.istd[j], invB = 1.0f / Bg;
-  for (int r = 0; r < d.B; ++r) {
+  for (int r = sl; r < d.B; r += nsl) {
     const float xh = d.xhat[(size_t)r * d.ld + j];
     const float dxh = d.du[(size_t)r * d.ld + j] * g;
     const float dh1 = istd * (dxh - invB * g * s1 - xh * invB * g * s2);
@@ -485,32 +501,46 @@ __global__ void __launch_bounds__(128) k_bn_bwd_apply(const BnDesc* __restrict__
   }
 }
 
-__global__ void __launch_bounds__(256) k_fm_stats(const LossDesc* __restrict__ descs, const DpBufs* __restrict__ bufs, int B) {
+// grid.x = column blocks of 32; block = 32 columns x (blockDim.x / 32) row slices
+__global__ void __launch_bounds__(1024) k_fm_stats(const LossDesc* __restrict__ descs, const DpBufs* __restrict__ bufs, int B) {
+  __shared__ float red[2][BN_MAX_SLICES][BN_COLS];
   const LossDesc d = descs[blockIdx.z];
-  for (int j = threadIdx.x; j < d.Wmid; j += blockDim.x) {
-    float mg = 0.f, mr = 0.f;
-    for (int r = 0; r < B; ++r) { mg += d.mid[(size_t)r * d.ldmid + j]; mr += d.mid[(size_t)(r + B) * d.ldmid + j]; }
+  const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
+  const int j = blockIdx.x * BN_COLS + cx;
+  float mg = 0.f, mr = 0.f;
+  if (j < d.Wmid) for (int r = sl; r < B; r += nsl) { mg += d.mid[(size_t)r * d.ldmid + j]; mr += d.mid[(size_t)(r + B) * d.ldmid + j]; }
+  red[0][sl][cx] = mg; red[1][sl][cx] = mr;
+  __syncthreads();
+  if (sl == 0 && j < d.Wmid) {
+    mg = 0.f; mr = 0.f;
+    for (int i = 0; i < nsl; ++i) { mg += red[0][i][cx]; mr += red[1][i][cx]; }
     bufs[blockIdx.z].fm[j] = mg; bufs[blockIdx.z].fm[d.Wmid + j] = mr;
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_fm_apply(const LossDesc* __restrict__ descs, const DpBufs* __restrict__ bufs, float* __restrict__ step_stats, int fold_base,
            int nf_total, int t, int B, int tf32, int Bg, int world) {
   __shared__ float sh[32];
   const LossDesc d = descs[blockIdx.z];
-  float s = 0.f;
-  for (int j = threadIdx.x; j < d.Wmid; j += blockDim.x) {
+  const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
+  const int j = blockIdx.x * BN_COLS + cx;
+  if (j < d.Wmid) {
     const float diff = (bufs[blockIdx.z].fm[j] - bufs[blockIdx.z].fm[d.Wmid + j]) / Bg;
-    s = fmaf(diff, diff, s);
     float g = 2.0f * diff / ((float)d.Wmid * Bg);
     if (tf32) g = rna_tf32(g);
-    for (int r = 0; r < B; ++r)
+    for (int r = sl; r < B; r += nsl)
       d.dmid[(size_t)r * d.lddmid + j] = (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : 0.f;
   }
-  s = block_sum(s, sh);
-  // every rank holds the same global loss; the statistics block is summed over ranks afterwards -> store 1/world of it
-  if (threadIdx.x == 0) step_stats[((size_t)t * nf_total + fold_base + blockIdx.z) * 4 + 3] = s / d.Wmid / world;
+  if (blockIdx.x == 0) {      // the loss itself: every rank holds the same global value; the statistics block is summed over ranks
+    float s = 0.f;            // afterwards, so 1/world of it is stored
+    for (int c = threadIdx.x; c < d.Wmid; c += blockDim.x) {
+      const float diff = (bufs[blockIdx.z].fm[c] - bufs[blockIdx.z].fm[d.Wmid + c]) / Bg;
+      s = fmaf(diff, diff, s);
+    }
+    s = block_sum(s, sh);
+    if (threadIdx.x == 0) step_stats[((size_t)t * nf_total + fold_base + blockIdx.z) * 4 + 3] = s / d.Wmid / world;
+  }
 }
 
 // ------------------------------------------------------------------ evaluation

@@ -452,6 +452,22 @@ void dp_allreduce_grads(mrgan_handle* h, int net) {
   dp_allreduce(h, h->Gr + h->net[net][0].off, (size_t)n);      // the nets of all folds are contiguous in the flat buffer
 }
 
+// Scratch of the split (statistics -> [all-reduce] -> apply) BatchNorm / feature-matching kernels: used by the data-parallel
+// mode and, on one GPU, by the large-batch regime where one CTA per fold would serialise thousands of rows.
+int alloc_split_bufs(mrgan_handle* h) {
+  if (h->d_dpbufs) return MRGAN_OK;
+  const int nf = h->nf;
+  const size_t per = 2 * kGH + 2 * kGH + 2 * kDW[4];
+  CK(cudaMalloc(&h->d_dpmem, per * nf * sizeof(float)));
+  CK(cudaMemset(h->d_dpmem, 0, per * nf * sizeof(float)));
+  h->dp_bnf = h->d_dpmem; h->dp_bnb = h->dp_bnf + (size_t)nf * 2 * kGH; h->dp_fm = h->dp_bnb + (size_t)nf * 2 * kGH;
+  std::vector<DpBufs> bufs(nf);
+  for (int f = 0; f < nf; ++f) bufs[f] = DpBufs{h->dp_bnf + (size_t)f * 2 * kGH, h->dp_bnb + (size_t)f * 2 * kGH, h->dp_fm + (size_t)f * 2 * kDW[4]};
+  CK(cudaMalloc(&h->d_dpbufs, nf * sizeof(DpBufs)));
+  CK(cudaMemcpy(h->d_dpbufs, bufs.data(), nf * sizeof(DpBufs), cudaMemcpyHostToDevice));
+  return MRGAN_OK;
+}
+
 // ------------------------------------------------------------------ launch sequences
 void launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override, cudaStream_t st = nullptr) {
   if (!st) st = h->stream;
@@ -521,15 +537,16 @@ bool deferred_join(const mrgan_handle*) { return false; }
 void enqueue_gen_fwd(mrgan_handle* h, int f0, int nfl, int op_g3) {
   if (deferred_join(h)) join_side(h);          // generator weights of the previous G step (GW1..3 on the side stream)
   launch_gemm(h, OP_G1, f0, nfl, 0);
-  const dim3 bng((kGH + 127) / 128, 1, nfl), bnf((kGH + BN_COLS - 1) / BN_COLS, 1, nfl);
+  const dim3 bnf((kGH + BN_COLS - 1) / BN_COLS, 1, nfl);
+  const dim3 bnt(h->cfg.batch > 256 ? 1024 : 256);     // 32 columns x 8 (reference batch) or 32 (large batch) row slices
   const int tf32 = h->cfg.precision == MRGAN_PREC_TF32;
-  if (h->dp_world > 1) {      // batch statistics over the GLOBAL batch: local sums -> NVLink all-reduce -> apply
-    k_bn_stats<<<bng, 128, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0);
+  if (h->d_dpbufs) {          // batch statistics over the GLOBAL batch: local sums -> NVLink all-reduce -> apply
+    k_bn_stats<<<bnf, bnt, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0);
     dp_allreduce(h, h->dp_bnf + (size_t)f0 * 2 * kGH, (size_t)nfl * 2 * kGH);
-    k_bn_apply<<<bng, 128, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, h->cfg.bn_eps, tf32, h->hp.dp_bg);
+    k_bn_apply<<<bnf, bnt, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, h->cfg.bn_eps, tf32, h->hp.dp_bg);
     h->launches += 2;
   } else {
-    launch_k(h, k_bn_fwd, bnf, dim3(256), 0, h->stream, (const BnDesc*)(h->d_bn + f0), h->cfg.bn_eps, tf32);
+    launch_k(h, k_bn_fwd, bnf, bnt, 0, h->stream, (const BnDesc*)(h->d_bn + f0), h->cfg.bn_eps, tf32);
   }
   launch_gemm(h, OP_G2, f0, nfl, 0);
   launch_gemm(h, op_g3, f0, nfl, 0);
@@ -563,11 +580,12 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   enqueue_gen_fwd(h, f0, nfl, OP_G3G);
   if (deferred_join(h)) join_side(h);          // discriminator weights updated by the D step's dW+Adam kernels
   for (int l = 0; l < 5; ++l) launch_gemm(h, OP_D1G + l, f0, nfl, 0);
-  if (h->dp_world > 1) {
-    k_fm_stats<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, B);
+  if (h->d_dpbufs) {
+    const dim3 fmg((kDW[4] + BN_COLS - 1) / BN_COLS, 1, nfl), fmt(B > 256 ? 1024 : 256);
+    k_fm_stats<<<fmg, fmt, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, B);
     dp_allreduce(h, h->dp_fm + (size_t)f0 * 2 * kDW[4], (size_t)nfl * 2 * kDW[4]);
-    k_fm_apply<<<dim3(1, 1, nfl), 256, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, h->d_step_stats, f0, h->nf, t, B,
-                                                       c.precision == MRGAN_PREC_TF32, h->hp.dp_bg, h->dp_world);
+    k_fm_apply<<<fmg, fmt, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, h->d_step_stats, f0, h->nf, t, B,
+                                           c.precision == MRGAN_PREC_TF32, h->hp.dp_bg, h->dp_world);
     h->launches += 2;
   } else {
     launch_k(h, k_fm, dim3(1, 1, nfl), dim3(1024), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, B,
@@ -581,14 +599,14 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   launch_gemm(h, OP_GX2, f0, nfl, 0);
   fork_side(h);
   launch_gemm(h, OP_GW2, f0, nfl, 0, h->side);
-  if (h->dp_world > 1) {
-    k_bn_bwd_stats<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0);
+  const dim3 bng((kGH + BN_COLS - 1) / BN_COLS, 1, nfl), bnt(B > 256 ? 1024 : 256);
+  if (h->d_dpbufs) {
+    k_bn_bwd_stats<<<bng, bnt, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0);
     dp_allreduce(h, h->dp_bnb + (size_t)f0 * 2 * kGH, (size_t)nfl * 2 * kGH);
-    k_bn_bwd_apply<<<dim3((kGH + 127) / 128, 1, nfl), 128, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, c.precision == MRGAN_PREC_TF32, h->hp.dp_bg);
+    k_bn_bwd_apply<<<bng, bnt, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, c.precision == MRGAN_PREC_TF32, h->hp.dp_bg);
     h->launches += 2;
   } else {
-    launch_k(h, k_bn_bwd, dim3((kGH + BN_COLS - 1) / BN_COLS, 1, nfl), dim3(256), 0, h->stream, (const BnDesc*)(h->d_bn + f0),
-             (int)(c.precision == MRGAN_PREC_TF32));
+    launch_k(h, k_bn_bwd, bng, bnt, 0, h->stream, (const BnDesc*)(h->d_bn + f0), (int)(c.precision == MRGAN_PREC_TF32));
   }
   fork_side(h);
   launch_gemm(h, OP_GW1, f0, nfl, 0, h->side);
@@ -1073,6 +1091,10 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   if (!ok) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, "stream/event/pinned allocation failed"));
   build_descs(h);
   init_ones(h);
+  if (cfg->model == MRGAN_MODEL_GAN && cfg->batch > 256) {   // large batch: row-parallel split BatchNorm / feature-matching kernels
+    int rc = alloc_split_bufs(h);
+    if (rc != MRGAN_OK) return cleanup(rc);
+  }
 #ifdef MRGAN_WITH_TC
   if (cfg->precision == MRGAN_PREC_TF32) {
     int rc = tc_setup(h);
@@ -1571,15 +1593,7 @@ int mrgan_dp_init(mrgan_handle* h, int rank, int world, const void* id128) {
   NcclId id; memcpy(id.b, id128, 128);
   const int nrc = g_nccl.CommInitRank(&h->nccl_comm, world, id, rank);
   if (nrc != 0) return fail(h, MRGAN_ERR_CUDA, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(nrc) : "error"));
-  const int nf = h->nf;
-  const size_t per = 2 * kGH + 2 * kGH + 2 * kDW[4];
-  CK(cudaMalloc(&h->d_dpmem, per * nf * sizeof(float)));
-  CK(cudaMemset(h->d_dpmem, 0, per * nf * sizeof(float)));
-  h->dp_bnf = h->d_dpmem; h->dp_bnb = h->dp_bnf + (size_t)nf * 2 * kGH; h->dp_fm = h->dp_bnb + (size_t)nf * 2 * kGH;
-  std::vector<DpBufs> bufs(nf);
-  for (int f = 0; f < nf; ++f) bufs[f] = DpBufs{h->dp_bnf + (size_t)f * 2 * kGH, h->dp_bnb + (size_t)f * 2 * kGH, h->dp_fm + (size_t)f * 2 * kDW[4]};
-  CK(cudaMalloc(&h->d_dpbufs, nf * sizeof(DpBufs)));
-  CK(cudaMemcpy(h->d_dpbufs, bufs.data(), nf * sizeof(DpBufs), cudaMemcpyHostToDevice));
+  rc = alloc_split_bufs(h); if (rc) return rc;
   h->dp_world = world; h->dp_rank = rank;
   h->hp.dp_bloc = h->cfg.batch; h->hp.dp_bg = h->cfg.batch * world; h->hp.dp_rank = rank;
 #ifdef MRGAN_WITH_TC

@@ -444,11 +444,13 @@ def test_extreme_widths_single_step_pair(precision, D):
     np.testing.assert_allclose(got[1], want_g, rtol=LOSS_RTOL[precision] if D >= 100 else GEN_RTOL_SMALL_BATCH[precision])
 
 
+@pytest.mark.parametrize("B", [192, 320])
 @pytest.mark.parametrize("precision", PRECISIONS)
-def test_large_batch_step_pair_against_oracle(precision):
+def test_large_batch_step_pair_against_oracle(precision, B):
     """Large-batch regime of BASELINE config 5 on one GPU (B=192 -> 576 stacked rows: 256x256-tile GEMMs, dW stored and
-    applied by the flat Adam kernel instead of the fused epilogue): one D and one G step from identical state."""
-    D, B = 300, 192
+    applied by the flat Adam kernel instead of the fused epilogue; B=320 additionally takes the row-parallel split
+    BatchNorm / feature-matching kernels): one D and one G step from identical state."""
+    D = 300
     key = philox.fold_key(8, 0)
     pD, pG, steps = make_golden.case_inputs(D, B, 77, 1)
     s = steps[0]
@@ -466,5 +468,5 @@ def test_large_batch_step_pair_against_oracle(precision):
         got_g = fg.train_batch_gen(0, s['x_unl2'], s['z_g'])
         _param_close(fg.get_params(0, 1), m.pG, pG, PARAM_TOL[precision])
     np.testing.assert_allclose(got_d[:2], want_d[:2], rtol=LOSS_RTOL[precision])
-    assert abs(got_d[2] - want_d[2]) < 1e-6
+    assert abs(got_d[2] - want_d[2]) <= FLIPS[precision] / B + 1e-6     # near-tie argmax among 320 random-init rows may flip in tf32
     np.testing.assert_allclose(got_g, want_g, rtol=LOSS_RTOL[precision])
