@@ -81,8 +81,10 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
+    path = os.environ.get("MRGAN_LIB") or _build.LIB      # MRGAN_LIB: a prebuilt library (kernel A/B experiments)
     if not os.path.exists(path):
+        if os.environ.get("MRGAN_LIB"):
+            raise RuntimeError("MRGAN_LIB=%s does not exist" % path)
         path = _build.build()
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():

@@ -187,23 +187,35 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
   }
 
   const bool aligned = (hp.dp_bloc & 3) == 0 || hp.dp_bg == hp.dp_bloc;   // 4-row noise groups stay inside one section
-  if (c < D) {
-    float nz[4];
-    if (aligned) normal4(fs.key0, fs.key1, (uint32_t)global_row(rg * 4, hp) >> 2, (uint32_t)c, step, 0u, nz);
-    else for (int i = 0; i < 4; ++i) nz[i] = normal1(fs.key0, fs.key1, (uint32_t)global_row(rg * 4 + i, hp), (uint32_t)c, step, 0u);
+  // rows of this group that this step assembles from the data set: mode 0 -> [0, 2B), mode 1 -> [B, 2B), mode 2 -> [0, nrows)
+  const int r_lo = (mode == 1) ? B : 0, r_hi = (mode == 2) ? nrows : min(nrows, 2 * B);
+  if (c < D && rg * 4 + 3 >= r_lo && rg * 4 < r_hi) {
+    // descriptor fields in registers: through the FoldState reference every use is a generic load that the stores to a0
+    // force the compiler to repeat; the 4 gathers are issued before the Philox rounds so their latency overlaps the ALU work
+    const float* const x_train = fs.x_train; const float* const stage_x = fs.stage_x;
+    float* const a0 = fs.a0;
+    const int ldx = fs.ldx, lda0 = fs.lda0;
+    const uint32_t key0 = fs.key0, key1 = fs.key1;
+    float xv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = rg * 4 + i;
-      if (r >= nrows) break;
-      int stream;
-      if (mode == 0) { if (r >= 2 * B) break; stream = (r < B) ? 0 : 1; }
-      else if (mode == 1) { if (r < B) continue; if (r >= 2 * B) break; stream = 2; }
-      else stream = 0;
+      xv[i] = 0.f;
+      if (r < r_lo || r >= r_hi) continue;
+      const int stream = (mode == 1) ? 2 : ((mode == 0 && r >= B) ? 1 : 0);
       const int lr = (mode == 2) ? r : (r < B ? r : r - B);
-      const float* src = from_stage ? fs.stage_x + (size_t)r * fs.ldx
-                                    : fs.x_train + (size_t)fs.idx[stream][(size_t)t * B + lr] * fs.ldx;
-      const float v = src[c] + sigma_in * nz[i];
-      fs.a0[(size_t)r * fs.lda0 + c] = tf32 ? rna_tf32(v) : v;
+      const float* src = from_stage ? stage_x + (size_t)r * ldx : x_train + (size_t)__ldg(fs.idx[stream] + (size_t)t * B + lr) * ldx;
+      xv[i] = __ldg(src + c);
+    }
+    float nz[4];
+    if (aligned) normal4(key0, key1, (uint32_t)global_row(rg * 4, hp) >> 2, (uint32_t)c, step, 0u, nz);
+    else for (int i = 0; i < 4; ++i) nz[i] = normal1(key0, key1, (uint32_t)global_row(rg * 4 + i, hp), (uint32_t)c, step, 0u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = rg * 4 + i;
+      if (r < r_lo || r >= r_hi) continue;
+      const float v = xv[i] + sigma_in * nz[i];
+      a0[(size_t)r * lda0 + c] = tf32 ? rna_tf32(v) : v;
     }
   }
   if (mode != 2 && c < noise_dim) {       // generator input z (mr_gan.py:206,212)

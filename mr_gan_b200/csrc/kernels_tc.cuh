@@ -31,7 +31,8 @@ struct alignas(64) TcOp {
   int bn;                     // MMA-N per tile (multiple of 16, <= 256; multiple of 32 when B is MN-major)
   int epi;                    // EPI_FWD / EPI_DX / EPI_STORE / EPI_ADAM
   int net;                    // 0 = discriminator, 1 = generator (which lr_t the fused Adam uses)
-  int pad_[2];
+  int ws_stride;              // split-K (large-batch dW): floats between the partial products of two contraction slices
+  float* ws;                  // ... and their workspace, laid out like C; k_splitk_reduce sums the slices in a fixed order
 };
 
 #define TC_KBLK 32            // contraction elements per stage (one 128-byte swizzle row of fp32)
@@ -131,7 +132,12 @@ __global__ void __launch_bounds__(64 + 32 * EPW, MINB)
 k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_override, AdamHyper hp) {
   using namespace tc;
   pdl_launch_dependents();
-  const TcOp& op = ops[blockIdx.z];      // descriptor tables are written once at handle creation: safe before pdl_wait()
+  // dW (B_MN) kernels take the number of contraction slices in `rows_override`: blockIdx.z = fold * ksplit + slice, each
+  // slice stores its partial product to op.ws (deterministic split-K: a fold's dW of the narrow layers is one or two
+  // tiles, which would leave a large-batch contraction of thousands of rows on one or two SMs)
+  const int ksplit = (B_MN && rows_override > 1) ? rows_override : 1;
+  const int kslice = (int)blockIdx.z % ksplit;
+  const TcOp& op = ops[blockIdx.z / ksplit];      // descriptor tables are written once at handle creation: safe before pdl_wait()
   const int ME = op.ME, KE = op.KE, bn = op.bn;
   int NE = op.NE;
   if (rows_override > 0 && !B_MN) NE = rows_override;      // fewer batch rows (G step)
@@ -148,7 +154,10 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (KE + TC_KBLK - 1) / TC_KBLK;
+  const int nkb_all = (KE + TC_KBLK - 1) / TC_KBLK;
+  const int kb_per = (nkb_all + ksplit - 1) / ksplit;
+  const int kb0 = kslice * kb_per;                           // the host picks ksplit so that no slice is empty
+  const int nkb = min(nkb_all, kb0 + kb_per) - kb0;
 
   if (warp == 0 && lane == 0) {
     prefetch_map(&op.mapA);
@@ -177,7 +186,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         mbar_expect_tx(&full[s], stage_bytes);
         uint8_t* sa = smem + (size_t)s * stage_bytes;
         uint8_t* sb = sa + a_bytes;
-        const int k0 = kb * TC_KBLK;
+        const int k0 = (kb0 + kb) * TC_KBLK;
         if (A_MN) {
 #pragma unroll
           for (int b = 0; b < 4 * MT; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * 4096, m0 + 32 * b, k0);
@@ -350,11 +359,12 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
             }
           }
         } else {   // EPI_STORE: dW into the flat gradient buffer (data-parallel mode: all-reduced before Adam)
+          float* const dst = ksplit > 1 ? op.ws + (size_t)kslice * op.ws_stride : g.C;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int k = n0 + c0 + j;
             if (k >= NE) break;
-            g.C[(size_t)k * g.ldc + f] = v[j];
+            dst[(size_t)k * g.ldc + f] = v[j];
           }
         }
       }
@@ -366,6 +376,22 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   if (warp == 1) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// Sums the `ks` contraction slices of a split-K dW in slice order (bitwise reproducible) into the gradient tensor.
+__global__ void __launch_bounds__(256) k_splitk_reduce(const TcOp* __restrict__ ops, int ks) {
+  const TcOp& op = ops[blockIdx.y];
+  const size_t n4 = (size_t)op.NE * op.g.ldc / 4, stride4 = (size_t)op.ws_stride / 4;
+  const float4* __restrict__ ws = reinterpret_cast<const float4*>(op.ws);
+  float4* __restrict__ out = reinterpret_cast<float4*>(op.g.C);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 a = ws[i];
+    for (int s = 1; s < ks; ++s) {
+      const float4 b = ws[(size_t)s * stride4 + i];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    out[i] = a;
   }
 }
 

@@ -77,6 +77,7 @@ int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g);
 }
 #endif
 
+constexpr int kMaxChains = 16;
 struct mrgan_handle {
   mrgan_config cfg;
   int nf = 0, R = 0, NE = 0, n_train = 0;
@@ -92,7 +93,7 @@ struct mrgan_handle {
   // the folds of a group are independent, so an epoch is captured as `nchains` parallel chains of kernels (disjoint fold
   // ranges, own main + side stream): one chain's latency-bound small kernels fill the SMs another chain leaves idle
   int nchains = 1;
-  cudaStream_t cmain[4] = {nullptr}, cside[4] = {nullptr};
+  cudaStream_t cmain[kMaxChains] = {nullptr}, cside[kMaxChains] = {nullptr};
   char* arena = nullptr; size_t arena_bytes = 0;
   float *P = nullptr, *Mo = nullptr, *Vo = nullptr, *Gr = nullptr; long long n_flat = 0;
   FoldState* d_folds = nullptr; std::vector<FoldState> h_folds;
@@ -121,6 +122,8 @@ struct mrgan_handle {
 #ifdef MRGAN_WITH_TC
   TcOp* d_tcops = nullptr;            // [NUM_OPS][nf] tensor maps + epilogue descriptors
   int tc_bn[NUM_OPS] = {0}, tc_maxME[NUM_OPS] = {0}, tc_maxNE[NUM_OPS] = {0};
+  int tc_ksplit[NUM_OPS] = {0};       // large-batch dW: contraction slices per tile (deterministic split-K), 0/1 = off
+  float* d_tcws = nullptr;            // ... and their partial-product workspace
   bool tc_fused_adam = true;          // dW epilogue applies Adam in place (no gradient round trip)
   bool tc_mt2 = true;                 // forward / dX: 256 features per CTA where the layer is wide enough (MRGAN_MT2=0 disables)
   bool tc_adam_tma = true;            // ... with W/m/v staged through smem by TMA (k_dw_adam_tc) instead of the LSU
@@ -894,6 +897,38 @@ int tc_setup(mrgan_handle* h) {
       if (t.NE > h->tc_maxNE[op]) h->tc_maxNE[op] = t.NE;
     }
   }
+  // Large-batch dW without the fused Adam: the narrow layers' gradients are a handful of 256x256 tiles with a contraction of
+  // thousands of rows -> split the contraction over ~2 CTAs per SM, partial products to a workspace, summed in slice order.
+  if (!h->tc_fused_adam) {
+    size_t ws_floats = 0;
+    for (int op = 0; op < NUM_OPS; ++op) {
+      const OpInfo& oi = h->ops[op];
+      if (!oi.used || !oi.at || h->tc_bn[op] != 256) continue;
+      const int nkb = (ops[(size_t)op * nf].KE + TC_KBLK - 1) / TC_KBLK;
+      const int tiles = ((h->tc_maxME[op] + 255) / 256) * ((h->tc_maxNE[op] + 255) / 256) * nf;
+      int ks = std::min(std::min(2 * 148 / tiles, nkb / 8), 32);
+      if (ks < 2) continue;
+      const int per = (nkb + ks - 1) / ks;
+      ks = (nkb + per - 1) / per;                       // no empty slice
+      h->tc_ksplit[op] = ks;
+      for (int f = 0; f < nf; ++f) {
+        TcOp& t = ops[(size_t)op * nf + f];
+        t.ws_stride = t.NE * t.g.ldc;
+        t.ws = reinterpret_cast<float*>(ws_floats);     // offset now, pointer once the workspace exists
+        ws_floats += (size_t)ks * t.ws_stride;
+      }
+    }
+    if (ws_floats) {
+      if (cudaMalloc(&h->d_tcws, ws_floats * sizeof(float)) != cudaSuccess) return fail(nullptr, MRGAN_ERR_CUDA, "cudaMalloc split-K workspace");
+      cudaMemset(h->d_tcws, 0, ws_floats * sizeof(float));      // pad columns are never written and must read as zero
+      for (int op = 0; op < NUM_OPS; ++op)
+        if (h->tc_ksplit[op] > 1)
+          for (int f = 0; f < nf; ++f) {
+            TcOp& t = ops[(size_t)op * nf + f];
+            t.ws = h->d_tcws + reinterpret_cast<size_t>(t.ws);
+          }
+    }
+  }
   if (cudaMalloc(&h->d_tcops, ops.size() * sizeof(TcOp)) != cudaSuccess) return fail(nullptr, MRGAN_ERR_CUDA, "cudaMalloc tc ops");
   cudaMemcpy(h->d_tcops, ops.data(), ops.size() * sizeof(TcOp), cudaMemcpyHostToDevice);
   if (h->tc_fused_adam && h->tc_adam_tma) {
@@ -936,6 +971,9 @@ int tc_setup(mrgan_handle* h) {
 void tc_teardown(mrgan_handle* h) {
   if (h->d_tcops) cudaFree(h->d_tcops);
   if (h->d_tcadam) cudaFree(h->d_tcadam);
+  if (h->d_tcws) cudaFree(h->d_tcws);
+  h->d_tcws = nullptr;
+  for (int i = 0; i < NUM_OPS; ++i) h->tc_ksplit[i] = 0;
   for (int n = 0; n < 2; ++n) { if (h->d_ranges_tc[n]) cudaFree(h->d_ranges_tc[n]); h->d_ranges_tc[n] = nullptr; }
   for (int i = 0; i < NUM_OPS; ++i) { h->tc_bn[i] = 0; h->tc_maxME[i] = 0; h->tc_maxNE[i] = 0; }
   h->d_tcadam = nullptr;
@@ -954,8 +992,15 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
   if (bn == 256 && (oi.at || h->tc_maxME[op] >= 500)) {     // large-batch regime
     grid.x = (h->tc_maxME[op] + 255) / 256;
     const size_t smem = tc_smem_bytes(256, TC_BIG_STAGES, 2);
-    if (oi.at) launch_k(h, K_TC_DW_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, 0, h->hp);
-    else if (!oi.bt) launch_k(h, K_TC_FWD_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp);
+    if (oi.at) {
+      const int ks = h->tc_ksplit[op] > 1 ? h->tc_ksplit[op] : 1;
+      grid.z = nfl * ks;
+      launch_k(h, K_TC_DW_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, ks, h->hp);
+      if (ks > 1) {
+        const int n4 = h->tc_maxNE[op] * pitch4(h->tc_maxME[op]) / 4;
+        launch_k(h, k_splitk_reduce, dim3(std::min((n4 + 255) / 256, 64), nfl, 1), dim3(256), 0, st, d, ks);
+      }
+    } else if (!oi.bt) launch_k(h, K_TC_FWD_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp);
     else launch_k(h, K_TC_DX_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp);
     return true;
   }
@@ -1072,7 +1117,7 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
     const char* env = getenv("MRGAN_CHAINS");
     int nch = env ? atoi(env) : (h->nf >= 32 ? 4 : (h->nf >= 8 ? 2 : 1));
     if (nch < 1) nch = 1;
-    if (nch > 4) nch = 4;
+    if (nch > kMaxChains) nch = kMaxChains;
     if (nch > h->nf) nch = h->nf;
     h->nchains = nch;
     h->cmain[0] = h->stream; h->cside[0] = h->side;
@@ -1132,7 +1177,7 @@ int mrgan_destroy(mrgan_handle* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int i = 0; i < 16; ++i) if (h->ev_pool[i]) cudaEventDestroy(h->ev_pool[i]);
-  for (int ch = 1; ch < 4; ++ch) { if (h->cmain[ch]) cudaStreamDestroy(h->cmain[ch]); if (h->cside[ch]) cudaStreamDestroy(h->cside[ch]); }
+  for (int ch = 1; ch < kMaxChains; ++ch) { if (h->cmain[ch]) cudaStreamDestroy(h->cmain[ch]); if (h->cside[ch]) cudaStreamDestroy(h->cside[ch]); }
   if (h->side) cudaStreamDestroy(h->side);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
