@@ -116,6 +116,22 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float v[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float v[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 }  // namespace tc
 
 // A_MN / B_MN: operand is MN-major (its MMA M/N dimension is the memory-contiguous one).
@@ -328,12 +344,30 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         }
       }
     } else {
+      // GaussianNoise of the next layer's input (EPI_FWD with C2): the draws do not depend on the accumulator, and the
+      // epilogue warps are idle while the TMA/MMA warps run the mainloop -- so they draw now and park the values in the
+      // TMEM columns the accumulator leaves free (sub-tile s owns columns [256 s + bn, 256 s + 256); with one sub-tile the
+      // two warp groups share [bn, TMEM_COLS)).  Row groups that do not fit are drawn in the epilogue as before.
+      int npre = 0;
+      uint32_t tnoise = 0;
+      if (epi == EPI_FWD && noisy && ((g.row0 + n0 + cbeg) & 3) == 0 && (hp.dp_bg == hp.dp_bloc || (hp.dp_bloc & 3) == 0)) {
+        int fbeg, flen;
+        if (MT == 2) { fbeg = 256 * sub + bn; flen = 256 - bn; }
+        else { flen = ((TMEM_COLS - bn) / (EPW == 8 ? 2 : 1)) & ~3; fbeg = bn + wg * flen; }
+        npre = min(flen >> 2, (ncols - cbeg + 3) >> 2);
+        tnoise = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)fbeg;
+        for (int gi = 0; gi < npre; ++gi) {
+          float nz[4];
+          normal4(key0, key1, (uint32_t)global_row(g.row0 + n0 + cbeg + 4 * gi, hp) >> 2, (uint32_t)f, step, (uint32_t)g.tid, nz);
+          tmem_st4(tnoise + 4u * (uint32_t)gi, nz);
+        }
+        if (npre > 0) tmem_wait_st();
+      }
       mbar_wait(tmem_full, 0);
       fence_after();
       for (int c0 = cbeg; c0 < ncols; c0 += 16) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c0, v);                   // warp-collective: every lane takes part
-        if (!f_ok) continue;
         if (epi == EPI_FWD) {
           // rows r = n0 + c0 + j; noise is grouped by 4 consecutive rows of one column (= this feature)
 #pragma unroll
@@ -342,11 +376,15 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
             if (r0 >= NE) break;
             float nz[4] = {0.f, 0.f, 0.f, 0.f};
             if (noisy) {
-              if (((g.row0 + r0) & 3) == 0 && (hp.dp_bg == hp.dp_bloc || (hp.dp_bloc & 3) == 0))
+              const int gi = ((c0 - cbeg) >> 2) + q;
+              if (gi < npre)                                 // warp-uniform: the TMEM load stays convergent
+                tmem_ld4(tnoise + 4u * (uint32_t)gi, nz);
+              else if (((g.row0 + r0) & 3) == 0 && (hp.dp_bg == hp.dp_bloc || (hp.dp_bloc & 3) == 0))
                 normal4(key0, key1, (uint32_t)global_row(g.row0 + r0, hp) >> 2, (uint32_t)f, step, (uint32_t)g.tid, nz);
               else
                 for (int i = 0; i < 4; ++i) nz[i] = normal1(key0, key1, (uint32_t)global_row(g.row0 + r0 + i, hp), (uint32_t)f, step, (uint32_t)g.tid);
             }
+            if (!f_ok) continue;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int r = r0 + i;
@@ -359,6 +397,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
             }
           }
         } else {   // EPI_STORE: dW into the flat gradient buffer (data-parallel mode: all-reduced before Adam)
+          if (!f_ok) continue;
           float* const dst = ksplit > 1 ? op.ws + (size_t)kslice * op.ws_stride : g.C;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
