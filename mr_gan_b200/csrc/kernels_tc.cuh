@@ -130,6 +130,15 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float v[4]) {
                ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
                : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float v[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 }  // namespace tc
@@ -329,11 +338,41 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
           g.C[(size_t)(n0 + c0 + j) * g.ldc + f] = (g.rnd & 1) ? rna_tf32(x) : x;
         }
       };
+      // The h values do not depend on the accumulator either: whole 16-row chunks of them are loaded while the mainloop
+      // runs and parked in the free TMEM columns (same split as the forward epilogue's noise); what does not fit is
+      // register-prefetched one chunk ahead as before.
       float avA[16], avB[16], v[16];
-      fetch(cbeg, avA);
+      int cpk = cbeg;                                   // rows [cbeg, cpk) of this thread's range are parked
+      uint32_t taux = 0;
+      if (g.act != ACT_NONE) {
+        int fbeg, flen;
+        if (MT == 2) { fbeg = 256 * sub + bn; flen = 256 - bn; }
+        else { flen = ((TMEM_COLS - bn) / (EPW == 8 ? 2 : 1)) & ~15; fbeg = bn + wg * flen; }
+        const int nchunk = min(flen >> 4, (ncols - cbeg + 15) >> 4);
+        taux = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)fbeg;
+        if (nchunk > 0) {
+          fetch(cbeg, avA);
+          for (int k = 0; k < nchunk; k += 2) {
+            if (k + 1 < nchunk) fetch(cbeg + 16 * (k + 1), avB);
+            tmem_st16(taux + 16u * (uint32_t)k, avA);
+            if (k + 1 < nchunk) {
+              if (k + 2 < nchunk) fetch(cbeg + 16 * (k + 2), avA);
+              tmem_st16(taux + 16u * (uint32_t)(k + 1), avB);
+            }
+          }
+          tmem_wait_st();
+          cpk = cbeg + 16 * nchunk;
+        }
+      }
+      if (cpk < ncols) fetch(cpk, avA);
       mbar_wait(tmem_full, 0);
       fence_after();
-      for (int c0 = cbeg; c0 < ncols; c0 += 32) {
+      for (int c0 = cbeg; c0 < min(cpk, ncols); c0 += 16) {
+        tmem_ld16(trow + (uint32_t)c0, v);
+        tmem_ld16(taux + (uint32_t)(c0 - cbeg), avB);
+        apply(c0, v, avB);
+      }
+      for (int c0 = cpk; c0 < ncols; c0 += 32) {
         tmem_ld16(trow + (uint32_t)c0, v);
         if (c0 + 16 < ncols) fetch(c0 + 16, avB);
         apply(c0, v, avA);

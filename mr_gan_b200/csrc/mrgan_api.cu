@@ -797,6 +797,7 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 #define K_TC_FWD_N k_gemm_tc<true, false, TC_FWD_STAGES, 512, 1, 8, 1>   // all 512 TMEM columns: room to park the epilogue's noise
 #define K_TC_DX k_gemm_tc<false, false, TC_FWD_STAGES, 256, 1, 8, 1>
 #define K_TC_FWD2 k_gemm_tc<true, false, TC_FWD_STAGES, 512, 1, 8, 2>     // 256 features per CTA (layers >= 500 wide)
+#define K_TC_DX_N k_gemm_tc<false, false, TC_FWD_STAGES, 512, 1, 8, 1>
 #define K_TC_DX2 k_gemm_tc<false, false, TC_FWD_STAGES, 512, 1, 8, 2>
 #define K_TC_DW k_gemm_tc<true, true, TC_DW_STAGES, 128, 2, 4, 1>
 // large-batch regime (more than 256 batch rows: data-parallel config 5): 256 x 256 tiles, 3-stage ring of 64 KB stages
@@ -823,6 +824,7 @@ void tc_set_smem_attr() {
   cudaFuncSetAttribute(K_TC_FWD, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
   cudaFuncSetAttribute(K_TC_FWD_N, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
   cudaFuncSetAttribute(K_TC_DX, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
+  cudaFuncSetAttribute(K_TC_DX_N, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
   cudaFuncSetAttribute(K_TC_FWD_BIG, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(K_TC_DX_BIG, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(K_TC_DW_BIG, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1020,7 +1022,12 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
     else
       launch_k(h, K_TC_FWD, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp);
   }
-  else if (!oi.at && oi.bt) launch_k(h, K_TC_DX, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp);
+  else if (!oi.at && oi.bt) {
+    if (2 * tc_smem_bytes(bn, TC_FWD_STAGES) > 227 * 1024)
+      launch_k(h, K_TC_DX_N, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp);
+    else
+      launch_k(h, K_TC_DX, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp);
+  }
   else if (h->d_tcadam) launch_k(h, k_dw_adam_tc, grid, dim3(192), (size_t)TCA_SMEM_BYTES, st, (const TcAdamOp*)(h->d_tcadam + (size_t)op * h->nf + f0), h->d_folds, h->hp);
   else launch_k(h, K_TC_DW, grid, dim3(TC_DW_THREADS), tc_smem_bytes(bn, TC_DW_STAGES), st, d, h->d_folds, 0, h->hp);
   return true;
