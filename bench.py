@@ -110,11 +110,12 @@ def make_jobs(D_modality, n_folds, seed):
     return X, y.astype(np.int32), folds
 
 
-def cpu_pairs_per_sec(D, B, n_pairs, warm=3):
+def cpu_pairs_per_sec(D, B, n_pairs, warm=3, threads=None):
     """Restated CPU baseline: torch-CPU fp32 twin, Python loop, two calls per iteration, host noise."""
     import torch
     from oracle import gan_oracle as O, torch_twin as T
-    torch.set_num_threads(max(1, os.cpu_count() or 1))      # torchrun exports OMP_NUM_THREADS=1: use every host thread
+    # torchrun exports OMP_NUM_THREADS=1: use every host thread unless a thread count is asked for
+    torch.set_num_threads(threads or max(1, os.cpu_count() or 1))
     rng = np.random.default_rng(0)
     m = T.TorchGan(O.init_disc_params(D, rng), O.init_gen_params(D, rng), dtype=torch.float32)
     X = rng.standard_normal((6000, D)).astype(np.float32)
@@ -386,7 +387,9 @@ def main():
             "sanity": {"final_test_err_mean": float(np.mean(errs)), "last_loss_lab": float(st[:, 0].mean())}}
     if rank == 0 and world == 1 and not args.no_cpu:
         v, threads = cpu_pairs_per_sec(D, B, args.cpu_pairs)
+        v1, _ = cpu_pairs_per_sec(D, B, max(2, args.cpu_pairs // 6), warm=1, threads=1)     # 1 thread and all threads
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
+                                "value_1thread": v1,
                                 "sample": "%d D+G step-pairs of one fold (D=%d, B=%d), torch-CPU fp32 twin of the oracle "
                                           "(restated baseline, not Keras 2.0.9/Theano 0.9)" % (args.cpu_pairs, D, B)}
     fg.close()
