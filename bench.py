@@ -148,8 +148,8 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t0
     sample = "%d step-pairs per step of one fold (D=%d, B=%d), torch-CPU fp32 twin of the oracle" % (pairs_per_step, D, B)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "warmup": args.warmup, "ms_per_step": 1e3 * pairs_per_step / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "wall_ms": 1e3 * dt,
             "config": {"workload": "mr_gan table-1 fold, force+temperature D=%d, B=50 (CPU sample)" % D},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                              "host_cpus": os.cpu_count()},
