@@ -133,3 +133,39 @@ def test_cli_prints_reference_strings(fake, capsys, monkeypatch):
     assert mg.main(["--tables", "3", "--epochs", "1", "--seed", "3"]) == 0
     out = capsys.readouterr().out
     assert out.count("Average leave-one-object-out error:") == 10 and "plastic_00 Test error: 0.125" in out   # mr_gan.py:280-282
+
+
+def test_loo_and_kfold_jobs_reproduce_the_reference_splits():
+    """mr_gan.py:264-282 (table 3): one fold per held-out object, train = every other object's rows in dictionary order,
+    test = the object's rows; mr_gan.py:255-257 (tables 1/5/6): stratified 6-fold -> 6000/1200 rows at N=7200."""
+    import itertools
+    mg = importlib.import_module("mr_gan_b200.mr_gan")
+    rng = np.random.default_rng(3)
+    objects = {}
+    for o in range(9):                       # 9 objects x 100 pokes (the reference has 72 x 100)
+        objects["obj%d" % o] = {"x": rng.standard_normal((100, 7)).astype(np.float32), "y": np.full(100, o % 6)}
+    jobs = mg._loo_jobs(objects, percentlabeled=16)
+    assert len(jobs) == len(objects)
+    for j, (name, data) in zip(jobs, objects.items()):
+        # literal restatement of mr_gan.py:274-278
+        Xtest = np.array(data["x"]); ytest = np.array(data["y"])
+        Xtrain = np.array(list(itertools.chain.from_iterable([d["x"] for n, d in objects.items() if n != name])))
+        ytrain = np.array(list(itertools.chain.from_iterable([d["y"] for n, d in objects.items() if n != name])))
+        assert j["name"] == name and j["percentlabeled"] == 16
+        np.testing.assert_array_equal(j["X"][j["train_idx"]], Xtrain)
+        np.testing.assert_array_equal(j["y"][j["train_idx"]], ytrain)
+        np.testing.assert_array_equal(j["X"][j["test_idx"]], Xtest)
+        np.testing.assert_array_equal(j["y"][j["test_idx"]], ytest)
+        assert mg.job_rows(j) == (800, 100) and mg.job_width(j) == 7
+
+    X = rng.standard_normal((7200, 5)).astype(np.float32)
+    y = np.repeat(np.arange(6), 1200)
+    kj = mg._kfold_jobs(X, y, 11, percentlabeled=50)
+    assert len(kj) == 6 and all(mg.job_rows(j) == (6000, 1200) for j in kj)
+    seen = np.concatenate([j["test_idx"] for j in kj])
+    assert np.array_equal(np.sort(seen), np.arange(7200))                  # every row is tested exactly once
+    for j in kj:
+        assert np.bincount(y[j["test_idx"]], minlength=6).tolist() == [200] * 6     # stratified (mr_gan.py:81: 200 per class)
+        assert not np.intersect1d(j["train_idx"], j["test_idx"]).size
+    again = mg._kfold_jobs(X, y, 11, percentlabeled=50)
+    assert all(np.array_equal(a["test_idx"], b["test_idx"]) for a, b in zip(kj, again))       # seeded -> reproducible
