@@ -33,6 +33,8 @@ struct alignas(64) TcOp {
   int net;                    // 0 = discriminator, 1 = generator (which lr_t the fused Adam uses)
   int ws_stride;              // split-K (large-batch dW): floats between the partial products of two contraction slices
   float* ws;                  // ... and their workspace, laid out like C; k_splitk_reduce sums the slices in a fixed order
+  int esz;                    // operand element size: 4 (or 0) = fp32 read as tf32, 2 = fp16 (kind::f16, fp32 accumulation)
+  int pad_[3];
 };
 
 #define TC_KBLK 32            // contraction elements per stage (one 128-byte swizzle row of fp32)
@@ -88,6 +90,13 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -179,7 +188,11 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb_all = (KE + TC_KBLK - 1) / TC_KBLK;
+  // 16-bit operands: a 128-byte swizzle row holds 64 contraction elements, an MMA covers K = 16, an MN-major box is
+  // 64 elements x 64 contraction rows (plain 128B swizzle, UMMA layout 2, SBO = 1024 B, LBO = 8192 B)
+  const bool f16 = op.esz == 2;
+  const int kblk = f16 ? 64 : TC_KBLK;
+  const int nkb_all = (KE + kblk - 1) / kblk;
   const int kb_per = (nkb_all + ksplit - 1) / ksplit;
   const int kb0 = kslice * kb_per;                           // the host picks ksplit so that no slice is empty
   const int nkb = min(nkb_all, kb0 + kb_per) - kb0;
@@ -211,16 +224,16 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         mbar_expect_tx(&full[s], stage_bytes);
         uint8_t* sa = smem + (size_t)s * stage_bytes;
         uint8_t* sb = sa + a_bytes;
-        const int k0 = (kb0 + kb) * TC_KBLK;
+        const int k0 = (kb0 + kb) * kblk;
+        const int bbytes = f16 ? 8192 : 4096;        // one MN-major box: kblk elements wide x kblk contraction rows
         if (A_MN) {
-#pragma unroll
-          for (int b = 0; b < 4 * MT; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * 4096, m0 + 32 * b, k0);
+          for (int b = 0; b < (128 / kblk) * MT; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * bbytes, m0 + kblk * b, k0);
         } else {
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) tma_load_2d(&op.mapA, &full[s], sa + mt * 16384, k0, m0 + 128 * mt);
         }
         if (B_MN) {
-          for (int b = 0; b < bn / 32; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * 4096, n0 + 32 * b, k0);
+          for (int b = 0; b < bn / kblk; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * bbytes, n0 + kblk * b, k0);
         } else {
           tma_load_2d(&op.mapB, &full[s], sb, k0, n0);
         }
@@ -229,12 +242,14 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+      const uint32_t fmt = f16 ? 0u : 2u;       // instruction descriptor operand formats: 0 = f16, 2 = tf32; D format 1 = f32
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t lboA = A_MN ? 4096u : 16u, lboB = B_MN ? 4096u : 16u;
-      const uint32_t sboA = A_MN ? 512u : 1024u, sboB = B_MN ? 512u : 1024u;
-      const uint32_t layA = A_MN ? 1u : 2u, layB = B_MN ? 1u : 2u;
-      const uint32_t stepA = A_MN ? 1024u : 32u, stepB = B_MN ? 1024u : 32u;   // bytes per 8 contraction elements
+      const uint32_t mn_lbo = f16 ? 8192u : 4096u, mn_sbo = f16 ? 1024u : 512u, mn_lay = f16 ? 2u : 1u, mn_step = f16 ? 2048u : 1024u;
+      const uint32_t lboA = A_MN ? mn_lbo : 16u, lboB = B_MN ? mn_lbo : 16u;
+      const uint32_t sboA = A_MN ? mn_sbo : 1024u, sboB = B_MN ? mn_sbo : 1024u;
+      const uint32_t layA = A_MN ? mn_lay : 2u, layB = B_MN ? mn_lay : 2u;
+      const uint32_t stepA = A_MN ? mn_step : 32u, stepB = B_MN ? mn_step : 32u;   // bytes per MMA (8 tf32 / 16 f16 contraction elements)
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -247,7 +262,8 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {      // sub-tile mt: A block at +16 KB, accumulator at TMEM column 256 * mt
             const uint64_t da = smem_desc(sa + mt * 16384u + k * stepA, lboA, sboA, layA);
-            mma_tf32(tmem_base + 256u * mt, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (f16) mma_f16(tmem_base + 256u * mt, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else mma_tf32(tmem_base + 256u * mt, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
         }
         mma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
@@ -264,6 +280,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
     const int f = m0 + 128 * sub + lane_base + lane;      // this thread's feature index (MMA-M)
     const bool f_ok = f < ME;
     const GemmDesc g = op.g;             // by value: descriptor fields must not be re-read from HBM around every store
+    const float debias = f16 ? 1.0f : TF32_TRUNC_DEBIAS;   // fp16 operand copies are rounded to nearest: nothing to remove
     const int epi = op.epi;
     float* const adamP = op.P; float* const adamM = op.Mo; float* const adamV = op.Vo;
     const int ncols = min(min(bn, NE - n0), cbeg + chalf);      // this warp's column range is [cbeg, ncols)
@@ -332,7 +349,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (c0 + j >= ncols) break;
-          float x = v[j] * TF32_TRUNC_DEBIAS;
+          float x = v[j] * debias;
           if (g.act == ACT_RELU) x = (av[j] > 0.f) ? x : 0.f;
           else if (g.act == ACT_SOFTPLUS) x *= 1.0f - __expf(-av[j]);
           g.C[(size_t)(n0 + c0 + j) * g.ldc + f] = (g.rnd & 1) ? rna_tf32(x) : x;
@@ -428,7 +445,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
             for (int i = 0; i < 4; ++i) {
               const int r = r0 + i;
               if (r >= NE) break;
-              float x = v[4 * q + i] * TF32_TRUNC_DEBIAS;
+              float x = v[4 * q + i] * debias;
               if (g.act == ACT_RELU) x = fmaxf(x, 0.f);
               else if (g.act == ACT_SOFTPLUS) x = softplusf(x);
               if (g.C) g.C[(size_t)r * g.ldc + f] = (g.rnd & 1) ? rna_tf32(x) : x;

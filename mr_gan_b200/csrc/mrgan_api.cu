@@ -2,6 +2,7 @@
 // declared in include/mrgan.h.  Reference interface replaced: the K.function callables of
 // mr_gan.py:169-171, the epoch loop mr_gan.py:183-230 and mr_nn.py:114-118.
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
@@ -73,7 +74,7 @@ int tc_setup(mrgan_handle* h);
 void tc_teardown(mrgan_handle* h);
 bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override, cudaStream_t st);
 void tc_params_changed(mrgan_handle* h, int fold, int net);
-int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g);
+int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g, int esz);
 }
 #endif
 
@@ -772,15 +773,21 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 // k-blocks touch the adjacent 128 bytes of the same DRAM page; fetching 256 B per miss halves the DRAM activations.
 CUtensorMapL2promotion g_l2_promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
 
-bool make_map(EncodeTiledFn fn, CUtensorMap* m, const float* base, int cols, int rows, int pitch, int box_rows,
-              bool mn_major, int box_cols = 32) {
+// esz = 4: fp32 elements (read as tf32); esz = 2: fp16 elements (`base` then points at __half data, pitch in elements).
+// The swizzled box is always one 128-byte row wide (32 fp32 / 64 fp16 elements); MN-major 32-bit operands need the
+// 32-byte-atom variant of the 128B swizzle, 16-bit ones the plain 128B swizzle.
+bool make_map(EncodeTiledFn fn, CUtensorMap* m, const void* base, int cols, int rows, int pitch, int box_rows,
+              bool mn_major, int box_cols = 0, int esz = 4) {
+  const int row_elems = 128 / esz;
+  if (box_cols == 0) box_cols = row_elems;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * (cuuint64_t)esz};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1u, 1u};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE,
-            box_cols != 32 ? CU_TENSOR_MAP_SWIZZLE_NONE : (mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
+  return fn(m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+            strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            box_cols != row_elems ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                  : ((mn_major && esz == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
             g_l2_promo,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -835,29 +842,32 @@ void tc_set_smem_attr() {
 }
 
 // fills the tcgen05 view of one GEMM (shapes in the fp32 path's convention); mode 0 fwd, 1 dX, 2 dW
-bool tc_fill_op(EncodeTiledFn fn, TcOp& t, const GemmDesc& g, int mode) {
+// esz = 2: g.A / g.B point at fp16 operand copies (pitches in elements); the epilogue side of g is unchanged.
+bool tc_fill_op(EncodeTiledFn fn, TcOp& t, const GemmDesc& g, int mode, int esz = 4) {
   t.g = g;
+  t.esz = esz;
   t.ME = g.N; t.NE = g.M; t.KE = g.K;
+  const int kb = 128 / esz;   // contraction rows of an MN-major box = elements of one 128-byte row
   if (mode == 0) {            // forward: C[M rows, N feats] = act[M, K] @ W[K, N]
     t.epi = EPI_FWD;
     t.bn = g.M <= 256 ? round_up(g.M, 16) : 256;
-    return make_map(fn, &t.mapA, g.B, g.N, g.K, g.ldb, 32, true) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false);
+    return make_map(fn, &t.mapA, g.B, g.N, g.K, g.ldb, kb, true, 0, esz) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false, 0, esz);
   }
   if (mode == 1) {            // dX: C[M rows, N in-feats] = dZ[M, K] @ W[N, K]^T
     t.epi = EPI_DX;
     t.bn = g.M <= 256 ? round_up(g.M, 16) : 256;
-    return make_map(fn, &t.mapA, g.B, g.K, g.N, g.ldb, 128, false) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false);
+    return make_map(fn, &t.mapA, g.B, g.K, g.N, g.ldb, 128, false, 0, esz) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false, 0, esz);
   }
   t.epi = EPI_STORE;          // dW: C[M in-feats(+1), N out-feats] = act[K rows, M]^T @ dZ[K rows, N]
   t.bn = g.K > 512 ? 256 : 128;   // a long contraction (large batch) is a regular big GEMM: 256 x 256 tiles
-  return make_map(fn, &t.mapA, g.B, g.N, g.K, g.ldb, 32, true) && make_map(fn, &t.mapB, g.A, g.M, g.K, g.lda, 32, true);
+  return make_map(fn, &t.mapA, g.B, g.N, g.K, g.ldb, kb, true, 0, esz) && make_map(fn, &t.mapB, g.A, g.M, g.K, g.lda, kb, true, 0, esz);
 }
 
-int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g) {
+int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g, int esz) {
   EncodeTiledFn fn = tc_encoder();
   if (!fn) return fail(h, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   TcOp t; memset(&t, 0, sizeof(t));
-  if (!tc_fill_op(fn, t, g, mode)) return fail(h, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  if (!tc_fill_op(fn, t, g, mode, esz)) return fail(h, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   TcOp* d = nullptr;
   CK(cudaMalloc(&d, sizeof(TcOp)));
   CK(cudaMemcpyAsync(d, &t, sizeof(t), cudaMemcpyHostToDevice, h->stream));
@@ -1720,8 +1730,23 @@ int mrgan_debug_gemm(mrgan_handle* h, int mode, int M, int N, int K, const float
   CK(cudaMemcpyAsync(dd, &g, sizeof(g), cudaMemcpyHostToDevice, h->stream));
   bool done = false;
 #ifdef MRGAN_WITH_TC
-  if (use_tc) {
-    rc = tc_debug_gemm(h, mode, g);
+  __half *hA = nullptr, *hB = nullptr;
+  if (use_tc == 2) {          // fp16 operand copies (kind::f16): host conversion, pitch rounded to 8 elements (16-byte TMA strides)
+    const int lha = (ac + 7) & ~7, lhb = (bc + 7) & ~7;
+    std::vector<__half> ha((size_t)ar * lha, __float2half(0.f)), hb((size_t)br * lhb, __float2half(0.f));
+    for (int r = 0; r < ar; ++r) for (int c2 = 0; c2 < ac; ++c2) ha[(size_t)r * lha + c2] = __float2half_rn(A[(size_t)r * ac + c2]);
+    for (int r = 0; r < br; ++r) for (int c2 = 0; c2 < bc; ++c2) hb[(size_t)r * lhb + c2] = __float2half_rn(B[(size_t)r * bc + c2]);
+    CK(cudaMalloc(&hA, ha.size() * sizeof(__half))); CK(cudaMalloc(&hB, hb.size() * sizeof(__half)));
+    CK(cudaMemcpy(hA, ha.data(), ha.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(hB, hb.data(), hb.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    GemmDesc gh = g;
+    gh.A = reinterpret_cast<const float*>(hA); gh.lda = lha; gh.B = reinterpret_cast<const float*>(hB); gh.ldb = lhb;
+    rc = tc_debug_gemm(h, mode, gh, 2);
+    cudaFree(hA); cudaFree(hB);
+    if (rc) return rc;
+    done = true;
+  } else if (use_tc) {
+    rc = tc_debug_gemm(h, mode, g, 4);
     if (rc) return rc;
     done = true;
   }
