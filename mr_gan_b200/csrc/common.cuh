@@ -9,6 +9,7 @@
 //    every activation buffer carries a constant 1.0 in column `in`, so bias add
 //    (forward) and bias gradient (backward) fall out of the GEMMs themselves.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -125,7 +126,15 @@ __device__ __forceinline__ float rna_tf32(float x) {
 //                         at the same element index (hbase[p - fbase]), so pitches and descriptor offsets carry over.
 //                         Gradient-side operands (dZ) are stored multiplied by the loss scale `gscale` (a power of two;
 //                         every consumer is linear, the Adam update divides it out again).
-struct OperandMode { int mode; float gscale; const float* fbase; __half* hbase; };
+//                         Alternative (grad_bf16 = 1, MRGAN_GRAD_BF16=1): gradient-side operands are stored as bf16 without
+//                         any scale -- fp32's exponent range, so tiny gradients keep their sign (Adam's first steps are
+//                         sign-like), at 8 instead of 11 significant bits; kind::f16 takes f16 and bf16 operands mixed.
+struct OperandMode { int mode; float gscale; const float* fbase; __half* hbase; int grad_bf16; };
+
+__device__ __forceinline__ void put_grad16(__half* dst, float x, const OperandMode& om) {
+  if (om.grad_bf16) *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(x);
+  else *dst = __float2half_rn(x);
+}
 
 #define MRGAN_F16_LOSS_SCALE 4096.0f
 
@@ -135,7 +144,8 @@ __device__ __forceinline__ void put_operand(float* p, float x, const OperandMode
 }
 // gradient-side operand produced from an UNSCALED value (loss heads, BatchNorm backward)
 __device__ __forceinline__ void put_grad_operand(float* p, float x, const OperandMode& om) {
-  put_operand(p, om.mode == 2 ? x * om.gscale : x, om);
+  if (om.mode == 2) put_grad16(om.hbase + (p - om.fbase), x * om.gscale, om);
+  else put_operand(p, x, om);
 }
 
 // kind::tf32 truncates the fp32 master weights it reads: w -> w (1 - e), e in [0, 2^-10).  For mantissas

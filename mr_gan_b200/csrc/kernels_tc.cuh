@@ -34,7 +34,8 @@ struct alignas(64) TcOp {
   int ws_stride;              // split-K (large-batch dW): floats between the partial products of two contraction slices
   float* ws;                  // ... and their workspace, laid out like C; k_splitk_reduce sums the slices in a fixed order
   int esz;                    // operand element size: 4 (or 0) = fp32 read as tf32, 2 = fp16 (kind::f16, fp32 accumulation)
-  int pad_[3];
+  int afmt, bfmt;             // esz == 2: element format of the A / B operand, 0 = f16, 1 = bf16 (gradient-side operands, optional)
+  int pad_[1];
 };
 
 #define TC_KBLK 32            // contraction elements per stage (one 128-byte swizzle row of fp32)
@@ -242,8 +243,9 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      const uint32_t fmt = f16 ? 0u : 2u;       // instruction descriptor operand formats: 0 = f16, 2 = tf32; D format 1 = f32
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+      // instruction descriptor operand formats: 0 = f16, 1 = bf16, 2 = tf32; D format 1 = f32
+      const uint32_t fmtA = f16 ? (uint32_t)op.afmt : 2u, fmtB = f16 ? (uint32_t)op.bfmt : 2u;
+      const uint32_t idesc = (1u << 4) | (fmtA << 7) | (fmtB << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t mn_lbo = f16 ? 8192u : 4096u, mn_sbo = f16 ? 1024u : 512u, mn_lay = f16 ? 2u : 1u, mn_step = f16 ? 2048u : 1024u;
       const uint32_t lboA = A_MN ? mn_lbo : 16u, lboB = B_MN ? mn_lbo : 16u;
@@ -356,7 +358,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
           if (g.act == ACT_RELU) x = (av[j] > 0.f) ? x : 0.f;
           else if (g.act == ACT_SOFTPLUS) x *= 1.0f - __expf(-av[j]);
           float* const pc = g.C + (size_t)(n0 + c0 + j) * g.ldc + f;
-          if (om.mode == 2 && (g.rnd & 1)) om.hbase[pc - om.fbase] = __float2half_rn(x);    // operand only: fp16 copy, loss-scaled like acc
+          if (om.mode == 2 && (g.rnd & 1)) put_grad16(om.hbase + (pc - om.fbase), x, om);    // operand only: 16-bit copy, loss-scaled like acc
           else *pc = (g.rnd & 1) ? rna_tf32(x) : x;
         }
       };
@@ -522,6 +524,7 @@ struct alignas(64) TcAdamOp {
   int fold;
   int net;
   int esz;                         // operand element size (4 = tf32, 2 = fp16 copies)
+  int afmt;                        // esz == 2: format of the dZ operand (0 = f16, 1 = bf16); the activation operand is f16
   int ldh;                         // pitch of W and of its fp16 operand copy
   float ginv;                      // 1 / loss scale carried by the dZ operand (1 unless fp16)
   __half* Ph;                      // fp16 operand copy of W, refreshed with every update (null unless fp16)
@@ -643,8 +646,8 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t fmt = f16 ? 0u : 2u;
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t fmtA = f16 ? (uint32_t)op.afmt : 2u, fmtB = f16 ? 0u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmtA << 7) | (fmtB << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t lbo = f16 ? 8192u : 4096u, sbo = f16 ? 1024u : 512u, lay = f16 ? 2u : 1u, kstep = f16 ? 2048u : 1024u;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;

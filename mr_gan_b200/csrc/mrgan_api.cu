@@ -97,7 +97,7 @@ struct mrgan_handle {
   cudaStream_t cmain[kMaxChains] = {nullptr}, cside[kMaxChains] = {nullptr};
   char* arena = nullptr; size_t arena_bytes = 0;
   __half* harena = nullptr;           // f16 mode: one __half per float of the arena (operand copies at the same element index)
-  OperandMode om = {0, 1.0f, nullptr, nullptr};
+  OperandMode om = {0, 1.0f, nullptr, nullptr, 0};
   float *P = nullptr, *Mo = nullptr, *Vo = nullptr, *Gr = nullptr; long long n_flat = 0;
   FoldState* d_folds = nullptr; std::vector<FoldState> h_folds;
   GemmDesc* d_descs = nullptr; std::vector<GemmDesc> h_descs;
@@ -200,9 +200,11 @@ __global__ void k_scale_buf(float* p, size_t n, float mul) {
 }
 
 // f16 mode, test hook: operand-only buffers exist as fp16 copies only; expand one (times `mul`) into a float scratch
-__global__ void k_from_half(const float* src, float* dst, size_t n, float mul, OperandMode om) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = __half2float(om.hbase[src + i - om.fbase]) * mul;
+__global__ void k_from_half(const float* src, float* dst, size_t n, float mul, OperandMode om, int bf16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const __half* p = om.hbase + (src + i - om.fbase);
+    dst[i] = (bf16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p)) : __half2float(*p)) * mul;
+  }
 }
 
 // ---- buffer layout (run twice: sizing pass with base == nullptr, then for real) ----
@@ -893,9 +895,9 @@ int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g, int esz) {
   CK(cudaMemcpyAsync(d, &t, sizeof(t), cudaMemcpyHostToDevice, h->stream));
   tc_set_smem_attr();
   dim3 grid((t.ME + 127) / 128, (t.NE + t.bn - 1) / t.bn, 1);
-  if (mode == 0) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr});
-  else if (mode == 1) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr});
-  else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr});
+  if (mode == 0) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
+  else if (mode == 1) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
+  else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
   h->launches++;
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(d);
@@ -925,6 +927,9 @@ int tc_setup(mrgan_handle* h) {
         gh.B = reinterpret_cast<const float*>(h->harena + (g.B - h->om.fbase));
         if (!tc_fill_op(fn, t, gh, mode, 2)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled (fp16 operands) failed");
         t.g = g;                // the epilogue keeps addressing the fp32 buffers (and derives the copies' addresses itself)
+        // which operand is gradient-side: dX contracts dZ (MMA-B) with W, dW contracts dZ^T (MMA-A) with the activations
+        t.afmt = (mode == 2) ? h->om.grad_bf16 : 0;
+        t.bfmt = (mode == 1) ? h->om.grad_bf16 : 0;
       } else if (!tc_fill_op(fn, t, g, mode)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
       t.net = (op == OP_GW1 || op == OP_GW2 || op == OP_GW3) ? 1 : 0;
       if (mode == 2) {
@@ -982,7 +987,7 @@ int tc_setup(mrgan_handle* h) {
         const TcOp& t = ops[(size_t)op * nf + f];
         TcAdamOp& a = aops[(size_t)op * nf + f];
         a.mapA = t.mapA; a.mapB = t.mapB; a.ME = t.ME; a.NE = t.NE; a.KE = t.KE; a.fold = t.g.fold; a.net = t.net;
-        a.esz = h->om.mode == 2 ? 2 : 4; a.ldh = t.g.ldc;
+        a.esz = h->om.mode == 2 ? 2 : 4; a.ldh = t.g.ldc; a.afmt = t.afmt;
         a.ginv = h->om.mode == 2 ? 1.0f / h->om.gscale : 1.0f;
         a.Ph = h->om.mode == 2 ? h->harena + (t.P - h->om.fbase) : nullptr;
         // W / m / v as [rows = in+1, cols = out] with the tensor's pitch; box 128 cols x KC rows, clipped at the logical extents
@@ -1160,7 +1165,7 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   if (e != cudaSuccess) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e)));
   Arena real; real.base = h->arena;
   layout_buffers(h, real);
-  h->om = OperandMode{cfg->precision, 1.0f, reinterpret_cast<const float*>(h->arena), nullptr};
+  h->om = OperandMode{cfg->precision, 1.0f, reinterpret_cast<const float*>(h->arena), nullptr, 0};
   if (cfg->precision == MRGAN_PREC_F16) {      // operand copies: one __half per float of the arena, zero like the arena
     e = cudaMalloc(&h->harena, h->arena_bytes / 2);
     if (e == cudaSuccess) e = cudaMemset(h->harena, 0, h->arena_bytes / 2);
@@ -1168,6 +1173,9 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
     if (e != cudaSuccess) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, std::string("cudaMalloc fp16 operand arena: ") + cudaGetErrorString(e)));
     h->om.hbase = h->harena;
     h->om.gscale = MRGAN_F16_LOSS_SCALE;
+    if (const char* gb = getenv("MRGAN_GRAD_BF16")) {      // gradient-side operands as unscaled bf16 instead of loss-scaled fp16
+      if (atoi(gb) != 0) { h->om.grad_bf16 = 1; h->om.gscale = 1.0f; }
+    }
   }
   bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess;
@@ -1403,7 +1411,7 @@ int mrgan_prepare_fold(mrgan_handle* h, int fold, int slot, const int32_t* train
   const int gx = (s.D + 127) / 128;
   k_col_stats<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows, s.n_train, s.D, h->d_prep_stats);
   k_scale_gather<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows, s.n_train, s.D, h->d_prep_stats, s.n_train,
-                                                     b.xtr, pitch8(s.D), ds.y, b.ytr, OperandMode{0, 1.0f, nullptr, nullptr});
+                                                     b.xtr, pitch8(s.D), ds.y, b.ytr, OperandMode{0, 1.0f, nullptr, nullptr, 0});
   k_scale_gather<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows + s.n_train, s.n_test, s.D, h->d_prep_stats, s.n_train,
                                                      b.xte, b.lda[0], ds.y, b.yte, h->om);
   h->launches += 3;
@@ -1763,7 +1771,8 @@ int mrgan_debug_buffer(mrgan_handle* h, int fold, int which, float* dst, int row
     const bool grad_only = (which >= 21 && which <= 25) || which == 31 || which == 32 || which == 44 || which == 46;
     if (act_only || grad_only) {
       CK(cudaMalloc(&tmp, (size_t)rows * ld * sizeof(float)));
-      k_from_half<<<256, 256, 0, h->stream>>>(src, tmp, (size_t)rows * ld, grad_only ? 1.0f / h->om.gscale : 1.0f, h->om);
+      k_from_half<<<256, 256, 0, h->stream>>>(src, tmp, (size_t)rows * ld, grad_only ? 1.0f / h->om.gscale : 1.0f, h->om,
+                                              grad_only && h->om.grad_bf16);
       src = tmp;
     } else if (which == 45) {   // du stays fp32 but carries the loss scale
       CK(cudaMalloc(&tmp, (size_t)rows * ld * sizeof(float)));
@@ -1868,9 +1877,9 @@ int mrgan_debug_gemm_time(mrgan_handle* h, int mode, int M, int N, int K, int gr
   const TcOp& t = ops[0];
   dim3 grid((t.ME + 127) / 128, (t.NE + t.bn - 1) / t.bn, groups);
   auto once = [&]() {
-    if (mode == 0) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr});
-    else if (mode == 1) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr});
-    else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr});
+    if (mode == 0) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
+    else if (mode == 1) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
+    else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
   };
   once();
   CK(cudaEventRecord(h->ev0, h->stream));
