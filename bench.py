@@ -235,7 +235,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--folds", type=int, default=74, help="fold-trainings grouped per GPU (table 1 has 294 = 4 x 73.5; 74 = 148/2 keeps every kernel at whole waves)")
     ap.add_argument("--modality", type=int, default=2, help="2 = force+temperature (D=1200)")
-    ap.add_argument("--precision", default=os.environ.get("MRGAN_PRECISION", "tf32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("MRGAN_PRECISION", "tf32"), choices=["fp32", "tf32", "f16"])
     ap.add_argument("--ref-pairs", type=int, default=12)
     ap.add_argument("--cpu-pairs", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")

@@ -48,7 +48,10 @@ enum { MRGAN_NET_D = 0, MRGAN_NET_G = 1 };
 enum { MRGAN_MODEL_GAN = 0,   /* mr_gan.py: G + D, feature matching          */
        MRGAN_MODEL_NN = 1 };  /* mr_nn.py: D as a plain classifier, MSE loss */
 enum { MRGAN_PREC_FP32 = 0,   /* FFMA kernels, fp32 operands (parity mode)                  */
-       MRGAN_PREC_TF32 = 1 }; /* tcgen05 kind::tf32 tensor-core kernels, fp32 accumulate    */
+       MRGAN_PREC_TF32 = 1,   /* tcgen05 kind::tf32 tensor-core kernels, fp32 accumulate    */
+       MRGAN_PREC_F16 = 2 };  /* tcgen05 kind::f16 on fp16 operand COPIES (weights, activations, loss-scaled
+                                 gradients; same 10-bit mantissa as tf32, rounded to nearest), fp32 master weights,
+                                 fp32 accumulation and Adam.  EXPERIMENTAL: not validated end to end yet. */
 
 /* Hyper-parameters; mrgan_default_config() fills the reference's values. */
 typedef struct {

@@ -9,6 +9,8 @@
 //    every activation buffer carries a constant 1.0 in column `in`, so bias add
 //    (forward) and bias gradient (backward) fall out of the GEMMs themselves.
 #pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -70,7 +72,8 @@ __host__ __device__ inline int global_row(int L, const AdamHyper& hp) {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-__host__ __device__ inline int pitch4(int w) { return (w + 3) & ~3; }
+// row pitch in elements: a multiple of 8 so that both the fp32 rows and their fp16 operand copies have 16-byte strides (TMA)
+__host__ __device__ inline int pitch8(int w) { return (w + 7) & ~7; }
 
 // ---------------------------------------------------------------- Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
@@ -114,6 +117,35 @@ __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
+}
+
+// How a kernel stores a value that the next tensor-core GEMM reads as an operand (precision mode of the handle):
+//   mode 0 (fp32 path)  : as is
+//   mode 1 (tf32)       : rounded to nearest onto the tf32 grid, in place
+//   mode 2 (f16)        : rounded to nearest to fp16 into the SHADOW arena -- one __half per float of the handle's arena
+//                         at the same element index (hbase[p - fbase]), so pitches and descriptor offsets carry over.
+//                         Gradient-side operands (dZ) are stored multiplied by the loss scale `gscale` (a power of two;
+//                         every consumer is linear, the Adam update divides it out again).
+//                         Alternative (grad_bf16 = 1, MRGAN_GRAD_BF16=1): gradient-side operands are stored as bf16 without
+//                         any scale -- fp32's exponent range, so tiny gradients keep their sign (Adam's first steps are
+//                         sign-like), at 8 instead of 11 significant bits; kind::f16 takes f16 and bf16 operands mixed.
+struct OperandMode { int mode; float gscale; const float* fbase; __half* hbase; int grad_bf16; };
+
+__device__ __forceinline__ void put_grad16(__half* dst, float x, const OperandMode& om) {
+  if (om.grad_bf16) *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(x);
+  else *dst = __float2half_rn(x);
+}
+
+#define MRGAN_F16_LOSS_SCALE 4096.0f
+
+__device__ __forceinline__ void put_operand(float* p, float x, const OperandMode& om) {
+  if (om.mode == 2) om.hbase[p - om.fbase] = __float2half_rn(x);
+  else *p = (om.mode == 1) ? rna_tf32(x) : x;
+}
+// gradient-side operand produced from an UNSCALED value (loss heads, BatchNorm backward)
+__device__ __forceinline__ void put_grad_operand(float* p, float x, const OperandMode& om) {
+  if (om.mode == 2) put_grad16(om.hbase + (p - om.fbase), x * om.gscale, om);
+  else put_operand(p, x, om);
 }
 
 // kind::tf32 truncates the fp32 master weights it reads: w -> w (1 - e), e in [0, 2^-10).  For mantissas

@@ -164,7 +164,7 @@ k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ fo
 // from_stage: rows come from the step-API staging buffers instead of the resident fold.
 __global__ void __launch_bounds__(128)
 k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, int t, int B, int nrows,
-       int noise_dim, float sigma_in, AdamHyper hp, int tf32) {
+       int noise_dim, float sigma_in, AdamHyper hp, OperandMode om) {
   pdl_launch_dependents();
   pdl_wait();
   FoldState& fs = folds[fold_base + blockIdx.z];
@@ -215,7 +215,7 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
       const int r = rg * 4 + i;
       if (r < r_lo || r >= r_hi) continue;
       const float v = xv[i] + sigma_in * nz[i];
-      a0[(size_t)r * lda0 + c] = tf32 ? rna_tf32(v) : v;
+      put_operand(a0 + (size_t)r * lda0 + c, v, om);
     }
   }
   if (mode != 2 && c < noise_dim) {       // generator input z (mr_gan.py:206,212)
@@ -229,7 +229,7 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
       const int r = rg * 4 + i;
       if (r >= B) break;
       const float v = from_stage ? fs.stage_z[(size_t)r * noise_dim + c] : nz[i];
-      fs.z[(size_t)r * fs.ldz + c] = tf32 ? rna_tf32(v) : v;
+      put_operand(fs.z + (size_t)r * fs.ldz + c, v, om);
     }
   }
 }
@@ -248,7 +248,7 @@ struct BnDesc {
 // The slice count is blockDim.x / 32: 8 at the reference batch, 32 in the large-batch regime.
 #define BN_COLS 32
 #define BN_MAX_SLICES 32
-__global__ void __launch_bounds__(1024) k_bn_fwd(const BnDesc* __restrict__ descs, float eps, int tf32) {
+__global__ void __launch_bounds__(1024) k_bn_fwd(const BnDesc* __restrict__ descs, float eps, OperandMode om) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[2][BN_MAX_SLICES][BN_COLS];
@@ -278,12 +278,12 @@ __global__ void __launch_bounds__(1024) k_bn_fwd(const BnDesc* __restrict__ desc
     const float xh = (d.h1[(size_t)r * d.ld + j] - mu) * istd;
     d.xhat[(size_t)r * d.ld + j] = xh;
     const float u = fmaf(g, xh, b);
-    d.u[(size_t)r * d.ldu + j] = tf32 ? rna_tf32(u) : u;
+    put_operand(d.u + (size_t)r * d.ldu + j, u, om);
   }
 }
 
 // BN backward + softplus' of the layer in front of it (G layer 1): du -> dgamma, dbeta, dz1.
-__global__ void __launch_bounds__(1024) k_bn_bwd(const BnDesc* __restrict__ descs, int tf32) {
+__global__ void __launch_bounds__(1024) k_bn_bwd(const BnDesc* __restrict__ descs, OperandMode om) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float red[2][BN_MAX_SLICES][BN_COLS];
@@ -292,9 +292,10 @@ __global__ void __launch_bounds__(1024) k_bn_bwd(const BnDesc* __restrict__ desc
   const int cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
   const int j = blockIdx.x * BN_COLS + cx;
   const bool ok = j < d.W;
+  const float ginv = (om.mode == 2) ? 1.0f / om.gscale : 1.0f;      // f16 mode: du arrives multiplied by the loss scale
   float p1 = 0.f, p2 = 0.f;
   if (ok) for (int r = sl; r < d.B; r += BN_SLICES) {
-    const float du = d.du[(size_t)r * d.ld + j];
+    const float du = d.du[(size_t)r * d.ld + j] * ginv;
     p1 += du;
     p2 = fmaf(du, d.xhat[(size_t)r * d.ld + j], p2);
   }
@@ -303,14 +304,17 @@ __global__ void __launch_bounds__(1024) k_bn_bwd(const BnDesc* __restrict__ desc
   float s1 = 0.f, s2 = 0.f;
   for (int i = 0; i < BN_SLICES; ++i) { s1 += red[0][i][cx]; s2 += red[1][i][cx]; }
   if (!ok) return;
-  if (sl == 0) { d.g_gamma[j] = s2; d.g_beta[j] = s1; }
+  if (sl == 0) {      // f16 mode: the whole gradient buffer carries the loss scale (k_adam divides it out)
+    const float gs = (om.mode == 2) ? om.gscale : 1.0f;
+    d.g_gamma[j] = s2 * gs; d.g_beta[j] = s1 * gs;
+  }
   const float g = d.gamma[j], istd = d.istd[j], invB = 1.0f / d.B;
   for (int r = sl; r < d.B; r += BN_SLICES) {
     const float xh = d.xhat[(size_t)r * d.ld + j];
-    const float dxh = d.du[(size_t)r * d.ld + j] * g;
+    const float dxh = d.du[(size_t)r * d.ld + j] * ginv * g;
     const float dh1 = istd * (dxh - invB * g * s1 - xh * invB * g * s2);
     const float dz = dh1 * (1.0f - expf(-d.h1[(size_t)r * d.ld + j]));
-    d.dz1[(size_t)r * d.ld + j] = tf32 ? rna_tf32(dz) : dz;
+    put_grad_operand(d.dz1 + (size_t)r * d.ld + j, dz, om);
   }
 }
 
@@ -325,7 +329,7 @@ struct LossDesc {
 // (mr_gan.py:146-149,161) and their gradients.
 __global__ void __launch_bounds__(256)
 k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total,
-            int t, int B, int K, float w_unl, int tf32, int Bg) {
+            int t, int B, int K, float w_unl, OperandMode om, int Bg) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sh[32];
@@ -345,7 +349,7 @@ k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, 
       s_err += (am != y) ? 1.f : 0.f;
       for (int k = 0; k < K; ++k) {
         const float g = (expf(l[k] - mx) * inv - (k == y ? 1.f : 0.f)) / Bg;
-        dl[k] = tf32 ? rna_tf32(g) : g;
+        put_grad_operand(dl + k, g, om);
       }
     } else {
       const float sp = softplusf(lse), sg = 1.0f / (1.0f + expf(-lse));
@@ -355,7 +359,7 @@ k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, 
       coef *= w_unl / Bg;
       for (int k = 0; k < K; ++k) {
         const float g = coef * expf(l[k] - mx) * inv;
-        dl[k] = tf32 ? rna_tf32(g) : g;
+        put_grad_operand(dl + k, g, om);
       }
     }
   }
@@ -372,7 +376,7 @@ k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, 
 // Writes dZ5 (already multiplied by ReLU') for the fake rows.  1024 threads = 256 columns x 4 row slices.
 __global__ void __launch_bounds__(1024)
 k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total, int t, int B,
-     int tf32) {
+     OperandMode om) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sh[32];
@@ -393,10 +397,9 @@ k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fol
     mr = red[1][0][cx] + red[1][1][cx] + red[1][2][cx] + red[1][3][cx];
     const float diff = (mg - mr) / B;
     if (sl == 0) s = fmaf(diff, diff, s);
-    float g = 2.0f * diff / ((float)d.Wmid * B);
-    if (tf32) g = rna_tf32(g);
+    const float g = 2.0f * diff / ((float)d.Wmid * B);
     for (int r = sl; r < B; r += 4)
-      d.dmid[(size_t)r * d.lddmid + j] = (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : 0.f;
+      put_grad_operand(d.dmid + (size_t)r * d.lddmid + j, (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : 0.f, om);
   }
   s = block_sum(s, sh);
   if (threadIdx.x == 0) step_stats[((size_t)t * nf_total + fold_base + blockIdx.z) * 4 + 3] = s / d.Wmid;
@@ -405,14 +408,14 @@ k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fol
 // mr_nn.py:114 loss='mse' vs one-hot, metrics=['accuracy'].
 __global__ void __launch_bounds__(256)
 k_loss_mse(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total,
-           int t, int n, int rows_total, int K, int tf32) {
+           int t, int n, int rows_total, int K, OperandMode om) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sh[32];
   const LossDesc d = descs[blockIdx.z];
   float s_loss = 0.f, s_acc = 0.f;
   for (int r = n + threadIdx.x; r < rows_total; r += blockDim.x)     // ragged batch: no gradient from the unused rows
-    for (int k = 0; k < K; ++k) d.dlogits[(size_t)r * d.ld + k] = 0.f;
+    for (int k = 0; k < K; ++k) put_grad_operand(d.dlogits + (size_t)r * d.ld + k, 0.f, om);
   for (int r = threadIdx.x; r < n; r += blockDim.x) {
     const float* l = d.logits + (size_t)r * d.ld;
     float* dl = d.dlogits + (size_t)r * d.ld;
@@ -424,7 +427,7 @@ k_loss_mse(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, i
       const float diff = l[k] - (k == y ? 1.f : 0.f);
       q = fmaf(diff, diff, q);
       const float g = 2.0f * diff / ((float)n * K);
-      dl[k] = tf32 ? rna_tf32(g) : g;
+      put_grad_operand(dl + k, g, om);
     }
     s_loss += q / K;
     s_acc += (am == y) ? 1.f : 0.f;
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(1024) k_bn_stats(const BnDesc* __restrict__ de
 }
 
 __global__ void __launch_bounds__(1024) k_bn_apply(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs,
-                                                   float eps, int tf32, int Bg) {
+                                                   float eps, OperandMode om, int Bg) {
   const BnDesc d = descs[blockIdx.z];
   const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
   const int j = blockIdx.x * BN_COLS + cx;
@@ -475,41 +478,45 @@ __global__ void __launch_bounds__(1024) k_bn_apply(const BnDesc* __restrict__ de
     const float xh = (d.h1[(size_t)r * d.ld + j] - mu) * istd;
     d.xhat[(size_t)r * d.ld + j] = xh;
     const float u = fmaf(g, xh, b);
-    d.u[(size_t)r * d.ldu + j] = tf32 ? rna_tf32(u) : u;
+    put_operand(d.u + (size_t)r * d.ldu + j, u, om);
   }
 }
 
-__global__ void __launch_bounds__(1024) k_bn_bwd_stats(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs) {
+__global__ void __launch_bounds__(1024) k_bn_bwd_stats(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs,
+                                                       OperandMode om) {
   __shared__ float red[2][BN_MAX_SLICES][BN_COLS];
   const BnDesc d = descs[blockIdx.z];
   const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
   const int j = blockIdx.x * BN_COLS + cx;
+  const float ginv = (om.mode == 2) ? 1.0f / om.gscale : 1.0f;
   float s1 = 0.f, s2 = 0.f;
-  if (j < d.W) for (int r = sl; r < d.B; r += nsl) { const float du = d.du[(size_t)r * d.ld + j]; s1 += du; s2 = fmaf(du, d.xhat[(size_t)r * d.ld + j], s2); }
+  if (j < d.W) for (int r = sl; r < d.B; r += nsl) { const float du = d.du[(size_t)r * d.ld + j] * ginv; s1 += du; s2 = fmaf(du, d.xhat[(size_t)r * d.ld + j], s2); }
   red[0][sl][cx] = s1; red[1][sl][cx] = s2;
   __syncthreads();
   if (sl == 0 && j < d.W) {
     s1 = 0.f; s2 = 0.f;
     for (int i = 0; i < nsl; ++i) { s1 += red[0][i][cx]; s2 += red[1][i][cx]; }
-    d.g_gamma[j] = s2; d.g_beta[j] = s1;        // LOCAL partial gradients: the flat gradient all-reduce completes them
+    const float gs = (om.mode == 2) ? om.gscale : 1.0f;
+    d.g_gamma[j] = s2 * gs; d.g_beta[j] = s1 * gs;        // LOCAL partial gradients: the flat gradient all-reduce completes them
     bufs[blockIdx.z].bnb[j] = s1; bufs[blockIdx.z].bnb[d.W + j] = s2;
   }
 }
 
 __global__ void __launch_bounds__(1024) k_bn_bwd_apply(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs,
-                                                       int tf32, int Bg) {
+                                                       OperandMode om, int Bg) {
   const BnDesc d = descs[blockIdx.z];
   const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
   const int j = blockIdx.x * BN_COLS + cx;
   if (j >= d.W) return;
   const float s1 = bufs[blockIdx.z].bnb[j], s2 = bufs[blockIdx.z].bnb[d.W + j];
   const float g = d.gamma[j], istd = d.istd[j], invB = 1.0f / Bg;
+  const float ginv = (om.mode == 2) ? 1.0f / om.gscale : 1.0f;
   for (int r = sl; r < d.B; r += nsl) {
     const float xh = d.xhat[(size_t)r * d.ld + j];
-    const float dxh = d.du[(size_t)r * d.ld + j] * g;
+    const float dxh = d.du[(size_t)r * d.ld + j] * ginv * g;
     const float dh1 = istd * (dxh - invB * g * s1 - xh * invB * g * s2);
     const float dz = dh1 * (1.0f - expf(-d.h1[(size_t)r * d.ld + j]));
-    d.dz1[(size_t)r * d.ld + j] = tf32 ? rna_tf32(dz) : dz;
+    put_grad_operand(d.dz1 + (size_t)r * d.ld + j, dz, om);
   }
 }
 
@@ -532,17 +539,16 @@ __global__ void __launch_bounds__(1024) k_fm_stats(const LossDesc* __restrict__ 
 
 __global__ void __launch_bounds__(1024)
 k_fm_apply(const LossDesc* __restrict__ descs, const DpBufs* __restrict__ bufs, float* __restrict__ step_stats, int fold_base,
-           int nf_total, int t, int B, int tf32, int Bg, int world) {
+           int nf_total, int t, int B, OperandMode om, int Bg, int world) {
   __shared__ float sh[32];
   const LossDesc d = descs[blockIdx.z];
   const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
   const int j = blockIdx.x * BN_COLS + cx;
   if (j < d.Wmid) {
     const float diff = (bufs[blockIdx.z].fm[j] - bufs[blockIdx.z].fm[d.Wmid + j]) / Bg;
-    float g = 2.0f * diff / ((float)d.Wmid * Bg);
-    if (tf32) g = rna_tf32(g);
+    const float g = 2.0f * diff / ((float)d.Wmid * Bg);
     for (int r = sl; r < B; r += nsl)
-      d.dmid[(size_t)r * d.lddmid + j] = (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : 0.f;
+      put_grad_operand(d.dmid + (size_t)r * d.lddmid + j, (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : 0.f, om);
   }
   if (blockIdx.x == 0) {      // the loss itself: every rank holds the same global value; the statistics block is summed over ranks
     float s = 0.f;            // afterwards, so 1/world of it is stored
@@ -609,7 +615,8 @@ struct AdamRange { long long off; long long n; };   // n multiple of 4, off 16B 
 
 __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ Vo, const float* __restrict__ G,
-       const AdamRange* __restrict__ ranges, FoldState* __restrict__ folds, int fold_base, int net, AdamHyper hp) {
+       const AdamRange* __restrict__ ranges, FoldState* __restrict__ folds, int fold_base, int net, AdamHyper hp,
+       float ginv, __half* __restrict__ Ph) {      // ginv: 1 / loss scale of the gradient buffer; Ph: fp16 operand copy of P or null
   pdl_launch_dependents();
   pdl_wait();
   const int f = fold_base + blockIdx.y;
@@ -624,16 +631,27 @@ k_adam(float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ Vo, co
   const float4* g4 = reinterpret_cast<const float4*>(G + rg.off);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 p = p4[i], m = m4[i], v = v4[i];
-    const float4 g = __ldg(g4 + i);
+    float4 g = __ldg(g4 + i);
+    g.x *= ginv; g.y *= ginv; g.z *= ginv; g.w *= ginv;
 #define ADAM1(c) m.c = fmaf(b1, m.c, c1 * g.c); v.c = fmaf(b2, v.c, c2 * g.c * g.c); p.c -= lr_t * m.c / (sqrtf(v.c) + eps);
     ADAM1(x) ADAM1(y) ADAM1(z) ADAM1(w)
 #undef ADAM1
     p4[i] = p; m4[i] = m; v4[i] = v;
+    if (Ph) {
+      __half2* h2 = reinterpret_cast<__half2*>(Ph + rg.off) + 2 * i;
+      h2[0] = __floats2half2_rn(p.x, p.y); h2[1] = __floats2half2_rn(p.z, p.w);
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     if (hp.shared_t) fs.iterations += 1; else fs.it_net[net] += 1;
     fs.rng_step += 1;
   }
+}
+
+// fp16 operand copy of a contiguous float range of the arena (f16 mode: uploaded parameters, test inputs)
+__global__ void __launch_bounds__(256) k_to_half(const float* __restrict__ src, size_t n, OperandMode om) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    om.hbase[src + i - om.fbase] = __float2half_rn(src[i]);
 }
 
 // standalone flat Adam on caller-provided buffers (mrgan_adam_flat; unit tests + roofline probe)
@@ -680,7 +698,7 @@ k_col_stats(const float* __restrict__ X, int ldx, const int* __restrict__ rows, 
 // StandardScaler.transform + row gather: out[i, c] = float((X[rows[i], c] - mean_c) / std_c), std 0 -> 1 (sklearn).
 __global__ void __launch_bounds__(128)
 k_scale_gather(const float* __restrict__ X, int ldx, const int* __restrict__ rows, int n_rows, int D, const double* __restrict__ stats,
-               int n_fit, float* __restrict__ out, int ldo, const int* __restrict__ y_src, int* __restrict__ y_out, int tf32) {
+               int n_fit, float* __restrict__ out, int ldo, const int* __restrict__ y_src, int* __restrict__ y_out, OperandMode om) {
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= D) return;
   const double mean = stats[c] / n_fit;
@@ -690,7 +708,8 @@ k_scale_gather(const float* __restrict__ X, int ldx, const int* __restrict__ row
   if (sd < 1e-300 || var <= 10.0 * 2.220446049250313e-16 * fabs(mean) * fabs(mean)) sd = 1.0;   // constant column
   for (int i = blockIdx.y; i < n_rows; i += gridDim.y) {
     const float v = (float)(((double)X[(size_t)rows[i] * ldx + c] - mean) / sd);
-    out[(size_t)i * ldo + c] = tf32 ? rna_tf32(v) : v;
+    out[(size_t)i * ldo + c] = (om.mode == 1) ? rna_tf32(v) : v;
+    if (om.mode == 2) om.hbase[out + (size_t)i * ldo + c - om.fbase] = __float2half_rn(v);     // X_test is a GEMM operand
     if (c == 0 && y_out) y_out[i] = y_src[rows[i]];
   }
 }

@@ -33,6 +33,9 @@ struct alignas(64) TcOp {
   int net;                    // 0 = discriminator, 1 = generator (which lr_t the fused Adam uses)
   int ws_stride;              // split-K (large-batch dW): floats between the partial products of two contraction slices
   float* ws;                  // ... and their workspace, laid out like C; k_splitk_reduce sums the slices in a fixed order
+  int esz;                    // operand element size: 4 (or 0) = fp32 read as tf32, 2 = fp16 (kind::f16, fp32 accumulation)
+  int afmt, bfmt;             // esz == 2: element format of the A / B operand, 0 = f16, 1 = bf16 (gradient-side operands, optional)
+  int pad_[1];
 };
 
 #define TC_KBLK 32            // contraction elements per stage (one 128-byte swizzle row of fp32)
@@ -88,6 +91,13 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t 
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -154,7 +164,7 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // warp group of the epilogue owns one sub-tile.  MT = 2 requires EPW = 8 and TMEM_COLS = 512.
 template <bool A_MN, bool B_MN, int STAGES, int TMEM_COLS, int MINB, int EPW, int MT>
 __global__ void __launch_bounds__(64 + 32 * EPW, MINB)
-k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_override, AdamHyper hp) {
+k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_override, AdamHyper hp, OperandMode om) {
   using namespace tc;
   pdl_launch_dependents();
   // dW (B_MN) kernels take the number of contraction slices in `rows_override`: blockIdx.z = fold * ksplit + slice, each
@@ -179,7 +189,11 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb_all = (KE + TC_KBLK - 1) / TC_KBLK;
+  // 16-bit operands: a 128-byte swizzle row holds 64 contraction elements, an MMA covers K = 16, an MN-major box is
+  // 64 elements x 64 contraction rows (plain 128B swizzle, UMMA layout 2, SBO = 1024 B, LBO = 8192 B)
+  const bool f16 = op.esz == 2;
+  const int kblk = f16 ? 64 : TC_KBLK;
+  const int nkb_all = (KE + kblk - 1) / kblk;
   const int kb_per = (nkb_all + ksplit - 1) / ksplit;
   const int kb0 = kslice * kb_per;                           // the host picks ksplit so that no slice is empty
   const int nkb = min(nkb_all, kb0 + kb_per) - kb0;
@@ -211,16 +225,16 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         mbar_expect_tx(&full[s], stage_bytes);
         uint8_t* sa = smem + (size_t)s * stage_bytes;
         uint8_t* sb = sa + a_bytes;
-        const int k0 = (kb0 + kb) * TC_KBLK;
+        const int k0 = (kb0 + kb) * kblk;
+        const int bbytes = f16 ? 8192 : 4096;        // one MN-major box: kblk elements wide x kblk contraction rows
         if (A_MN) {
-#pragma unroll
-          for (int b = 0; b < 4 * MT; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * 4096, m0 + 32 * b, k0);
+          for (int b = 0; b < (128 / kblk) * MT; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * bbytes, m0 + kblk * b, k0);
         } else {
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) tma_load_2d(&op.mapA, &full[s], sa + mt * 16384, k0, m0 + 128 * mt);
         }
         if (B_MN) {
-          for (int b = 0; b < bn / 32; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * 4096, n0 + 32 * b, k0);
+          for (int b = 0; b < bn / kblk; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * bbytes, n0 + kblk * b, k0);
         } else {
           tma_load_2d(&op.mapB, &full[s], sb, k0, n0);
         }
@@ -229,12 +243,15 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+      // instruction descriptor operand formats: 0 = f16, 1 = bf16, 2 = tf32; D format 1 = f32
+      const uint32_t fmtA = f16 ? (uint32_t)op.afmt : 2u, fmtB = f16 ? (uint32_t)op.bfmt : 2u;
+      const uint32_t idesc = (1u << 4) | (fmtA << 7) | (fmtB << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t lboA = A_MN ? 4096u : 16u, lboB = B_MN ? 4096u : 16u;
-      const uint32_t sboA = A_MN ? 512u : 1024u, sboB = B_MN ? 512u : 1024u;
-      const uint32_t layA = A_MN ? 1u : 2u, layB = B_MN ? 1u : 2u;
-      const uint32_t stepA = A_MN ? 1024u : 32u, stepB = B_MN ? 1024u : 32u;   // bytes per 8 contraction elements
+      const uint32_t mn_lbo = f16 ? 8192u : 4096u, mn_sbo = f16 ? 1024u : 512u, mn_lay = f16 ? 2u : 1u, mn_step = f16 ? 2048u : 1024u;
+      const uint32_t lboA = A_MN ? mn_lbo : 16u, lboB = B_MN ? mn_lbo : 16u;
+      const uint32_t sboA = A_MN ? mn_sbo : 1024u, sboB = B_MN ? mn_sbo : 1024u;
+      const uint32_t layA = A_MN ? mn_lay : 2u, layB = B_MN ? mn_lay : 2u;
+      const uint32_t stepA = A_MN ? mn_step : 32u, stepB = B_MN ? mn_step : 32u;   // bytes per MMA (8 tf32 / 16 f16 contraction elements)
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -247,7 +264,8 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {      // sub-tile mt: A block at +16 KB, accumulator at TMEM column 256 * mt
             const uint64_t da = smem_desc(sa + mt * 16384u + k * stepA, lboA, sboA, layA);
-            mma_tf32(tmem_base + 256u * mt, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (f16) mma_f16(tmem_base + 256u * mt, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            else mma_tf32(tmem_base + 256u * mt, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
         }
         mma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
@@ -264,6 +282,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
     const int f = m0 + 128 * sub + lane_base + lane;      // this thread's feature index (MMA-M)
     const bool f_ok = f < ME;
     const GemmDesc g = op.g;             // by value: descriptor fields must not be re-read from HBM around every store
+    const float debias = f16 ? 1.0f : TF32_TRUNC_DEBIAS;   // fp16 operand copies are rounded to nearest: nothing to remove
     const int epi = op.epi;
     float* const adamP = op.P; float* const adamM = op.Mo; float* const adamV = op.Vo;
     const int ncols = min(min(bn, NE - n0), cbeg + chalf);      // this warp's column range is [cbeg, ncols)
@@ -282,6 +301,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
       // W, m, v.  The three streams are register double-buffered one 16-column chunk ahead, and the first chunk
       // is requested BEFORE the accumulator is ready, so HBM latency overlaps the TMA/MMA phase.
       const float b1 = hp.b1, b2 = hp.b2, c1 = 1.0f - hp.b1, c2 = 1.0f - hp.b2, eps = hp.eps;
+      const float ginv_a = (om.mode == 2) ? 1.0f / om.gscale : 1.0f;      // the dZ operand carries the loss scale
       // 8-column chunks: 2 x 24 prefetch registers keep the kernel under the 2-CTA/SM register budget (no spills,
       // which would force every load to be waited for immediately)
       auto fetch = [&](int c0, float (&pw)[8], float (&pm)[8], float (&pv)[8]) {
@@ -298,10 +318,12 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         for (int j = 0; j < 8; ++j) {
           if (f_ok && c0 + j < ncols) {
             const size_t idx = (size_t)(n0 + c0 + j) * g.ldc + f;
-            const float gr = v[j];
+            const float gr = v[j] * ginv_a;
             const float m = fmaf(b1, pm[j], c1 * gr), vv = fmaf(b2, pv[j], c2 * gr * gr);
             __stcs(adamM + idx, m); __stcs(adamV + idx, vv);
-            __stcs(adamP + idx, pw[j] - lr_t * __fdividef(m, sqrtf(vv) + eps));
+            const float w = pw[j] - lr_t * __fdividef(m, sqrtf(vv) + eps);
+            __stcs(adamP + idx, w);
+            if (om.mode == 2) om.hbase[adamP + idx - om.fbase] = __float2half_rn(w);
           }
         }
       };
@@ -332,10 +354,12 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           if (c0 + j >= ncols) break;
-          float x = v[j] * TF32_TRUNC_DEBIAS;
+          float x = v[j] * debias;
           if (g.act == ACT_RELU) x = (av[j] > 0.f) ? x : 0.f;
           else if (g.act == ACT_SOFTPLUS) x *= 1.0f - __expf(-av[j]);
-          g.C[(size_t)(n0 + c0 + j) * g.ldc + f] = (g.rnd & 1) ? rna_tf32(x) : x;
+          float* const pc = g.C + (size_t)(n0 + c0 + j) * g.ldc + f;
+          if (om.mode == 2 && (g.rnd & 1)) put_grad16(om.hbase + (pc - om.fbase), x, om);    // operand only: 16-bit copy, loss-scaled like acc
+          else *pc = (g.rnd & 1) ? rna_tf32(x) : x;
         }
       };
       // The h values do not depend on the accumulator either: whole 16-row chunks of them are loaded while the mainloop
@@ -428,11 +452,20 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
             for (int i = 0; i < 4; ++i) {
               const int r = r0 + i;
               if (r >= NE) break;
-              float x = v[4 * q + i] * TF32_TRUNC_DEBIAS;
+              float x = v[4 * q + i] * debias;
               if (g.act == ACT_RELU) x = fmaxf(x, 0.f);
               else if (g.act == ACT_SOFTPLUS) x = softplusf(x);
-              if (g.C) g.C[(size_t)r * g.ldc + f] = (g.rnd & 1) ? rna_tf32(x) : x;
-              if (g.C2) { const float y = x + g.sigma * nz[i]; g.C2[(size_t)r * g.ldc2 + f] = (g.rnd & 2) ? rna_tf32(y) : y; }
+              if (g.C) {            // clean activation: kept in fp32 (act' of the backward pass, feature matching) ...
+                float* const pc = g.C + (size_t)r * g.ldc + f;
+                *pc = ((g.rnd & 1) && om.mode == 1) ? rna_tf32(x) : x;
+                if (om.mode == 2 && (g.rnd & 1)) om.hbase[pc - om.fbase] = __float2half_rn(x);     // ... plus its operand copy
+              }
+              if (g.C2) {           // noisy activation: only ever a GEMM operand
+                const float y = x + g.sigma * nz[i];
+                float* const pc2 = g.C2 + (size_t)r * g.ldc2 + f;
+                if (om.mode == 2 && (g.rnd & 2)) om.hbase[pc2 - om.fbase] = __float2half_rn(y);
+                else *pc2 = (g.rnd & 2) ? rna_tf32(y) : y;
+              }
             }
           }
         } else {   // EPI_STORE: dW into the flat gradient buffer (data-parallel mode: all-reduced before Adam)
@@ -490,6 +523,11 @@ struct alignas(64) TcAdamOp {
   int ME, NE, KE;                  // out-features n, in-features(+1) k, contraction rows r
   int fold;
   int net;
+  int esz;                         // operand element size (4 = tf32, 2 = fp16 copies)
+  int afmt;                        // esz == 2: format of the dZ operand (0 = f16, 1 = bf16); the activation operand is f16
+  int ldh;                         // pitch of W and of its fp16 operand copy
+  float ginv;                      // 1 / loss scale carried by the dZ operand (1 unless fp16)
+  __half* Ph;                      // fp16 operand copy of W, refreshed with every update (null unless fp16)
 };
 
 #define TCA_KC 8
@@ -538,7 +576,9 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
   auto buf_ptr = [&](int b) -> uint8_t* { return b < NB ? cbuf + (size_t)b * CHUNK_BYTES : smem + (size_t)(b - NB) * CHUNK_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (KE + TC_KBLK - 1) / TC_KBLK;
+  const bool f16 = op.esz == 2;                 // see k_gemm_tc: 64 contraction rows per stage, 8 KB MN-major boxes
+  const int kblk = f16 ? 64 : TC_KBLK;
+  const int nkb = (KE + kblk - 1) / kblk;
   const int ncols = min(128, NE - n0);
   const int nch = (ncols + KC - 1) / KC;
 
@@ -578,11 +618,10 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
         mbar_expect_tx(&full[s], STAGE_BYTES);
         uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
         uint8_t* sb = sa + 128 * 128;
-        const int k0 = kb * TC_KBLK;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * 4096, m0 + 32 * b, k0);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * 4096, n0 + 32 * b, k0);
+        const int k0 = kb * kblk;
+        const int bbytes = f16 ? 8192 : 4096;
+        for (int b = 0; b < 128 / kblk; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * bbytes, m0 + kblk * b, k0);
+        for (int b = 0; b < 128 / kblk; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * bbytes, n0 + kblk * b, k0);
       }
       // the MMAs have consumed every operand stage once the accumulator is complete: the operand region now takes
       // NX more chunks in flight
@@ -607,7 +646,9 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t fmtA = f16 ? (uint32_t)op.afmt : 2u, fmtB = f16 ? 0u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmtA << 7) | (fmtB << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t lbo = f16 ? 8192u : 4096u, sbo = f16 ? 1024u : 512u, lay = f16 ? 2u : 1u, kstep = f16 ? 2048u : 1024u;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -615,9 +656,11 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
         fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES), sb = sa + 128 * 128;
 #pragma unroll
-        for (int k = 0; k < TC_KBLK / 8; ++k)
-          mma_tf32(tmem_base, smem_desc(sa + k * 1024u, 4096u, 512u, 1u), smem_desc(sb + k * 1024u, 4096u, 512u, 1u), idesc,
-                   (kb > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = smem_desc(sa + k * kstep, lbo, sbo, lay), db = smem_desc(sb + k * kstep, lbo, sbo, lay);
+          if (f16) mma_f16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          else mma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
         mma_commit(&empty[s]);
       }
       mma_commit(tmem_full);
@@ -629,6 +672,10 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
     const uint32_t trow = tmem_base + ((uint32_t)lane_base << 16);
     const float lr_t = folds[op.fold].lr_t[op.net];
     const float b1 = hp.b1, b2 = hp.b2, c1 = 1.0f - hp.b1, c2 = 1.0f - hp.b2, eps = hp.eps;
+    const float ginv = op.ginv;
+    __half* const Ph = op.Ph;
+    const int ldh = op.ldh;
+    const bool n_ok = m0 + nl < ME;
     mbar_wait(tmem_full, 0);
     fence_after();
     for (int c = 0; c < nch; ++c) {
@@ -642,9 +689,14 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
 #pragma unroll
       for (int j = 0; j < KC; ++j) {
         const int i = j * 128 + nl;
-        const float m = fmaf(b1, sM[i], c1 * g[j]), v = fmaf(b2, sV[i], c2 * g[j] * g[j]);
+        const float gr = g[j] * ginv;
+        const float m = fmaf(b1, sM[i], c1 * gr), v = fmaf(b2, sV[i], c2 * gr * gr);
         sM[i] = m; sV[i] = v;
-        sP[i] -= lr_t * __fdividef(m, sqrtf(v) + eps);
+        const float w = sP[i] - lr_t * __fdividef(m, sqrtf(v) + eps);
+        sP[i] = w;
+        // fp16 operand copy of the updated weights for the next forward / dX (2 more bytes per parameter; a warp writes
+        // 64 contiguous bytes per row).  The TMA store of the fp32 tile clips at the tensor's extents; this store must too.
+        if (Ph && n_ok && c * KC + j < ncols) Ph[(size_t)(n0 + c * KC + j) * ldh + m0 + nl] = __float2half_rn(w);
       }
       fence_proxy_async();              // generic-proxy writes -> visible to the bulk store
       mbar_arrive(&cdone[b]);

@@ -2,6 +2,7 @@
 // declared in include/mrgan.h.  Reference interface replaced: the K.function callables of
 // mr_gan.py:169-171, the epoch loop mr_gan.py:183-230 and mr_nn.py:114-118.
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
@@ -73,7 +74,7 @@ int tc_setup(mrgan_handle* h);
 void tc_teardown(mrgan_handle* h);
 bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override, cudaStream_t st);
 void tc_params_changed(mrgan_handle* h, int fold, int net);
-int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g);
+int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g, int esz);
 }
 #endif
 
@@ -95,6 +96,8 @@ struct mrgan_handle {
   int nchains = 1;
   cudaStream_t cmain[kMaxChains] = {nullptr}, cside[kMaxChains] = {nullptr};
   char* arena = nullptr; size_t arena_bytes = 0;
+  __half* harena = nullptr;           // f16 mode: one __half per float of the arena (operand copies at the same element index)
+  OperandMode om = {0, 1.0f, nullptr, nullptr, 0};
   float *P = nullptr, *Mo = nullptr, *Vo = nullptr, *Gr = nullptr; long long n_flat = 0;
   FoldState* d_folds = nullptr; std::vector<FoldState> h_folds;
   GemmDesc* d_descs = nullptr; std::vector<GemmDesc> h_descs;
@@ -156,7 +159,7 @@ NetLayout layout_disc(int D, int K) {
   NetLayout L;
   int dims[7] = {D, kDW[0], kDW[1], kDW[2], kDW[3], kDW[4], K};
   for (int l = 0; l < 6; ++l) {
-    TensorLayout t{dims[l] + 1, dims[l + 1], pitch4(dims[l + 1]), L.n};
+    TensorLayout t{dims[l] + 1, dims[l + 1], pitch8(dims[l + 1]), L.n};
     L.t.push_back(t);
     L.n = align32(L.n + (long long)t.rows * t.pitch);
     L.n_ref += (long long)(dims[l] + 1) * dims[l + 1];
@@ -167,7 +170,7 @@ NetLayout layout_disc(int D, int K) {
 NetLayout layout_gen(int D, int nd) {
   NetLayout L;
   auto add = [&](int rows, int cols) {
-    TensorLayout t{rows, cols, pitch4(cols), L.n};
+    TensorLayout t{rows, cols, pitch8(cols), L.n};
     L.t.push_back(t);
     L.n = align32(L.n + (long long)rows * t.pitch);
     L.n_ref += (long long)rows * cols;
@@ -184,9 +187,24 @@ __global__ void k_round_tf32(float* p, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = rna_tf32(p[i]);
 }
 
-__global__ void k_set_col(float* p, int ld, int rows, int col, float v) {
+__global__ void k_set_col(float* p, int ld, int rows, int col, float v, OperandMode om) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < rows) p[(size_t)r * ld + col] = v;
+  if (r < rows) {
+    p[(size_t)r * ld + col] = v;
+    if (om.mode == 2) om.hbase[p + (size_t)r * ld + col - om.fbase] = __float2half_rn(v);
+  }
+}
+
+__global__ void k_scale_buf(float* p, size_t n, float mul) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] *= mul;
+}
+
+// f16 mode, test hook: operand-only buffers exist as fp16 copies only; expand one (times `mul`) into a float scratch
+__global__ void k_from_half(const float* src, float* dst, size_t n, float mul, OperandMode om, int bf16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const __half* p = om.hbase + (src + i - om.fbase);
+    dst[i] = (bf16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p)) : __half2float(*p)) * mul;
+  }
 }
 
 // ---- buffer layout (run twice: sizing pass with base == nullptr, then for real) ----
@@ -211,9 +229,9 @@ void layout_buffers(mrgan_handle* h, Arena& ar) {
   for (int f = 0; f < nf; ++f) {
     FoldBuffers& b = h->fb[f];
     const int D = h->shapes[f].D, ntr = h->shapes[f].n_train, nte = h->shapes[f].n_test;
-    const int ldx = pitch4(D);
+    const int ldx = pitch8(D);
     int win[6] = {D, kDW[0], kDW[1], kDW[2], kDW[3], kDW[4]};
-    for (int l = 0; l < 6; ++l) { b.lda[l] = pitch4(win[l] + 1); b.ldz[l] = pitch4(win[l]); }
+    for (int l = 0; l < 6; ++l) { b.lda[l] = pitch8(win[l] + 1); b.ldz[l] = pitch8(win[l]); }
     b.a[0] = ar.take<float>((size_t)R * b.lda[0]);
     b.hb[0] = nullptr; b.dz[0] = nullptr;
     for (int l = 1; l <= 5; ++l) {
@@ -221,28 +239,29 @@ void layout_buffers(mrgan_handle* h, Arena& ar) {
       b.a[l] = (l < 5) ? ar.take<float>((size_t)R * b.lda[l]) : b.hb[l];
       b.dz[l] = ar.take<float>((size_t)R * b.ldz[l]);
     }
-    b.lg = ar.take<float>((size_t)R * pitch4(K));
-    b.dlg = ar.take<float>((size_t)R * pitch4(K));
+    b.lg = ar.take<float>((size_t)R * pitch8(K));
+    b.dlg = ar.take<float>((size_t)R * pitch8(K));
     b.labels_cur = ar.take<int>(R);
     b.stage_x = ar.take<float>((size_t)R * ldx);
     b.stage_y = ar.take<int>(R);
     if (gan) {
       b.dfake = ar.take<float>((size_t)B * ldx);
-      b.zb = ar.take<float>((size_t)B * pitch4(nd + 1));
-      b.h1g = ar.take<float>((size_t)B * kGH);
-      b.xhat = ar.take<float>((size_t)B * kGH);
+      b.zb = ar.take<float>((size_t)B * pitch8(nd + 1));
+      const int ldg = pitch8(kGH);
+      b.h1g = ar.take<float>((size_t)B * ldg);
+      b.xhat = ar.take<float>((size_t)B * ldg);
       b.istd = ar.take<float>(kGH);
-      b.u = ar.take<float>((size_t)B * pitch4(kGH + 1));
-      b.h2g = ar.take<float>((size_t)B * pitch4(kGH + 1));
-      b.dz2g = ar.take<float>((size_t)B * kGH);
-      b.du = ar.take<float>((size_t)B * kGH);
-      b.dz1g = ar.take<float>((size_t)B * kGH);
+      b.u = ar.take<float>((size_t)B * pitch8(kGH + 1));
+      b.h2g = ar.take<float>((size_t)B * pitch8(kGH + 1));
+      b.dz2g = ar.take<float>((size_t)B * ldg);
+      b.du = ar.take<float>((size_t)B * ldg);
+      b.dz1g = ar.take<float>((size_t)B * ldg);
       b.stage_z = ar.take<float>((size_t)B * nd);
     }
     b.ex_stage = ar.take<float>((size_t)NE * b.lda[0]);
     b.xte = ar.take<float>((size_t)nte * b.lda[0]);
     for (int l = 1; l <= 5; ++l) b.eh[l] = ar.take<float>((size_t)NE * b.lda[l]);
-    b.elg = ar.take<float>((size_t)NE * pitch4(K));
+    b.elg = ar.take<float>((size_t)NE * pitch8(K));
     b.ey_stage = ar.take<int>(NE);
     b.eval_out = ar.take<float>(4);
     b.eval_out_s = ar.take<float>(4);
@@ -270,9 +289,9 @@ void build_descs(mrgan_handle* h) {
   h->h_folds.assign(nf, FoldState{});
   std::vector<BnDesc> bn(nf); std::vector<LossDesc> ls(nf); std::vector<EvalDesc> ev(nf), evs(nf);
   std::vector<AdamRange> rg0(nf), rg1(nf);
-  const bool tf32 = c.precision == MRGAN_PREC_TF32;
+  const bool tensor = c.precision != MRGAN_PREC_FP32;      // tf32 / f16: which outputs feed a tensor-core GEMM as operands
   auto setop = [&](int op, int f, GemmDesc d, bool at, bool bt, int rnd = 0) {
-    d.rnd = tf32 ? rnd : 0;
+    d.rnd = tensor ? rnd : 0;
     h->h_descs[(size_t)op * nf + f] = d;
     OpInfo& oi = h->ops[op];
     oi.at = at; oi.bt = bt; oi.used = true;
@@ -291,7 +310,7 @@ void build_descs(mrgan_handle* h) {
     for (int l = 1; l <= 6; ++l) {
       const TensorLayout& W = LD.t[l - 1];
       float* C = (l <= 5) ? b.hb[l] : b.lg;
-      const int ldc = (l <= 5) ? b.lda[l] : pitch4(K);
+      const int ldc = (l <= 5) ? b.lda[l] : pitch8(K);
       GemmDesc d = make_desc(b.a[l - 1], b.lda[l - 1], PD + W.off, W.pitch, C, ldc, R, wout[l - 1], win[l - 1] + 1,
                              EPI_FWD, l <= 5 ? ACT_RELU : ACT_NONE, f);
       if (l <= 4) { d.C2 = b.a[l]; d.ldc2 = b.lda[l]; d.sigma = sig[l]; d.tid = l; d.row0 = 0; }
@@ -306,7 +325,7 @@ void build_descs(mrgan_handle* h) {
       if (l == 1) { e.A = b.ex_stage; setop(OP_E1S, f, e, false, false, 1); }
       // dW (+db): grad(Waug_l) = a[l-1]^T @ dZ[l]
       const float* dZ = (l <= 5) ? b.dz[l] : b.dlg;
-      const int lddz = (l <= 5) ? b.ldz[l] : pitch4(K);
+      const int lddz = (l <= 5) ? b.ldz[l] : pitch8(K);
       GemmDesc w = make_desc(b.a[l - 1], b.lda[l - 1], dZ, lddz, GD + W.off, W.pitch, win[l - 1] + 1, wout[l - 1], R,
                              EPI_STORE, ACT_NONE, f);
       setop(OP_DW1 + l - 1, f, w, true, false);
@@ -320,15 +339,15 @@ void build_descs(mrgan_handle* h) {
       }
     }
     rg0[f] = AdamRange{LD.off, LD.n};
-    ls[f] = LossDesc{b.lg, b.dlg, pitch4(K), b.labels_cur, b.hb[5], b.dz[5], b.lda[5], b.ldz[5], kDW[4]};
-    ev[f] = EvalDesc{b.elg, pitch4(K), b.yte, h->shapes[f].n_test, (h->shapes[f].n_test / B) * B, b.eval_out};
-    evs[f] = EvalDesc{b.elg, pitch4(K), b.ey_stage, h->shapes[f].n_test, 0, b.eval_out_s};
+    ls[f] = LossDesc{b.lg, b.dlg, pitch8(K), b.labels_cur, b.hb[5], b.dz[5], b.lda[5], b.ldz[5], kDW[4]};
+    ev[f] = EvalDesc{b.elg, pitch8(K), b.yte, h->shapes[f].n_test, (h->shapes[f].n_test / B) * B, b.eval_out};
+    evs[f] = EvalDesc{b.elg, pitch8(K), b.ey_stage, h->shapes[f].n_test, 0, b.eval_out_s};
     if (gan) {
       const NetLayout& LG = h->net[1][f];
       float* PG = h->P + LG.off; float* GG = h->Gr + LG.off;
       const TensorLayout &W1 = LG.t[0], &Tg = LG.t[1], &Tb = LG.t[2], &W2 = LG.t[3], &W3 = LG.t[4];
-      const int ldzb = pitch4(nd + 1), ldu = pitch4(kGH + 1), ldx = pitch4(D);
-      setop(OP_G1, f, make_desc(b.zb, ldzb, PG + W1.off, W1.pitch, b.h1g, kGH, B, kGH, nd + 1, EPI_FWD, ACT_SOFTPLUS, f), false, false);
+      const int ldzb = pitch8(nd + 1), ldu = pitch8(kGH + 1), ldx = pitch8(D), ldg = pitch8(kGH);
+      setop(OP_G1, f, make_desc(b.zb, ldzb, PG + W1.off, W1.pitch, b.h1g, ldg, B, kGH, nd + 1, EPI_FWD, ACT_SOFTPLUS, f), false, false);
       setop(OP_G2, f, make_desc(b.u, ldu, PG + W2.off, W2.pitch, b.h2g, ldu, B, kGH, kGH + 1, EPI_FWD, ACT_SOFTPLUS, f), false, false, 1);
       GemmDesc g3 = make_desc(b.h2g, ldu, PG + W3.off, W3.pitch, nullptr, 0, B, D, kGH + 1, EPI_FWD, ACT_NONE, f);
       g3.C2 = b.a[0] + (size_t)2 * B * b.lda[0]; g3.ldc2 = b.lda[0]; g3.sigma = c.sigma_in; g3.tid = 0; g3.row0 = 2 * B;
@@ -339,24 +358,24 @@ void build_descs(mrgan_handle* h) {
       const TensorLayout& DW1 = LD.t[0];
       setop(OP_DX1G, f, make_desc(b.dz[1], b.ldz[1], PD + DW1.off, DW1.pitch, b.dfake, ldx, B, D, kDW[0], EPI_DX, ACT_NONE, f), false, true, 1);
       setop(OP_GW3, f, make_desc(b.h2g, ldu, b.dfake, ldx, GG + W3.off, W3.pitch, kGH + 1, D, B, EPI_STORE, ACT_NONE, f), true, false);
-      GemmDesc gx3 = make_desc(b.dfake, ldx, PG + W3.off, W3.pitch, b.dz2g, kGH, B, kGH, D, EPI_DX, ACT_SOFTPLUS, f);
+      GemmDesc gx3 = make_desc(b.dfake, ldx, PG + W3.off, W3.pitch, b.dz2g, ldg, B, kGH, D, EPI_DX, ACT_SOFTPLUS, f);
       gx3.aux = b.h2g; gx3.ldaux = ldu;
       setop(OP_GX3, f, gx3, false, true, 1);
-      setop(OP_GW2, f, make_desc(b.u, ldu, b.dz2g, kGH, GG + W2.off, W2.pitch, kGH + 1, kGH, B, EPI_STORE, ACT_NONE, f), true, false);
-      setop(OP_GX2, f, make_desc(b.dz2g, kGH, PG + W2.off, W2.pitch, b.du, kGH, B, kGH, kGH, EPI_DX, ACT_NONE, f), false, true);
-      setop(OP_GW1, f, make_desc(b.zb, ldzb, b.dz1g, kGH, GG + W1.off, W1.pitch, nd + 1, kGH, B, EPI_STORE, ACT_NONE, f), true, false);
+      setop(OP_GW2, f, make_desc(b.u, ldu, b.dz2g, ldg, GG + W2.off, W2.pitch, kGH + 1, kGH, B, EPI_STORE, ACT_NONE, f), true, false);
+      setop(OP_GX2, f, make_desc(b.dz2g, ldg, PG + W2.off, W2.pitch, b.du, ldg, B, kGH, kGH, EPI_DX, ACT_NONE, f), false, true);
+      setop(OP_GW1, f, make_desc(b.zb, ldzb, b.dz1g, ldg, GG + W1.off, W1.pitch, nd + 1, kGH, B, EPI_STORE, ACT_NONE, f), true, false);
       bn[f] = BnDesc{b.h1g, b.xhat, b.u, b.istd, PG + Tg.off, PG + Tb.off, b.du, b.dz1g, GG + Tg.off, GG + Tb.off,
-                     kGH, ldu, B, kGH};
+                     ldg, ldu, B, kGH};
       rg1[f] = AdamRange{LG.off, LG.n};
     }
     FoldState& fs = h->h_folds[f];
     fs.key0 = (uint32_t)(h->shapes[f].seed & 0xFFFFFFFFull);
     fs.key1 = (uint32_t)(h->shapes[f].seed >> 32);
-    fs.D = D; fs.n_train = h->shapes[f].n_train; fs.n_test = h->shapes[f].n_test; fs.ldx = pitch4(D);
+    fs.D = D; fs.n_train = h->shapes[f].n_train; fs.n_test = h->shapes[f].n_test; fs.ldx = pitch8(D);
     fs.x_train = b.xtr; fs.y_train = b.ytr; fs.y_test = b.yte;
     for (int s = 0; s < 3; ++s) fs.idx[s] = b.idx + (size_t)s * h->shapes[f].n_train;
     fs.stage_x = b.stage_x; fs.stage_y = b.stage_y; fs.stage_z = gan ? b.stage_z : nullptr;
-    fs.a0 = b.a[0]; fs.lda0 = b.lda[0]; fs.z = gan ? b.zb : nullptr; fs.ldz = pitch4(nd + 1);
+    fs.a0 = b.a[0]; fs.lda0 = b.lda[0]; fs.z = gan ? b.zb : nullptr; fs.ldz = pitch8(nd + 1);
     fs.labels_cur = b.labels_cur;
   }
   cudaMemcpy(h->d_descs, h->h_descs.data(), h->h_descs.size() * sizeof(GemmDesc), cudaMemcpyHostToDevice);
@@ -372,7 +391,7 @@ void build_descs(mrgan_handle* h) {
 }
 
 void set_ones(mrgan_handle* h, float* p, int ld, int rows, int col) {
-  k_set_col<<<(rows + 127) / 128, 128, 0, h->stream>>>(p, ld, rows, col, 1.0f);
+  k_set_col<<<(rows + 127) / 128, 128, 0, h->stream>>>(p, ld, rows, col, 1.0f, h->om);
 }
 
 void init_ones(mrgan_handle* h) {
@@ -391,9 +410,9 @@ void init_ones(mrgan_handle* h) {
       set_ones(h, b.eh[l], b.lda[l], h->NE, win[l]);
     }
     if (gan) {
-      set_ones(h, b.zb, pitch4(c.noise_dim + 1), c.batch, c.noise_dim);
-      set_ones(h, b.u, pitch4(kGH + 1), c.batch, kGH);
-      set_ones(h, b.h2g, pitch4(kGH + 1), c.batch, kGH);
+      set_ones(h, b.zb, pitch8(c.noise_dim + 1), c.batch, c.noise_dim);
+      set_ones(h, b.u, pitch8(kGH + 1), c.batch, kGH);
+      set_ones(h, b.h2g, pitch8(kGH + 1), c.batch, kGH);
     }
   }
 }
@@ -479,7 +498,7 @@ void launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override, cu
   if (rows_override > 0 && !oi.at) M = rows_override;
   const GemmDesc* d = h->d_descs + (size_t)op * h->nf + f0;
 #ifdef MRGAN_WITH_TC
-  if (h->cfg.precision == MRGAN_PREC_TF32 && tc_launch_gemm(h, op, f0, nfl, rows_override, st)) return;
+  if (h->cfg.precision != MRGAN_PREC_FP32 && tc_launch_gemm(h, op, f0, nfl, rows_override, st)) return;
 #endif
   dim3 grid((oi.maxN + 63) / 64, (M + 63) / 64, nfl);
   if (!oi.at && !oi.bt) launch_k(h, k_gemm_simt<false, false>, grid, dim3(256), 0, st, d, (const FoldState*)h->d_folds, rows_override, h->hp);
@@ -515,7 +534,7 @@ void launch_prep(mrgan_handle* h, int f0, int nfl, int mode, int from_stage, int
   if (c.noise_dim > cols) cols = c.noise_dim;
   dim3 grid((cols + 127) / 128, (nrows + 3) / 4, nfl);
   launch_k(h, k_prep, grid, dim3(128), 0, h->stream, h->d_folds, f0, mode, from_stage, t, c.batch, nrows, c.noise_dim, c.sigma_in, h->hp,
-           (int)(c.precision == MRGAN_PREC_TF32));
+           h->om);
 }
 
 void launch_adam(mrgan_handle* h, int f0, int nfl, int net) {
@@ -526,9 +545,13 @@ void launch_adam(mrgan_handle* h, int f0, int nfl, int net) {
   if (blocks < 1) blocks = 1;
   const AdamRange* ranges = h->d_ranges[net];
 #ifdef MRGAN_WITH_TC
-  if (h->cfg.precision == MRGAN_PREC_TF32 && h->tc_fused_adam) { ranges = h->d_ranges_tc[net]; blocks = 1; }
+  if (h->cfg.precision != MRGAN_PREC_FP32 && h->tc_fused_adam) { ranges = h->d_ranges_tc[net]; blocks = 1; }
 #endif
-  launch_k(h, k_adam, dim3(blocks, nfl), dim3(256), 0, h->stream, h->P, h->Mo, h->Vo, (const float*)h->Gr, ranges, h->d_folds, f0, net, h->hp);
+  // f16 mode: the gradient buffer carries the loss scale, and every parameter update refreshes the fp16 operand copy
+  const float ginv = h->om.mode == 2 ? 1.0f / h->om.gscale : 1.0f;
+  __half* Ph = h->om.mode == 2 ? h->harena + (h->P - reinterpret_cast<float*>(h->arena)) : nullptr;
+  launch_k(h, k_adam, dim3(blocks, nfl), dim3(256), 0, h->stream, h->P, h->Mo, h->Vo, (const float*)h->Gr, ranges, h->d_folds, f0, net, h->hp,
+           ginv, Ph);
 }
 
 // The side stream's dW kernels read the step's activation buffers (a[l], dZ[l]), which the NEXT step's batch assembly
@@ -542,7 +565,7 @@ void enqueue_gen_fwd(mrgan_handle* h, int f0, int nfl, int op_g3) {
   launch_gemm(h, OP_G1, f0, nfl, 0);
   const dim3 bnf((kGH + BN_COLS - 1) / BN_COLS, 1, nfl);
   const dim3 bnt(h->cfg.batch > 256 ? 1024 : 256);     // 32 columns x 8 (reference batch) or 32 (large batch) row slices
-  const int tf32 = h->cfg.precision == MRGAN_PREC_TF32;
+  const OperandMode tf32 = h->om;
   if (h->d_dpbufs) {          // batch statistics over the GLOBAL batch: local sums -> NVLink all-reduce -> apply
     k_bn_stats<<<bnf, bnt, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0);
     dp_allreduce(h, h->dp_bnf + (size_t)f0 * 2 * kGH, (size_t)nfl * 2 * kGH);
@@ -563,7 +586,7 @@ void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) 
   enqueue_gen_fwd(h, f0, nfl, OP_G3D);
   for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 0);
   launch_k(h, k_loss_disc, dim3(1, 1, nfl), dim3(256), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, B,
-           c.n_classes, c.unlabeled_weight, (int)(c.precision == MRGAN_PREC_TF32), h->hp.dp_bg);
+           c.n_classes, c.unlabeled_weight, h->om, h->hp.dp_bg);
   for (int l = 6; l >= 1; --l) {      // dX first: it reads W_l, which the fused-Adam dW epilogue overwrites
     if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
     fork_side(h);                     // dW_l (+Adam) streams HBM on the side while main continues the dX chain
@@ -588,11 +611,11 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
     k_fm_stats<<<fmg, fmt, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, B);
     dp_allreduce(h, h->dp_fm + (size_t)f0 * 2 * kDW[4], (size_t)nfl * 2 * kDW[4]);
     k_fm_apply<<<fmg, fmt, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, h->d_step_stats, f0, h->nf, t, B,
-                                           c.precision == MRGAN_PREC_TF32, h->hp.dp_bg, h->dp_world);
+                                           h->om, h->hp.dp_bg, h->dp_world);
     h->launches += 2;
   } else {
     launch_k(h, k_fm, dim3(1, 1, nfl), dim3(1024), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, B,
-             (int)(c.precision == MRGAN_PREC_TF32));
+             h->om);
   }
   for (int l = 5; l >= 2; --l) launch_gemm(h, OP_DX2G + l - 2, f0, nfl, 0);
   launch_gemm(h, OP_DX1G, f0, nfl, 0);
@@ -604,12 +627,12 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   launch_gemm(h, OP_GW2, f0, nfl, 0, h->side);
   const dim3 bng((kGH + BN_COLS - 1) / BN_COLS, 1, nfl), bnt(B > 256 ? 1024 : 256);
   if (h->d_dpbufs) {
-    k_bn_bwd_stats<<<bng, bnt, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0);
+    k_bn_bwd_stats<<<bng, bnt, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, h->om);
     dp_allreduce(h, h->dp_bnb + (size_t)f0 * 2 * kGH, (size_t)nfl * 2 * kGH);
-    k_bn_bwd_apply<<<bng, bnt, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, c.precision == MRGAN_PREC_TF32, h->hp.dp_bg);
+    k_bn_bwd_apply<<<bng, bnt, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, h->om, h->hp.dp_bg);
     h->launches += 2;
   } else {
-    launch_k(h, k_bn_bwd, bng, bnt, 0, h->stream, (const BnDesc*)(h->d_bn + f0), (int)(c.precision == MRGAN_PREC_TF32));
+    launch_k(h, k_bn_bwd, bng, bnt, 0, h->stream, (const BnDesc*)(h->d_bn + f0), h->om);
   }
   fork_side(h);
   launch_gemm(h, OP_GW1, f0, nfl, 0, h->side);
@@ -627,7 +650,7 @@ void enqueue_nn_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage, in
   launch_prep(h, f0, nfl, 2, from_stage, t, n);
   for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 0);
   launch_k(h, k_loss_mse, dim3(1, 1, nfl), dim3(256), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, n, h->R,
-           c.n_classes, (int)(c.precision == MRGAN_PREC_TF32));
+           c.n_classes, h->om);
   for (int l = 6; l >= 1; --l) {
     if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
     fork_side(h);
@@ -772,15 +795,21 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 // k-blocks touch the adjacent 128 bytes of the same DRAM page; fetching 256 B per miss halves the DRAM activations.
 CUtensorMapL2promotion g_l2_promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
 
-bool make_map(EncodeTiledFn fn, CUtensorMap* m, const float* base, int cols, int rows, int pitch, int box_rows,
-              bool mn_major, int box_cols = 32) {
+// esz = 4: fp32 elements (read as tf32); esz = 2: fp16 elements (`base` then points at __half data, pitch in elements).
+// The swizzled box is always one 128-byte row wide (32 fp32 / 64 fp16 elements); MN-major 32-bit operands need the
+// 32-byte-atom variant of the 128B swizzle, 16-bit ones the plain 128B swizzle.
+bool make_map(EncodeTiledFn fn, CUtensorMap* m, const void* base, int cols, int rows, int pitch, int box_rows,
+              bool mn_major, int box_cols = 0, int esz = 4) {
+  const int row_elems = 128 / esz;
+  if (box_cols == 0) box_cols = row_elems;
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)pitch * sizeof(float)};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * (cuuint64_t)esz};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1u, 1u};
-  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, es,
-            CU_TENSOR_MAP_INTERLEAVE_NONE,
-            box_cols != 32 ? CU_TENSOR_MAP_SWIZZLE_NONE : (mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
+  return fn(m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+            strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            box_cols != row_elems ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                  : ((mn_major && esz == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
             g_l2_promo,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -835,37 +864,40 @@ void tc_set_smem_attr() {
 }
 
 // fills the tcgen05 view of one GEMM (shapes in the fp32 path's convention); mode 0 fwd, 1 dX, 2 dW
-bool tc_fill_op(EncodeTiledFn fn, TcOp& t, const GemmDesc& g, int mode) {
+// esz = 2: g.A / g.B point at fp16 operand copies (pitches in elements); the epilogue side of g is unchanged.
+bool tc_fill_op(EncodeTiledFn fn, TcOp& t, const GemmDesc& g, int mode, int esz = 4) {
   t.g = g;
+  t.esz = esz;
   t.ME = g.N; t.NE = g.M; t.KE = g.K;
+  const int kb = 128 / esz;   // contraction rows of an MN-major box = elements of one 128-byte row
   if (mode == 0) {            // forward: C[M rows, N feats] = act[M, K] @ W[K, N]
     t.epi = EPI_FWD;
     t.bn = g.M <= 256 ? round_up(g.M, 16) : 256;
-    return make_map(fn, &t.mapA, g.B, g.N, g.K, g.ldb, 32, true) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false);
+    return make_map(fn, &t.mapA, g.B, g.N, g.K, g.ldb, kb, true, 0, esz) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false, 0, esz);
   }
   if (mode == 1) {            // dX: C[M rows, N in-feats] = dZ[M, K] @ W[N, K]^T
     t.epi = EPI_DX;
     t.bn = g.M <= 256 ? round_up(g.M, 16) : 256;
-    return make_map(fn, &t.mapA, g.B, g.K, g.N, g.ldb, 128, false) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false);
+    return make_map(fn, &t.mapA, g.B, g.K, g.N, g.ldb, 128, false, 0, esz) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false, 0, esz);
   }
   t.epi = EPI_STORE;          // dW: C[M in-feats(+1), N out-feats] = act[K rows, M]^T @ dZ[K rows, N]
   t.bn = g.K > 512 ? 256 : 128;   // a long contraction (large batch) is a regular big GEMM: 256 x 256 tiles
-  return make_map(fn, &t.mapA, g.B, g.N, g.K, g.ldb, 32, true) && make_map(fn, &t.mapB, g.A, g.M, g.K, g.lda, 32, true);
+  return make_map(fn, &t.mapA, g.B, g.N, g.K, g.ldb, kb, true, 0, esz) && make_map(fn, &t.mapB, g.A, g.M, g.K, g.lda, kb, true, 0, esz);
 }
 
-int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g) {
+int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g, int esz) {
   EncodeTiledFn fn = tc_encoder();
   if (!fn) return fail(h, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   TcOp t; memset(&t, 0, sizeof(t));
-  if (!tc_fill_op(fn, t, g, mode)) return fail(h, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  if (!tc_fill_op(fn, t, g, mode, esz)) return fail(h, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   TcOp* d = nullptr;
   CK(cudaMalloc(&d, sizeof(TcOp)));
   CK(cudaMemcpyAsync(d, &t, sizeof(t), cudaMemcpyHostToDevice, h->stream));
   tc_set_smem_attr();
   dim3 grid((t.ME + 127) / 128, (t.NE + t.bn - 1) / t.bn, 1);
-  if (mode == 0) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp);
-  else if (mode == 1) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp);
-  else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp);
+  if (mode == 0) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
+  else if (mode == 1) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
+  else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
   h->launches++;
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(d);
@@ -889,7 +921,16 @@ int tc_setup(mrgan_handle* h) {
       const GemmDesc& g = h->h_descs[(size_t)op * nf + f];
       TcOp& t = ops[(size_t)op * nf + f];
       const int mode = (!oi.at && !oi.bt) ? 0 : ((!oi.at && oi.bt) ? 1 : 2);
-      if (!tc_fill_op(fn, t, g, mode)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+      if (h->om.mode == 2) {    // operands come from the fp16 copies (same element offsets and pitches as the fp32 buffers)
+        GemmDesc gh = g;
+        gh.A = reinterpret_cast<const float*>(h->harena + (g.A - h->om.fbase));
+        gh.B = reinterpret_cast<const float*>(h->harena + (g.B - h->om.fbase));
+        if (!tc_fill_op(fn, t, gh, mode, 2)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled (fp16 operands) failed");
+        t.g = g;                // the epilogue keeps addressing the fp32 buffers (and derives the copies' addresses itself)
+        // which operand is gradient-side: dX contracts dZ (MMA-B) with W, dW contracts dZ^T (MMA-A) with the activations
+        t.afmt = (mode == 2) ? h->om.grad_bf16 : 0;
+        t.bfmt = (mode == 1) ? h->om.grad_bf16 : 0;
+      } else if (!tc_fill_op(fn, t, g, mode)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
       t.net = (op == OP_GW1 || op == OP_GW2 || op == OP_GW3) ? 1 : 0;
       if (mode == 2) {
         if (h->tc_fused_adam) t.epi = EPI_ADAM;
@@ -908,7 +949,8 @@ int tc_setup(mrgan_handle* h) {
     for (int op = 0; op < NUM_OPS; ++op) {
       const OpInfo& oi = h->ops[op];
       if (!oi.used || !oi.at || h->tc_bn[op] != 256) continue;
-      const int nkb = (ops[(size_t)op * nf].KE + TC_KBLK - 1) / TC_KBLK;
+      const int kblk = h->om.mode == 2 ? 64 : TC_KBLK;      // contraction rows per stage (one 128-byte row of operand elements)
+      const int nkb = (ops[(size_t)op * nf].KE + kblk - 1) / kblk;
       const int tiles = ((h->tc_maxME[op] + 255) / 256) * ((h->tc_maxNE[op] + 255) / 256) * nf;
       int ks = std::min(std::min(2 * 148 / tiles, nkb / 8), 32);
       if (ks < 2) continue;
@@ -945,6 +987,9 @@ int tc_setup(mrgan_handle* h) {
         const TcOp& t = ops[(size_t)op * nf + f];
         TcAdamOp& a = aops[(size_t)op * nf + f];
         a.mapA = t.mapA; a.mapB = t.mapB; a.ME = t.ME; a.NE = t.NE; a.KE = t.KE; a.fold = t.g.fold; a.net = t.net;
+        a.esz = h->om.mode == 2 ? 2 : 4; a.ldh = t.g.ldc; a.afmt = t.afmt;
+        a.ginv = h->om.mode == 2 ? 1.0f / h->om.gscale : 1.0f;
+        a.Ph = h->om.mode == 2 ? h->harena + (t.P - h->om.fbase) : nullptr;
         // W / m / v as [rows = in+1, cols = out] with the tensor's pitch; box 128 cols x KC rows, clipped at the logical extents
         if (!make_map(fn, &a.mapP, t.P, t.ME, t.NE, t.g.ldc, TCA_KC, false, 128) ||
             !make_map(fn, &a.mapM, t.Mo, t.ME, t.NE, t.g.ldc, TCA_KC, false, 128) ||
@@ -999,37 +1044,37 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
     if (oi.at) {
       const int ks = h->tc_ksplit[op] > 1 ? h->tc_ksplit[op] : 1;
       grid.z = nfl * ks;
-      launch_k(h, K_TC_DW_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, ks, h->hp);
+      launch_k(h, K_TC_DW_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, ks, h->hp, h->om);
       if (ks > 1) {
-        const int n4 = h->tc_maxNE[op] * pitch4(h->tc_maxME[op]) / 4;
+        const int n4 = h->tc_maxNE[op] * pitch8(h->tc_maxME[op]) / 4;
         launch_k(h, k_splitk_reduce, dim3(std::min((n4 + 255) / 256, 64), nfl, 1), dim3(256), 0, st, d, ks);
       }
-    } else if (!oi.bt) launch_k(h, K_TC_FWD_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp);
-    else launch_k(h, K_TC_DX_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp);
+    } else if (!oi.bt) launch_k(h, K_TC_FWD_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
+    else launch_k(h, K_TC_DX_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
     return true;
   }
   if (!oi.at && h->tc_mt2 && tc_use_mt2(h->tc_maxME[op], bn)) {
     grid.x = (h->tc_maxME[op] + 255) / 256;
     const size_t smem = tc_smem_bytes(bn, TC_FWD_STAGES, 2);
-    if (!oi.bt) launch_k(h, K_TC_FWD2, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp);
-    else launch_k(h, K_TC_DX2, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp);
+    if (!oi.bt) launch_k(h, K_TC_FWD2, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
+    else launch_k(h, K_TC_DX2, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
     return true;
   }
   if (!oi.at && !oi.bt) {
     // one CTA per SM anyway once the stages exceed half the shared memory: take the whole TMEM then (noise parking)
     if (2 * tc_smem_bytes(bn, TC_FWD_STAGES) > 227 * 1024)
-      launch_k(h, K_TC_FWD_N, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp);
+      launch_k(h, K_TC_FWD_N, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp, h->om);
     else
-      launch_k(h, K_TC_FWD, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp);
+      launch_k(h, K_TC_FWD, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp, h->om);
   }
   else if (!oi.at && oi.bt) {
     if (2 * tc_smem_bytes(bn, TC_FWD_STAGES) > 227 * 1024)
-      launch_k(h, K_TC_DX_N, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp);
+      launch_k(h, K_TC_DX_N, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp, h->om);
     else
-      launch_k(h, K_TC_DX, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp);
+      launch_k(h, K_TC_DX, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp, h->om);
   }
   else if (h->d_tcadam) launch_k(h, k_dw_adam_tc, grid, dim3(192), (size_t)TCA_SMEM_BYTES, st, (const TcAdamOp*)(h->d_tcadam + (size_t)op * h->nf + f0), h->d_folds, h->hp);
-  else launch_k(h, K_TC_DW, grid, dim3(TC_DW_THREADS), tc_smem_bytes(bn, TC_DW_STAGES), st, d, h->d_folds, 0, h->hp);
+  else launch_k(h, K_TC_DW, grid, dim3(TC_DW_THREADS), tc_smem_bytes(bn, TC_DW_STAGES), st, d, h->d_folds, 0, h->hp, h->om);
   return true;
 }
 
@@ -1081,8 +1126,9 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major < 10)
     return fail(nullptr, MRGAN_ERR_NO_DEVICE, "device is not sm_100 (Blackwell): this library has no CPU fallback");
+  if (cfg->precision < MRGAN_PREC_FP32 || cfg->precision > MRGAN_PREC_F16) return fail(nullptr, MRGAN_ERR_ARG, "bad config (precision)");
 #ifndef MRGAN_WITH_TC
-  if (cfg->precision == MRGAN_PREC_TF32) return fail(nullptr, MRGAN_ERR_ARG, "library built without the tcgen05 kernels");
+  if (cfg->precision != MRGAN_PREC_FP32) return fail(nullptr, MRGAN_ERR_ARG, "library built without the tcgen05 kernels");
 #endif
   h = new mrgan_handle();
   h->cfg = *cfg;
@@ -1119,6 +1165,18 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   if (e != cudaSuccess) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e)));
   Arena real; real.base = h->arena;
   layout_buffers(h, real);
+  h->om = OperandMode{cfg->precision, 1.0f, reinterpret_cast<const float*>(h->arena), nullptr, 0};
+  if (cfg->precision == MRGAN_PREC_F16) {      // operand copies: one __half per float of the arena, zero like the arena
+    e = cudaMalloc(&h->harena, h->arena_bytes / 2);
+    if (e == cudaSuccess) e = cudaMemset(h->harena, 0, h->arena_bytes / 2);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, std::string("cudaMalloc fp16 operand arena: ") + cudaGetErrorString(e)));
+    h->om.hbase = h->harena;
+    h->om.gscale = MRGAN_F16_LOSS_SCALE;
+    if (const char* gb = getenv("MRGAN_GRAD_BF16")) {      // gradient-side operands as unscaled bf16 instead of loss-scaled fp16
+      if (atoi(gb) != 0) { h->om.grad_bf16 = 1; h->om.gscale = 1.0f; }
+    }
+  }
   bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess;
   for (int i = 0; i < 16 && ok; ++i) ok = cudaEventCreateWithFlags(&h->ev_pool[i], cudaEventDisableTiming) == cudaSuccess;
@@ -1156,7 +1214,7 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
     if (rc != MRGAN_OK) return cleanup(rc);
   }
 #ifdef MRGAN_WITH_TC
-  if (cfg->precision == MRGAN_PREC_TF32) {
+  if (cfg->precision != MRGAN_PREC_FP32) {
     int rc = tc_setup(h);
     if (rc != MRGAN_OK) return cleanup(rc);
   }
@@ -1183,6 +1241,7 @@ int mrgan_destroy(mrgan_handle* h) {
   tc_teardown(h);
 #endif
   if (h->arena) cudaFree(h->arena);
+  if (h->harena) cudaFree(h->harena);
   if (h->h_epoch_stats) cudaFreeHost(h->h_epoch_stats);
   if (h->h_scratch) cudaFreeHost(h->h_scratch);
   for (int s = 0; s < 2; ++s) {
@@ -1223,9 +1282,13 @@ int mrgan_set_params(mrgan_handle* h, int fold, int net, const float* src, int64
   std::vector<float> buf((size_t)L.n, 0.f);
   pack_params(h, fold, net, src, buf, true, nullptr);
   CK(cudaMemcpyAsync(h->P + L.off, buf.data(), (size_t)L.n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  if (h->om.mode == 2) {      // refresh the fp16 operand copy of the uploaded weights
+    k_to_half<<<256, 256, 0, h->stream>>>(h->P + L.off, (size_t)L.n, h->om);
+    h->launches++;
+  }
   CK(cudaStreamSynchronize(h->stream));
 #ifdef MRGAN_WITH_TC
-  if (h->cfg.precision == MRGAN_PREC_TF32) tc_params_changed(h, fold, net);
+  if (h->cfg.precision != MRGAN_PREC_FP32) tc_params_changed(h, fold, net);
 #endif
   return MRGAN_OK;
 }
@@ -1282,12 +1345,15 @@ int mrgan_load_fold(mrgan_handle* h, int fold, const float* x_train, const int32
     if (y_test[i] < 0 || y_test[i] >= h->cfg.n_classes) return fail(h, MRGAN_ERR_ARG, "load_fold: y_test label out of range");
   FoldBuffers& b = h->fb[fold];
   const size_t w = (size_t)s.D * sizeof(float);
-  CK(cudaMemcpy2DAsync(b.xtr, (size_t)pitch4(s.D) * sizeof(float), x_train, w, w, s.n_train, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(b.xtr, (size_t)pitch8(s.D) * sizeof(float), x_train, w, w, s.n_train, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpy2DAsync(b.xte, (size_t)b.lda[0] * sizeof(float), x_test, w, w, s.n_test, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(b.ytr, y_train, (size_t)s.n_train * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(b.yte, y_test, (size_t)s.n_test * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (h->cfg.precision == MRGAN_PREC_TF32) {   // X_test feeds the first eval MMA directly: put it on the tf32 grid (RN) once
     k_round_tf32<<<256, 256, 0, h->stream>>>(b.xte, (size_t)s.n_test * b.lda[0]);
+    h->launches++;
+  } else if (h->om.mode == 2) {                // ... or make its fp16 operand copy (ones column included)
+    k_to_half<<<256, 256, 0, h->stream>>>(b.xte, (size_t)s.n_test * b.lda[0], h->om);
     h->launches++;
   }
   CK(cudaStreamSynchronize(h->stream));
@@ -1304,7 +1370,7 @@ int mrgan_load_dataset(mrgan_handle* h, int slot, const float* x, const int32_t*
   int rc = finish_pending(h); if (rc) return rc;
   mrgan_handle::Dataset& ds = h->datasets[slot];
   if (ds.x && (ds.n != n_rows || ds.D != D)) { cudaFree(ds.x); cudaFree(ds.y); ds.x = nullptr; ds.y = nullptr; }
-  ds.n = n_rows; ds.D = D; ds.ld = pitch4(D);
+  ds.n = n_rows; ds.D = D; ds.ld = pitch8(D);
   if (!ds.x) {       // a re-upload of the same shape reuses the buffers (cudaFree / cudaMalloc synchronise the device)
     CK(cudaMalloc(&ds.x, (size_t)n_rows * ds.ld * sizeof(float)));
     CK(cudaMalloc(&ds.y, (size_t)n_rows * sizeof(int)));
@@ -1345,9 +1411,9 @@ int mrgan_prepare_fold(mrgan_handle* h, int fold, int slot, const int32_t* train
   const int gx = (s.D + 127) / 128;
   k_col_stats<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows, s.n_train, s.D, h->d_prep_stats);
   k_scale_gather<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows, s.n_train, s.D, h->d_prep_stats, s.n_train,
-                                                     b.xtr, pitch4(s.D), ds.y, b.ytr, 0);
+                                                     b.xtr, pitch8(s.D), ds.y, b.ytr, OperandMode{0, 1.0f, nullptr, nullptr, 0});
   k_scale_gather<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows + s.n_train, s.n_test, s.D, h->d_prep_stats, s.n_train,
-                                                     b.xte, b.lda[0], ds.y, b.yte, h->cfg.precision == MRGAN_PREC_TF32);
+                                                     b.xte, b.lda[0], ds.y, b.yte, h->om);
   h->launches += 3;
   CK(cudaStreamSynchronize(h->stream));     // the pageable index arrays are borrowed only for the call
   CK(cudaGetLastError());
@@ -1366,9 +1432,9 @@ int mrgan_disc_step(mrgan_handle* h, int fold, const float* x_lab, const int32_t
   for (int i = 0; i < B; ++i)
     if (labels[i] < 0 || labels[i] >= h->cfg.n_classes) return fail(h, MRGAN_ERR_ARG, "disc_step: label out of range");
   FoldBuffers& b = h->fb[fold];
-  const size_t w = (size_t)D * sizeof(float), ld = (size_t)pitch4(D) * sizeof(float);
+  const size_t w = (size_t)D * sizeof(float), ld = (size_t)pitch8(D) * sizeof(float);
   CK(cudaMemcpy2DAsync(b.stage_x, ld, x_lab, w, w, B, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpy2DAsync(b.stage_x + (size_t)B * pitch4(D), ld, x_unl, w, w, B, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(b.stage_x + (size_t)B * pitch8(D), ld, x_unl, w, w, B, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(b.stage_y, labels, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(b.stage_z, z, (size_t)B * nd * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   enqueue_disc_step(h, fold, 1, 0, 1);
@@ -1387,8 +1453,8 @@ int mrgan_gen_step(mrgan_handle* h, int fold, const float* x_unl, const float* z
   rc = finish_pending(h); if (rc) return rc;
   const int B = h->cfg.batch, D = h->shapes[fold].D, nd = h->cfg.noise_dim;
   FoldBuffers& b = h->fb[fold];
-  const size_t w = (size_t)D * sizeof(float), ld = (size_t)pitch4(D) * sizeof(float);
-  CK(cudaMemcpy2DAsync(b.stage_x + (size_t)B * pitch4(D), ld, x_unl, w, w, B, cudaMemcpyHostToDevice, h->stream));
+  const size_t w = (size_t)D * sizeof(float), ld = (size_t)pitch8(D) * sizeof(float);
+  CK(cudaMemcpy2DAsync(b.stage_x + (size_t)B * pitch8(D), ld, x_unl, w, w, B, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(b.stage_z, z, (size_t)B * nd * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   enqueue_gen_step(h, fold, 1, 0, 1);
   CK(cudaMemcpyAsync(h->h_scratch, h->d_step_stats + (size_t)fold * 4, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -1413,6 +1479,9 @@ int mrgan_test_batch(mrgan_handle* h, int fold, const float* x, const int32_t* y
   CK(cudaMemcpyAsync(b.ey_stage, y, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   if (h->cfg.precision == MRGAN_PREC_TF32) {
     k_round_tf32<<<64, 256, 0, h->stream>>>(b.ex_stage, (size_t)n * b.lda[0]);
+    h->launches++;
+  } else if (h->om.mode == 2) {
+    k_to_half<<<64, 256, 0, h->stream>>>(b.ex_stage, (size_t)n * b.lda[0], h->om);
     h->launches++;
   }
   enqueue_eval(h, fold, 1, true, n);
@@ -1498,7 +1567,7 @@ int mrnn_step(mrgan_handle* h, int fold, const float* x, const int32_t* labels, 
   FoldBuffers& b = h->fb[fold];
   const int D = h->shapes[fold].D;
   const size_t w = (size_t)D * sizeof(float);
-  CK(cudaMemcpy2DAsync(b.stage_x, (size_t)pitch4(D) * sizeof(float), x, w, w, n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(b.stage_x, (size_t)pitch8(D) * sizeof(float), x, w, w, n, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(b.stage_y, labels, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   enqueue_nn_step(h, fold, 1, 0, 1, n);
   CK(cudaMemcpyAsync(h->h_scratch, h->d_step_stats + (size_t)fold * 4, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -1644,6 +1713,7 @@ int mrgan_dp_init(mrgan_handle* h, int rank, int world, const void* id128) {
   if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
   if (world < 1 || rank < 0 || rank >= world || !id128) return fail(h, MRGAN_ERR_ARG, "dp_init: bad rank / world / id");
   if (h->cfg.model != MRGAN_MODEL_GAN) return fail(h, MRGAN_ERR_STATE, "dp_init: data-parallel mode is implemented for the GAN model");
+  if (h->cfg.precision == MRGAN_PREC_F16) return fail(h, MRGAN_ERR_STATE, "dp_init: the fp16 operand mode is single-GPU for now");
   if (h->dp_world > 1 || h->nccl_comm) return fail(h, MRGAN_ERR_STATE, "dp_init called twice");
   if (world == 1) return MRGAN_OK;
   if (h->cfg.batch % 4) return fail(h, MRGAN_ERR_ARG, "dp_init: the local batch must be a multiple of 4 (noise row groups)");
@@ -1657,7 +1727,7 @@ int mrgan_dp_init(mrgan_handle* h, int rank, int world, const void* id128) {
   h->dp_world = world; h->dp_rank = rank;
   h->hp.dp_bloc = h->cfg.batch; h->hp.dp_bg = h->cfg.batch * world; h->hp.dp_rank = rank;
 #ifdef MRGAN_WITH_TC
-  if (h->cfg.precision == MRGAN_PREC_TF32) {   // gradients must be all-reduced before Adam: dW stores them, k_adam applies
+  if (h->cfg.precision != MRGAN_PREC_FP32) {   // gradients must be all-reduced before Adam: dW stores them, k_adam applies
     tc_teardown(h);
     h->tc_fused_adam = false;
     rc = tc_setup(h); if (rc) return rc;
@@ -1681,22 +1751,41 @@ int mrgan_debug_buffer(mrgan_handle* h, int fold, int which, float* dst, int row
   if (which >= 0 && which <= 5) { src = b.a[which]; ld = b.lda[which]; }
   else if (which >= 11 && which <= 15) { src = b.hb[which - 10]; ld = b.lda[which - 10]; }
   else if (which >= 21 && which <= 25) { src = b.dz[which - 20]; ld = b.ldz[which - 20]; }
-  else if (which == 30) { src = b.lg; ld = pitch4(K); }
-  else if (which == 31) { src = b.dlg; ld = pitch4(K); }
-  else if (which == 50) { src = b.xtr; ld = pitch4(D); }
+  else if (which == 30) { src = b.lg; ld = pitch8(K); }
+  else if (which == 31) { src = b.dlg; ld = pitch8(K); }
+  else if (which == 50) { src = b.xtr; ld = pitch8(D); }
   else if (which == 51) { src = b.xte; ld = b.lda[0]; }
-  else if (gan && which == 32) { src = b.dfake; ld = pitch4(D); }
-  else if (gan && which == 40) { src = b.zb; ld = pitch4(nd + 1); }
-  else if (gan && which == 41) { src = b.h1g; ld = kGH; }
-  else if (gan && which == 42) { src = b.u; ld = pitch4(kGH + 1); }
-  else if (gan && which == 43) { src = b.h2g; ld = pitch4(kGH + 1); }
-  else if (gan && which == 44) { src = b.dz2g; ld = kGH; }
-  else if (gan && which == 45) { src = b.du; ld = kGH; }
-  else if (gan && which == 46) { src = b.dz1g; ld = kGH; }
+  else if (gan && which == 32) { src = b.dfake; ld = pitch8(D); }
+  else if (gan && which == 40) { src = b.zb; ld = pitch8(nd + 1); }
+  else if (gan && which == 41) { src = b.h1g; ld = pitch8(kGH); }
+  else if (gan && which == 42) { src = b.u; ld = pitch8(kGH + 1); }
+  else if (gan && which == 43) { src = b.h2g; ld = pitch8(kGH + 1); }
+  else if (gan && which == 44) { src = b.dz2g; ld = pitch8(kGH); }
+  else if (gan && which == 45) { src = b.du; ld = pitch8(kGH); }
+  else if (gan && which == 46) { src = b.dz1g; ld = pitch8(kGH); }
   if (!src || cols > ld) return fail(h, MRGAN_ERR_ARG, "debug_buffer: unknown buffer or too many columns");
-  CK(cudaMemcpy2DAsync(dst, (size_t)cols * sizeof(float), src, (size_t)ld * sizeof(float), (size_t)cols * sizeof(float), rows,
-                       cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  float* tmp = nullptr;
+  if (h->om.mode == 2) {
+    // f16 mode: noisy activations / inputs and every dZ exist only as fp16 operand copies (dZ times the loss scale)
+    const bool act_only = (which >= 0 && which <= 4) || which == 40 || which == 42;
+    const bool grad_only = (which >= 21 && which <= 25) || which == 31 || which == 32 || which == 44 || which == 46;
+    if (act_only || grad_only) {
+      CK(cudaMalloc(&tmp, (size_t)rows * ld * sizeof(float)));
+      k_from_half<<<256, 256, 0, h->stream>>>(src, tmp, (size_t)rows * ld, grad_only ? 1.0f / h->om.gscale : 1.0f, h->om,
+                                              grad_only && h->om.grad_bf16);
+      src = tmp;
+    } else if (which == 45) {   // du stays fp32 but carries the loss scale
+      CK(cudaMalloc(&tmp, (size_t)rows * ld * sizeof(float)));
+      CK(cudaMemcpyAsync(tmp, src, (size_t)rows * ld * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+      k_scale_buf<<<256, 256, 0, h->stream>>>(tmp, (size_t)rows * ld, 1.0f / h->om.gscale);
+      src = tmp;
+    }
+  }
+  cudaError_t ce = cudaMemcpy2DAsync(dst, (size_t)cols * sizeof(float), src, (size_t)ld * sizeof(float), (size_t)cols * sizeof(float), rows,
+                                     cudaMemcpyDeviceToHost, h->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+  if (tmp) cudaFree(tmp);
+  if (ce != cudaSuccess) return fail(h, MRGAN_ERR_CUDA, std::string("debug_buffer: ") + cudaGetErrorString(ce));
   return MRGAN_OK;
 }
 
@@ -1708,7 +1797,7 @@ int mrgan_debug_gemm(mrgan_handle* h, int mode, int M, int N, int K, const float
   // operand shapes (rows, cols) as stored
   const int ar = mode == 2 ? K : M, ac = mode == 2 ? M : K;
   const int br = mode == 1 ? N : K, bc = mode == 1 ? K : N;
-  const int lda = pitch4(ac), ldb = pitch4(bc), ldc = pitch4(N);
+  const int lda = pitch8(ac), ldb = pitch8(bc), ldc = pitch8(N);
   float *dA = nullptr, *dB = nullptr, *dC = nullptr; GemmDesc* dd = nullptr;
   CK(cudaMalloc(&dA, (size_t)ar * lda * 4)); CK(cudaMalloc(&dB, (size_t)br * ldb * 4)); CK(cudaMalloc(&dC, (size_t)M * ldc * 4));
   CK(cudaMalloc(&dd, sizeof(GemmDesc)));
@@ -1720,8 +1809,23 @@ int mrgan_debug_gemm(mrgan_handle* h, int mode, int M, int N, int K, const float
   CK(cudaMemcpyAsync(dd, &g, sizeof(g), cudaMemcpyHostToDevice, h->stream));
   bool done = false;
 #ifdef MRGAN_WITH_TC
-  if (use_tc) {
-    rc = tc_debug_gemm(h, mode, g);
+  __half *hA = nullptr, *hB = nullptr;
+  if (use_tc == 2) {          // fp16 operand copies (kind::f16): host conversion, pitch rounded to 8 elements (16-byte TMA strides)
+    const int lha = (ac + 7) & ~7, lhb = (bc + 7) & ~7;
+    std::vector<__half> ha((size_t)ar * lha, __float2half(0.f)), hb((size_t)br * lhb, __float2half(0.f));
+    for (int r = 0; r < ar; ++r) for (int c2 = 0; c2 < ac; ++c2) ha[(size_t)r * lha + c2] = __float2half_rn(A[(size_t)r * ac + c2]);
+    for (int r = 0; r < br; ++r) for (int c2 = 0; c2 < bc; ++c2) hb[(size_t)r * lhb + c2] = __float2half_rn(B[(size_t)r * bc + c2]);
+    CK(cudaMalloc(&hA, ha.size() * sizeof(__half))); CK(cudaMalloc(&hB, hb.size() * sizeof(__half)));
+    CK(cudaMemcpy(hA, ha.data(), ha.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(hB, hb.data(), hb.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    GemmDesc gh = g;
+    gh.A = reinterpret_cast<const float*>(hA); gh.lda = lha; gh.B = reinterpret_cast<const float*>(hB); gh.ldb = lhb;
+    rc = tc_debug_gemm(h, mode, gh, 2);
+    cudaFree(hA); cudaFree(hB);
+    if (rc) return rc;
+    done = true;
+  } else if (use_tc) {
+    rc = tc_debug_gemm(h, mode, g, 4);
     if (rc) return rc;
     done = true;
   }
@@ -1752,7 +1856,7 @@ int mrgan_debug_gemm_time(mrgan_handle* h, int mode, int M, int N, int K, int gr
   int rc = finish_pending(h); if (rc) return rc;
   const int ar = mode == 2 ? K : M, ac = mode == 2 ? M : K;
   const int br = mode == 1 ? N : K, bc = mode == 1 ? K : N;
-  const int lda = pitch4(ac), ldb = pitch4(bc), ldc = pitch4(N);
+  const int lda = pitch8(ac), ldb = pitch8(bc), ldc = pitch8(N);
   const size_t sa = (size_t)ar * lda, sb = (size_t)br * ldb, sc = (size_t)M * ldc;
   float* buf = nullptr;
   CK(cudaMalloc(&buf, (sa + sb + sc) * groups * 4));
@@ -1773,9 +1877,9 @@ int mrgan_debug_gemm_time(mrgan_handle* h, int mode, int M, int N, int K, int gr
   const TcOp& t = ops[0];
   dim3 grid((t.ME + 127) / 128, (t.NE + t.bn - 1) / t.bn, groups);
   auto once = [&]() {
-    if (mode == 0) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp);
-    else if (mode == 1) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp);
-    else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp);
+    if (mode == 0) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
+    else if (mode == 1) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
+    else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
   };
   once();
   CK(cudaEventRecord(h->ev0, h->stream));

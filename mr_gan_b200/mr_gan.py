@@ -164,7 +164,7 @@ def main(argv=None):
     # additive flags (defaults reproduce the reference's behaviour)
     parser.add_argument('--seed', type=int, default=None, help='seed for splits, initial weights, permutations and noise')
     parser.add_argument('--epochs', type=int, default=100)
-    parser.add_argument('--precision', choices=['fp32', 'tf32'], default='fp32')
+    parser.add_argument('--precision', choices=['fp32', 'tf32', 'f16'], default='fp32')
     parser.add_argument('--group', type=int, default=42, help='folds trained side by side per GPU launch (42 = one modality of table 1)')
     parser.add_argument('--data-dir', default='data_processed')
     args = parser.parse_args(argv)

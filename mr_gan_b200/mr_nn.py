@@ -79,7 +79,7 @@ def main(argv=None):
     parser.add_argument('-v', '--verbose', help='Verbose', action='store_true')
     parser.add_argument('--seed', type=int, default=None)
     parser.add_argument('--epochs', type=int, default=100)
-    parser.add_argument('--precision', choices=['fp32', 'tf32'], default='fp32')
+    parser.add_argument('--precision', choices=['fp32', 'tf32', 'f16'], default='fp32')
     parser.add_argument('--group', type=int, default=42)
     parser.add_argument('--data-dir', default='data_processed')
     args = parser.parse_args(argv)

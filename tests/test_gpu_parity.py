@@ -12,14 +12,14 @@ from oracle import fold_loop, gan_oracle as O, make_golden, philox
 
 pytestmark = pytest.mark.gpu
 
-PRECISIONS = ["fp32", "tf32"]
-LOSS_RTOL = {"fp32": 1e-3, "tf32": 1e-3}        # the north_star's tolerance, both modes (B=50)
+PRECISIONS = ["fp32", "tf32", "f16"]        # f16 = fp16 operand copies: same 10 explicit mantissa bits as tf32 -> same tolerances
+LOSS_RTOL = {"fp32": 1e-3, "tf32": 1e-3, "f16": 1e-3}        # the north_star's tolerance, both modes (B=50)
 # argmax-based statistics after several tf32 steps: a borderline sample may flip (tolerance in samples)
-FLIPS = {"fp32": 0, "tf32": 2}
+FLIPS = {"fp32": 0, "tf32": 2, "f16": 2}
 # means over an epoch of tiny batches (B=10): per-step differences compound along the trajectory
-TRAJ_RTOL = {"fp32": 1e-3, "tf32": 5e-3}
-GEN_RTOL_SMALL_BATCH = {"fp32": 1e-3, "tf32": 3e-3}   # feature-matching loss at B<=25: a squared difference of tiny batch means
-PARAM_TOL = {"fp32": 1e-3, "tf32": 0.35}        # |dp| relative to lr-sized updates, see _param_close
+TRAJ_RTOL = {"fp32": 1e-3, "tf32": 5e-3, "f16": 5e-3}
+GEN_RTOL_SMALL_BATCH = {"fp32": 1e-3, "tf32": 3e-3, "f16": 3e-3}   # feature-matching loss at B<=25: a squared difference of tiny batch means
+PARAM_TOL = {"fp32": 1e-3, "tf32": 0.35, "f16": 0.35}        # |dp| relative to lr-sized updates, see _param_close
 
 
 def _key64(key):
