@@ -49,9 +49,9 @@ enum { MRGAN_MODEL_GAN = 0,   /* mr_gan.py: G + D, feature matching          */
        MRGAN_MODEL_NN = 1 };  /* mr_nn.py: D as a plain classifier, MSE loss */
 enum { MRGAN_PREC_FP32 = 0,   /* FFMA kernels, fp32 operands (parity mode)                  */
        MRGAN_PREC_TF32 = 1,   /* tcgen05 kind::tf32 tensor-core kernels, fp32 accumulate    */
-       MRGAN_PREC_F16 = 2 };  /* tcgen05 kind::f16 on fp16 operand COPIES (weights, activations, loss-scaled
-                                 gradients; same 10-bit mantissa as tf32, rounded to nearest), fp32 master weights,
-                                 fp32 accumulation and Adam.  EXPERIMENTAL: not validated end to end yet. */
+       MRGAN_PREC_F16 = 2 };  /* tcgen05 kind::f16 on 16-bit operand COPIES: fp16 weights and activations (the same
+                                 10-bit mantissa as tf32, rounded to nearest), bf16 gradients (fp32's exponent
+                                 range, no loss scale); fp32 master weights, fp32 accumulation and Adam. */
 
 /* Hyper-parameters; mrgan_default_config() fills the reference's values. */
 typedef struct {
@@ -178,6 +178,10 @@ int  mrgan_debug_gemm_time(mrgan_handle* h, int mode, int M, int N, int K, int g
 int64_t mrgan_kernel_launches(const mrgan_handle* h); /* kernels launched so far (graph nodes count per replay) */
 double  mrgan_last_device_ms(const mrgan_handle* h);  /* CUDA-event time of the last train_epoch */
 const char* mrgan_version(void);
+/* ABI guard for hand-written bindings (ctypes / cgo / JNI lay the structs out by hand): fills
+ * {MRGAN_ABI_VERSION, sizeof(mrgan_config), sizeof(mrgan_fold_shape), sizeof(mrgan_epoch_stats)}. */
+#define MRGAN_ABI_VERSION 2
+int  mrgan_abi_info(int out[4]);
 
 #ifdef __cplusplus
 }

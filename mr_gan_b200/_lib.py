@@ -69,7 +69,10 @@ SYMBOLS = {
     "mrgan_kernel_launches": (C.c_int64, [_H]),
     "mrgan_last_device_ms": (C.c_double, [_H]),
     "mrgan_version": (C.c_char_p, []),
+    "mrgan_abi_info": (C.c_int, [C.POINTER(C.c_int)]),
 }
+
+ABI_VERSION = 2      # MRGAN_ABI_VERSION of include/mrgan.h this binding was written against
 
 
 def lib_path():
@@ -81,16 +84,25 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = os.environ.get("MRGAN_LIB") or _build.LIB      # MRGAN_LIB: a prebuilt library (kernel A/B experiments)
-    if not os.path.exists(path):
-        if os.environ.get("MRGAN_LIB"):
+    path = os.environ.get("MRGAN_LIB")                    # MRGAN_LIB: a prebuilt library (kernel A/B experiments)
+    if path:
+        if not os.path.exists(path):
             raise RuntimeError("MRGAN_LIB=%s does not exist" % path)
-        path = _build.build()
+    else:
+        path = _build.build()        # no-op when the library matches the sources (content hash); rebuilds a stale one
     lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)          # AttributeError if the library lacks a declared symbol
         fn.restype = res
         fn.argtypes = args
+    # the structs above are laid out by hand: refuse a library whose ABI differs instead of corrupting memory
+    info = (C.c_int * 4)()
+    if lib.mrgan_abi_info(info) != 0:
+        raise RuntimeError("mrgan_abi_info failed")
+    want = [ABI_VERSION, C.sizeof(Config), C.sizeof(FoldShape), C.sizeof(EpochStats)]
+    if list(info) != want:
+        raise RuntimeError("libmrgan.so ABI mismatch: library %s, binding %s (version, sizeof config / fold_shape / "
+                           "epoch_stats)" % (list(info), want))
     _LIB = lib
     return lib
 

@@ -113,6 +113,8 @@ struct mrgan_handle {
   bool epoch_pending = false; double last_ms = 0.0;
   long long launches = 0;
   std::string err;
+  int sticky = 0;                     // first failure of a call that cannot return a status itself (kernel launch, NCCL enqueue):
+                                      // surfaced by the next public entry point through take_sticky()
   AdamHyper hp;
   // data-parallel mode (mrgan_dp_init): NCCL communicator + buffers of the all-reduced batch statistics
   // device-resident raw datasets (mrgan_load_dataset) and scratch of the device-side fold preparation
@@ -137,11 +139,20 @@ struct mrgan_handle {
 
 namespace {
 
+int take_sticky(mrgan_handle* h);
+
 int fail(mrgan_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
   g_last_error = msg;
   return code;
 }
+
+#define CKS()                                                                                      \
+  do {                                                                                             \
+    CK(cudaGetLastError());                                                                        \
+    const int _s = take_sticky(h);                                                                 \
+    if (_s) return _s;                                                                             \
+  } while (0)
 
 #define CK(expr)                                                                                   \
   do {                                                                                             \
@@ -281,7 +292,7 @@ GemmDesc make_desc(const float* A, int lda, const float* Bm, int ldb, float* C, 
   return d;
 }
 
-void build_descs(mrgan_handle* h) {
+int build_descs(mrgan_handle* h) {
   const mrgan_config& c = h->cfg;
   const int B = c.batch, R = h->R, K = c.n_classes, nd = c.noise_dim, nf = h->nf;
   const bool gan = c.model == MRGAN_MODEL_GAN;
@@ -378,16 +389,17 @@ void build_descs(mrgan_handle* h) {
     fs.a0 = b.a[0]; fs.lda0 = b.lda[0]; fs.z = gan ? b.zb : nullptr; fs.ldz = pitch8(nd + 1);
     fs.labels_cur = b.labels_cur;
   }
-  cudaMemcpy(h->d_descs, h->h_descs.data(), h->h_descs.size() * sizeof(GemmDesc), cudaMemcpyHostToDevice);
-  cudaMemcpy(h->d_folds, h->h_folds.data(), nf * sizeof(FoldState), cudaMemcpyHostToDevice);
-  cudaMemcpy(h->d_loss, ls.data(), nf * sizeof(LossDesc), cudaMemcpyHostToDevice);
-  cudaMemcpy(h->d_eval, ev.data(), nf * sizeof(EvalDesc), cudaMemcpyHostToDevice);
-  cudaMemcpy(h->d_eval_s, evs.data(), nf * sizeof(EvalDesc), cudaMemcpyHostToDevice);
-  cudaMemcpy(h->d_ranges[0], rg0.data(), nf * sizeof(AdamRange), cudaMemcpyHostToDevice);
+  CK(cudaMemcpy(h->d_descs, h->h_descs.data(), h->h_descs.size() * sizeof(GemmDesc), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_folds, h->h_folds.data(), nf * sizeof(FoldState), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_loss, ls.data(), nf * sizeof(LossDesc), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_eval, ev.data(), nf * sizeof(EvalDesc), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_eval_s, evs.data(), nf * sizeof(EvalDesc), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_ranges[0], rg0.data(), nf * sizeof(AdamRange), cudaMemcpyHostToDevice));
   if (gan) {
-    cudaMemcpy(h->d_bn, bn.data(), nf * sizeof(BnDesc), cudaMemcpyHostToDevice);
-    cudaMemcpy(h->d_ranges[1], rg1.data(), nf * sizeof(AdamRange), cudaMemcpyHostToDevice);
+    CK(cudaMemcpy(h->d_bn, bn.data(), nf * sizeof(BnDesc), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_ranges[1], rg1.data(), nf * sizeof(AdamRange), cudaMemcpyHostToDevice));
   }
+  return MRGAN_OK;
 }
 
 void set_ones(mrgan_handle* h, float* p, int ld, int rows, int col) {
@@ -429,8 +441,18 @@ void launch_k(mrgan_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, si
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = h->use_pdl ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+  if (e != cudaSuccess && !h->sticky) { h->sticky = MRGAN_ERR_CUDA; h->err = std::string("kernel launch: ") + cudaGetErrorString(e); }
   h->launches++;
+}
+
+// status of everything enqueued since the last check (launch_k / dp_allreduce record the first failure)
+int take_sticky(mrgan_handle* h) {
+  if (!h->sticky) return MRGAN_OK;
+  const int code = h->sticky;
+  h->sticky = 0;
+  g_last_error = h->err;
+  return code;
 }
 
 // ------------------------------------------------------------------ NCCL (resolved at run time: no link dependency)
@@ -464,7 +486,10 @@ bool nccl_load() {
 void dp_allreduce(mrgan_handle* h, float* buf, size_t n) {
   if (h->dp_world <= 1 || n == 0) return;
   const int rc = g_nccl.AllReduce(buf, buf, n, 7, 0, h->nccl_comm, h->stream);
-  if (rc != 0) h->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+  if (rc != 0 && !h->sticky) {
+    h->sticky = MRGAN_ERR_CUDA;
+    h->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error");
+  }
 }
 
 void dp_allreduce_grads(mrgan_handle* h, int net) {
@@ -753,6 +778,7 @@ int build_graph(mrgan_handle* h, int key, int nb, int n_idx_nn) {
   h->launches++;
   CK(cudaMemcpyAsync(h->h_epoch_stats, h->d_epoch_stats, (size_t)h->nf * 8 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamEndCapture(h->stream, &g));
+  { const int sk = take_sticky(h); if (sk) { cudaGraphDestroy(g); return sk; } }
   cudaGraphExec_t ge = nullptr;
   CK(cudaGraphInstantiate(&ge, g, 0));
   CK(cudaGraphDestroy(g));
@@ -976,7 +1002,7 @@ int tc_setup(mrgan_handle* h) {
     }
   }
   if (cudaMalloc(&h->d_tcops, ops.size() * sizeof(TcOp)) != cudaSuccess) return fail(nullptr, MRGAN_ERR_CUDA, "cudaMalloc tc ops");
-  cudaMemcpy(h->d_tcops, ops.data(), ops.size() * sizeof(TcOp), cudaMemcpyHostToDevice);
+  if (cudaMemcpy(h->d_tcops, ops.data(), ops.size() * sizeof(TcOp), cudaMemcpyHostToDevice) != cudaSuccess) return fail(nullptr, MRGAN_ERR_CUDA, "cudaMemcpy tc ops");
   if (h->tc_fused_adam && h->tc_adam_tma) {
     std::vector<TcAdamOp> aops((size_t)NUM_OPS * nf);
     memset(aops.data(), 0, aops.size() * sizeof(TcAdamOp));
@@ -998,7 +1024,7 @@ int tc_setup(mrgan_handle* h) {
       }
     }
     if (cudaMalloc(&h->d_tcadam, aops.size() * sizeof(TcAdamOp)) != cudaSuccess) return fail(nullptr, MRGAN_ERR_CUDA, "cudaMalloc tc adam ops");
-    cudaMemcpy(h->d_tcadam, aops.data(), aops.size() * sizeof(TcAdamOp), cudaMemcpyHostToDevice);
+    if (cudaMemcpy(h->d_tcadam, aops.data(), aops.size() * sizeof(TcAdamOp), cudaMemcpyHostToDevice) != cudaSuccess) return fail(nullptr, MRGAN_ERR_CUDA, "cudaMemcpy tc adam ops");
   }
   // what is left for the flat Adam kernel when dW applies Adam itself
   std::vector<AdamRange> r0(nf), r1(nf);
@@ -1011,7 +1037,7 @@ int tc_setup(mrgan_handle* h) {
   }
   for (int n = 0; n < 2; ++n) {
     if (cudaMalloc(&h->d_ranges_tc[n], nf * sizeof(AdamRange)) != cudaSuccess) return fail(nullptr, MRGAN_ERR_CUDA, "cudaMalloc");
-    cudaMemcpy(h->d_ranges_tc[n], (n == 0 ? r0 : r1).data(), nf * sizeof(AdamRange), cudaMemcpyHostToDevice);
+    if (cudaMemcpy(h->d_ranges_tc[n], (n == 0 ? r0 : r1).data(), nf * sizeof(AdamRange), cudaMemcpyHostToDevice) != cudaSuccess) return fail(nullptr, MRGAN_ERR_CUDA, "cudaMemcpy adam ranges");
   }
   tc_set_smem_attr();
   return MRGAN_OK;
@@ -1084,7 +1110,13 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
 // ====================================================================== C-ABI
 extern "C" {
 
-const char* mrgan_version(void) { return "mrgan-b200 0.1 (sm_100a)"; }
+const char* mrgan_version(void) { return "mrgan-b200 0.2 (sm_100a)"; }
+
+int mrgan_abi_info(int out[4]) {
+  if (!out) return fail(nullptr, MRGAN_ERR_ARG, "abi_info: null pointer");
+  out[0] = MRGAN_ABI_VERSION; out[1] = (int)sizeof(mrgan_config); out[2] = (int)sizeof(mrgan_fold_shape); out[3] = (int)sizeof(mrgan_epoch_stats);
+  return MRGAN_OK;
+}
 
 int mrgan_default_config(int model, mrgan_config* cfg) {
   if (!cfg) return fail(nullptr, MRGAN_ERR_ARG, "cfg is null");
@@ -1124,8 +1156,8 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev)
     return fail(nullptr, MRGAN_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major < 10)
-    return fail(nullptr, MRGAN_ERR_NO_DEVICE, "device is not sm_100 (Blackwell): this library has no CPU fallback");
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10 || prop.minor != 0)
+    return fail(nullptr, MRGAN_ERR_NO_DEVICE, "device is not sm_100 (B200): the library holds sm_100a code only and has no CPU fallback");
   if (cfg->precision < MRGAN_PREC_FP32 || cfg->precision > MRGAN_PREC_F16) return fail(nullptr, MRGAN_ERR_ARG, "bad config (precision)");
 #ifndef MRGAN_WITH_TC
   if (cfg->precision != MRGAN_PREC_FP32) return fail(nullptr, MRGAN_ERR_ARG, "library built without the tcgen05 kernels");
@@ -1172,9 +1204,11 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, std::string("cudaMalloc fp16 operand arena: ") + cudaGetErrorString(e)));
     h->om.hbase = h->harena;
-    h->om.gscale = MRGAN_F16_LOSS_SCALE;
-    if (const char* gb = getenv("MRGAN_GRAD_BF16")) {      // gradient-side operands as unscaled bf16 instead of loss-scaled fp16
-      if (atoi(gb) != 0) { h->om.grad_bf16 = 1; h->om.gscale = 1.0f; }
+    // gradient-side operands: unscaled bf16 (fp32's exponent range: tiny gradients keep their sign, which Adam's sign-like
+    // first steps need; no overflow whatever the batch size).  MRGAN_GRAD_BF16=0 selects loss-scaled fp16 instead (A/B).
+    h->om.grad_bf16 = 1; h->om.gscale = 1.0f;
+    if (const char* gb = getenv("MRGAN_GRAD_BF16")) {
+      if (atoi(gb) == 0) { h->om.grad_bf16 = 0; h->om.gscale = MRGAN_F16_LOSS_SCALE; }
     }
   }
   bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -1207,7 +1241,7 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
     ok = ok && cudaEventCreateWithFlags(&h->idx_free[s], cudaEventDisableTiming) == cudaSuccess;
   }
   if (!ok) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, "stream/event/pinned allocation failed"));
-  build_descs(h);
+  { const int rc = build_descs(h); if (rc != MRGAN_OK) return cleanup(rc); }
   init_ones(h);
   if (cfg->model == MRGAN_MODEL_GAN && cfg->batch > 256) {   // large batch: row-parallel split BatchNorm / feature-matching kernels
     int rc = alloc_split_bufs(h);
@@ -1416,7 +1450,7 @@ int mrgan_prepare_fold(mrgan_handle* h, int fold, int slot, const int32_t* train
                                                      b.xte, b.lda[0], ds.y, b.yte, h->om);
   h->launches += 3;
   CK(cudaStreamSynchronize(h->stream));     // the pageable index arrays are borrowed only for the call
-  CK(cudaGetLastError());
+  CKS();
   b.loaded = true;
   return MRGAN_OK;
 }
@@ -1440,7 +1474,7 @@ int mrgan_disc_step(mrgan_handle* h, int fold, const float* x_lab, const int32_t
   enqueue_disc_step(h, fold, 1, 0, 1);
   CK(cudaMemcpyAsync(h->h_scratch, h->d_step_stats + (size_t)fold * 4, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaGetLastError());
+  CKS();
   out[0] = h->h_scratch[0]; out[1] = h->h_scratch[1]; out[2] = h->h_scratch[2];
   return MRGAN_OK;
 }
@@ -1459,7 +1493,7 @@ int mrgan_gen_step(mrgan_handle* h, int fold, const float* x_unl, const float* z
   enqueue_gen_step(h, fold, 1, 0, 1);
   CK(cudaMemcpyAsync(h->h_scratch, h->d_step_stats + (size_t)fold * 4, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaGetLastError());
+  CKS();
   out[0] = h->h_scratch[3];
   return MRGAN_OK;
 }
@@ -1487,7 +1521,7 @@ int mrgan_test_batch(mrgan_handle* h, int fold, const float* x, const int32_t* y
   enqueue_eval(h, fold, 1, true, n);
   CK(cudaMemcpyAsync(h->h_scratch, b.eval_out_s, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaGetLastError());
+  CKS();
   err[0] = h->h_scratch[1];
   return MRGAN_OK;
 }
@@ -1501,7 +1535,7 @@ int mrgan_eval(mrgan_handle* h, int fold, float* err) {
   enqueue_eval(h, fold, 1, false, 0);
   CK(cudaMemcpyAsync(h->h_scratch, h->fb[fold].eval_out, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaGetLastError());
+  CKS();
   err[0] = h->h_scratch[1];
   return MRGAN_OK;
 }
@@ -1510,7 +1544,7 @@ int mrgan_epoch_result(mrgan_handle* h, mrgan_epoch_stats* stats) {
   if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
   CK(cudaSetDevice(h->cfg.device));
   int rc = finish_pending(h); if (rc) return rc;
-  CK(cudaGetLastError());
+  CKS();
   if (stats)
     for (int f = 0; f < h->nf; ++f) {
       const float* s = h->h_epoch_stats + (size_t)f * 8;
@@ -1551,6 +1585,7 @@ int mrgan_train_epoch(mrgan_handle* h, const int32_t* idx_lab, const int32_t* id
   }
   CK(cudaEventRecord(h->ev1, h->stream));
   h->epoch_pending = true;
+  { const int sk = take_sticky(h); if (sk) return sk; }
   if (stats) return mrgan_epoch_result(h, stats);
   return MRGAN_OK;
 }
@@ -1572,7 +1607,7 @@ int mrnn_step(mrgan_handle* h, int fold, const float* x, const int32_t* labels, 
   enqueue_nn_step(h, fold, 1, 0, 1, n);
   CK(cudaMemcpyAsync(h->h_scratch, h->d_step_stats + (size_t)fold * 4, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaGetLastError());
+  CKS();
   out[0] = h->h_scratch[0]; out[1] = h->h_scratch[1];
   return MRGAN_OK;
 }
@@ -1599,7 +1634,7 @@ int mrnn_train_epoch(mrgan_handle* h, const int32_t* idx, int n_idx, float* loss
   h->epoch_pending = true;
   if (loss_acc) {
     rc = finish_pending(h); if (rc) return rc;
-    CK(cudaGetLastError());
+    CKS();
     for (int f = 0; f < h->nf; ++f) { loss_acc[2 * f] = h->h_epoch_stats[f * 8]; loss_acc[2 * f + 1] = h->h_epoch_stats[f * 8 + 1]; }
   }
   return MRGAN_OK;
@@ -1614,7 +1649,7 @@ int mrnn_evaluate(mrgan_handle* h, int fold, float out[2]) {
   enqueue_eval(h, fold, 1, false, 0);
   CK(cudaMemcpyAsync(h->h_scratch, h->fb[fold].eval_out, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaGetLastError());
+  CKS();
   out[0] = h->h_scratch[2]; out[1] = 1.0f - h->h_scratch[1];
   return MRGAN_OK;
 }
@@ -1692,7 +1727,7 @@ int mrgan_time_op(mrgan_handle* h, int which, int reps, float* ms_avg) {
   for (int i = 0; i < reps; ++i) once();
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaGetLastError());
+  CKS();
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   *ms_avg = ms / reps;
@@ -1886,7 +1921,7 @@ int mrgan_debug_gemm_time(mrgan_handle* h, int mode, int M, int N, int K, int gr
   for (int i = 0; i < reps; ++i) once();
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  CK(cudaGetLastError());
+  CKS();
   float t_ms = 0.f;
   CK(cudaEventElapsedTime(&t_ms, h->ev0, h->ev1));
   *ms = t_ms / reps;

@@ -20,11 +20,16 @@ MODALITIES = ['Force', 'Temperature', 'Force and Temperature', 'Contact mic', 'T
 
 
 def dataset(modalities=0, forcetempTime=4, contactmicTime=0.2, leaveObjectOut=False, verbose=False, *,
-            seed=0, data_dir='data_processed'):
-    """mr_gan.py:23-71.  The MREO pickles are not distributed with the reference; when
-    ``data_dir`` does not hold them, data of the same shape is synthesised (synthetic.py)."""
-    path = os.path.join(data_dir, 'processed_0.1sbefore_%s_times_%.2f_%.2f.pkl' % (MATERIALS[0], forcetempTime, contactmicTime))
-    if os.path.exists(path):
+            seed=0, data_dir='data_processed', synthetic_data=False):
+    """mr_gan.py:23-71.  Loads the processed MREO pickles from ``data_dir`` and, like the reference, raises IOError when
+    they are missing.  The pickles are not distributed with the reference, so data of the same shape can be
+    synthesised instead (synthetic.py) -- only on request (``synthetic_data=True`` / ``--synthetic``): a mistyped path
+    must not silently turn into plausible-looking numbers."""
+    if not synthetic_data:
+        path = os.path.join(data_dir, 'processed_0.1sbefore_%s_times_%.2f_%.2f.pkl' % (MATERIALS[0], forcetempTime, contactmicTime))
+        if not os.path.exists(path):
+            raise IOError("processed MREO data not found: %s (pass synthetic_data=True / --synthetic for synthetic data "
+                          "of the MREO shape)" % path)
         from .realdata import load_processed
         return load_processed(modalities, forcetempTime, contactmicTime, leaveObjectOut, verbose, data_dir)
     out = synthetic.synthetic_dataset(modalities, forcetempTime, contactmicTime, leaveObjectOut, seed=seed)
@@ -167,10 +172,13 @@ def main(argv=None):
     parser.add_argument('--precision', choices=['fp32', 'tf32', 'f16'], default='fp32')
     parser.add_argument('--group', type=int, default=42, help='folds trained side by side per GPU launch (42 = one modality of table 1)')
     parser.add_argument('--data-dir', default='data_processed')
+    parser.add_argument('--synthetic', action='store_true', help='synthetic data of the MREO shape instead of the processed pickles')
     args = parser.parse_args(argv)
-    seed = args.seed if args.seed is not None else int(np.random.SeedSequence().entropy % (2 ** 31))
     rank, world, local = sweep.dist_env()
+    seed = sweep.shared_seed(args.seed)          # one seed for every rank: same dataset, same splits, same job streams
     say = print if rank == 0 else (lambda *a, **k: None)
+    if rank == 0:
+        sys.stderr.write('seed: %d%s\n' % (seed, '   [SYNTHETIC data of the MREO shape: not the paper\'s dataset]' if args.synthetic else ''))
     jid = [0]
 
     def run(jobs):
@@ -193,7 +201,7 @@ def main(argv=None):
         percents = [1, 2, 4, 8, 16, 50, 100]
         jobs = []
         for modality in range(len(MODALITIES)):
-            X, y = dataset(modalities=modality, seed=seed, data_dir=args.data_dir)
+            X, y = dataset(modalities=modality, seed=seed, data_dir=args.data_dir, synthetic_data=args.synthetic)
             jobs += [j for p in percents for j in _kfold_jobs(X, y, seed + p, percentlabeled=p)]
         errors = run(jobs)
         say('\n', '-' * 25, 'Testing various amounts of labeled training data', '-' * 25)
@@ -212,7 +220,7 @@ def main(argv=None):
         say('-' * 100)
         for modality in [2, 5]:
             say('-' * 25, MODALITIES[modality], 'modality', '-' * 25)
-            objects = dataset(modalities=modality, leaveObjectOut=True, seed=seed, data_dir=args.data_dir)
+            objects = dataset(modalities=modality, leaveObjectOut=True, seed=seed, data_dir=args.data_dir, synthetic_data=args.synthetic)
             percents = [1, 4, 16, 50, 100]
             jobs = [j for p in percents for j in _loo_jobs(objects, percentlabeled=p)]
             errors = run(jobs)
@@ -233,7 +241,7 @@ def main(argv=None):
                 jobs = []
                 for tm in times:
                     kw = dict(contactmicTime=tm) if is_contact else dict(forcetempTime=tm)
-                    X, y = dataset(modalities=modality, seed=seed, data_dir=args.data_dir, **kw)
+                    X, y = dataset(modalities=modality, seed=seed, data_dir=args.data_dir, synthetic_data=args.synthetic, **kw)
                     jobs += _kfold_jobs(X, y, seed, percentlabeled=100)
                 errors = run(jobs)
                 for k, tm in enumerate(times):
@@ -247,7 +255,7 @@ def main(argv=None):
         say('-' * 100)
         for modality in [2, 5]:
             say('-' * 25, MODALITIES[modality], 'modality', '-' * 25)
-            X, y = dataset(modalities=modality, seed=seed, data_dir=args.data_dir)
+            X, y = dataset(modalities=modality, seed=seed, data_dir=args.data_dir, synthetic_data=args.synthetic)
             for percentlabeled in [4]:
                 say('-' * 15, 'Percentage of training data labeled: %d%%' % percentlabeled, '-' * 15)
                 unl = [0, 4, 8, 16, 32, 64, 100 - percentlabeled]

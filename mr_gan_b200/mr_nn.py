@@ -82,10 +82,13 @@ def main(argv=None):
     parser.add_argument('--precision', choices=['fp32', 'tf32', 'f16'], default='fp32')
     parser.add_argument('--group', type=int, default=42)
     parser.add_argument('--data-dir', default='data_processed')
+    parser.add_argument('--synthetic', action='store_true', help='synthetic data of the MREO shape instead of the processed pickles')
     args = parser.parse_args(argv)
-    seed = args.seed if args.seed is not None else int(np.random.SeedSequence().entropy % (2 ** 31))
     rank, world, local = sweep.dist_env()
+    seed = sweep.shared_seed(args.seed)          # one seed for every rank: same dataset, same splits, same job streams
     say = print if rank == 0 else (lambda *a, **k: None)
+    if rank == 0:
+        sys.stderr.write('seed: %d%s\n' % (seed, '   [SYNTHETIC data of the MREO shape: not the paper\'s dataset]' if args.synthetic else ''))
     jid = [0]
 
     def run(jobs):
@@ -104,7 +107,7 @@ def main(argv=None):
         say('-' * 100)
         for modality in [2, 5]:
             say('-' * 25, MODALITIES[modality], 'modality', '-' * 25)
-            X, y = dataset(modalities=modality, seed=seed, data_dir=args.data_dir)
+            X, y = dataset(modalities=modality, seed=seed, data_dir=args.data_dir, synthetic_data=args.synthetic)
             percents = [1, 2, 4, 8, 16, 50, 100]
             jobs = [j for p in percents for j in _kfold_jobs(X, y, seed + p, percentlabeled=p)]
             errors = run(jobs)
@@ -119,7 +122,7 @@ def main(argv=None):
         say('-' * 100)
         for modality in [2, 5]:
             say('-' * 25, MODALITIES[modality], 'modality', '-' * 25)
-            objects = dataset(modalities=modality, leaveObjectOut=True, seed=seed, data_dir=args.data_dir)
+            objects = dataset(modalities=modality, leaveObjectOut=True, seed=seed, data_dir=args.data_dir, synthetic_data=args.synthetic)
             percents = [1, 4, 16, 50, 100]
             jobs = [j for p in percents for j in _loo_jobs(objects, percentlabeled=p)]
             errors = run(jobs)

@@ -17,6 +17,27 @@ def dist_env():
     return rank, world, local
 
 
+def _ensure_group():
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        dist.init_process_group("gloo")      # host-side exchange only (seed, one float per fold): no GPU collective on this path
+    return dist
+
+
+def shared_seed(seed=None):
+    """The sweep's seed, identical on every rank.  It drives the synthetic data, the StratifiedKFold random_state and
+    every job's streams, so ranks that drew their own would each train folds of a DIFFERENT partition.  ``seed=None``
+    keeps the reference's 'Non Deterministic output' (mr_gan.py:74-75): rank 0 draws, everybody else receives."""
+    rank, world, _ = dist_env()
+    if seed is None:
+        seed = int(np.random.SeedSequence().entropy % (2 ** 31))
+    if world > 1:
+        box = [int(seed)]
+        _ensure_group().broadcast_object_list(box, src=0)
+        seed = box[0]
+    return int(seed)
+
+
 def make_groups(jobs, group_size, key=lambda j: 0):
     """Split jobs (kept in order) into groups of <= group_size whose members share key(job)."""
     groups, cur, cur_key = [], [], None
@@ -59,8 +80,8 @@ def run_sharded(jobs, train_group, group_size=6, key=lambda j: 0, cost=lambda j:
             mine[i] = r
     if world > 1:
         import torch.distributed as dist
-        if not dist.is_initialized() and init_dist:
-            dist.init_process_group("gloo")      # host-side gather of one float per fold: no GPU collective on this path
+        if init_dist:
+            _ensure_group()
         parts = [None] * world
         dist.all_gather_object(parts, mine)
         mine = {}

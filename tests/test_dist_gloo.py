@@ -13,6 +13,13 @@ import torch.distributed as dist
 from mr_gan_b200 import sweep
 dist.init_process_group("gloo")
 rank = dist.get_rank()
+# one seed for the whole sweep: an omitted --seed is drawn on rank 0 and shared (each rank drawing its own would build a
+# different dataset and different splits per rank), an explicit one passes through
+s = sweep.shared_seed(None)
+got = [None, None]
+dist.all_gather_object(got, s)
+assert got[0] == got[1] and 0 <= s < 2 ** 31, got
+assert sweep.shared_seed(1234 + rank * 0) == 1234
 jobs = [dict(D=d, n=6000 if i < 9 else 7100) for i, d in enumerate([400, 800, 1200] * 4)]
 seen = []
 def train_group(js, dev):

@@ -359,7 +359,7 @@ def test_final_accuracy_tf32_vs_fp32_over_seed_set():
     for prec in ("tf32", "fp32"):
         a = []
         for seed in range(5):
-            X, y = dataset(modalities=2, seed=seed)
+            X, y = dataset(modalities=2, seed=seed, synthetic_data=True)
             jobs = _kfold_jobs(X, y, seed, percentlabeled=8)
             a += [1.0 - e for e in train_gan_folds(jobs, epochs=15, seed=seed, precision=prec)]
         acc[prec] = np.array(a)

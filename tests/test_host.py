@@ -90,6 +90,27 @@ def test_sweep_grouping_and_assignment():
     assert res == [2 * j['D'] for j in jobs]
 
 
+def test_dataset_raises_without_the_pickles_unless_synthetic_is_requested(tmp_path):
+    """The reference's dataset() raises IOError on a missing pickle (mr_gan.py:33 open()); so does the drop-in.  Synthetic
+    data is opt-in: a wrong --data-dir must not print plausible tables from made-up data."""
+    with pytest.raises(IOError):
+        mg.dataset(modalities=1, data_dir=str(tmp_path / "nope"))
+    X, y = mg.dataset(modalities=1, data_dir=str(tmp_path / "nope"), synthetic_data=True)
+    assert X.shape == (7200, 400) and y.shape == (7200,)
+    assert sweep.shared_seed(7) == 7 and 0 <= sweep.shared_seed(None) < 2 ** 31
+
+
+def test_build_is_content_hashed_and_abi_checked():
+    from mr_gan_b200 import build as B
+    assert not B._stale()                       # the suite built / loaded it already
+    h = B.source_hash()
+    assert open(B.HASH).read().strip() == h
+    lib = _lib.load()
+    info = (C.c_int * 4)()
+    assert lib.mrgan_abi_info(info) == 0
+    assert list(info) == [_lib.ABI_VERSION, C.sizeof(_lib.Config), C.sizeof(_lib.FoldShape), C.sizeof(_lib.EpochStats)]
+
+
 def test_cli_surface_matches_reference_flags():
     for mod in (mg, mn):
         with pytest.raises(SystemExit):

@@ -6,7 +6,7 @@ python - <<'PY'
 import time, numpy as np
 from mr_gan_b200.mr_gan import dataset, mr_gan, train_gan_folds, _kfold_jobs
 from mr_gan_b200.mr_nn import mr_nn
-X, y = dataset(modalities=1)            # temperature, D=400 (synthetic MREO shape)
+X, y = dataset(modalities=1, synthetic_data=True)            # temperature, D=400 (synthetic MREO shape)
 t = time.time(); e = mr_gan(X, y, percentlabeled=16, epochs=3, seed=1, verbose=True); print("mr_gan fp32 3 epochs: err %.4f in %.1fs" % (e, time.time() - t))
 t = time.time(); e = mr_gan(X, y, percentlabeled=16, epochs=3, seed=1, precision='tf32'); print("mr_gan tf32 3 epochs: err %.4f in %.1fs" % (e, time.time() - t))
 t = time.time(); e = mr_nn(X, y, percentlabeled=16, epochs=5, seed=1, precision='tf32'); print("mr_nn tf32 5 epochs: err %.4f in %.1fs" % (e, time.time() - t))
