@@ -9,7 +9,6 @@
 //    every activation buffer carries a constant 1.0 in column `in`, so bias add
 //    (forward) and bias gradient (backward) fall out of the GEMMs themselves.
 #pragma once
-#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -73,7 +72,11 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // row pitch in elements: a multiple of 8 so that both the fp32 rows and their fp16 operand copies have 16-byte strides (TMA)
+#ifdef MRGAN_PITCH4_EXPERIMENT
+__host__ __device__ inline int pitch8(int w) { return (w + 3) & ~3; }
+#else
 __host__ __device__ inline int pitch8(int w) { return (w + 7) & ~7; }
+#endif
 
 // ---------------------------------------------------------------- Philox4x32-10
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
@@ -87,6 +90,12 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
   return c;
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // The 4 normals of rows 4*rowgroup .. 4*rowgroup+3 at column `col`
 // (definition: oracle/philox.py module docstring).
 __device__ __forceinline__ void normal4(uint32_t k0, uint32_t k1, uint32_t rowgroup, uint32_t col,
@@ -97,11 +106,34 @@ __device__ __forceinline__ void normal4(uint32_t k0, uint32_t k1, uint32_t rowgr
   const float u1b = ((float)(x.z >> 9) + 0.5f) * s, u2b = ((float)(x.w >> 9) + 0.5f) * s;
   // fast-math intrinsics: |error| of a normal <= ~3e-6 (lg2.approx / sin.approx / cos.approx on [-pi, pi]), far below
   // the 1e-3 loss tolerance; the epilogue warps generate ~800k normals per fold and step pair
-  const float ra = __fsqrt_rn(-2.0f * __logf(u1a)), rb = __fsqrt_rn(-2.0f * __logf(u1b));
+  const float ra = sqrt_approx(-2.0f * __logf(u1a)), rb = sqrt_approx(-2.0f * __logf(u1b));
   const float pi = 3.14159265358979323846f;
   const float ta = pi * (2.0f * u2a - 1.0f), tb = pi * (2.0f * u2b - 1.0f);
   const float sa = __sinf(ta), ca = __cosf(ta), sb = __sinf(tb), cb = __cosf(tb);
   out[0] = ra * ca; out[1] = ra * sa; out[2] = rb * cb; out[3] = rb * sb;
+}
+
+// Out-of-line noise draws for the GEMM epilogues: they draw up to 38 row groups per thread from several places, and an
+// inlined Philox (~150 instructions, plus the integer division of global_row) per call site grew the forward kernel to
+// 9 k instructions = 146 KB of SASS, far beyond the instruction cache -- the epilogue loop was fetching its own code
+// from L2 (ncu: no_inst stalls).  One call per row group; with 2 epilogue warps per scheduler a single Philox chain per
+// warp already keeps the issue slots busy.  `local_row` is this rank's stacked row index (see global_row).
+__device__ __noinline__ float4 noise4_call(uint32_t k0, uint32_t k1, int local_row, uint32_t col, uint32_t step, uint32_t tid,
+                                           int dp_bloc, int dp_bg, int dp_rank) {
+  AdamHyper hp; hp.dp_bloc = dp_bloc; hp.dp_bg = dp_bg; hp.dp_rank = dp_rank;
+  float n[4];
+  normal4(k0, k1, (uint32_t)global_row(local_row, hp) >> 2, col, step, tid, n);
+  return make_float4(n[0], n[1], n[2], n[3]);
+}
+// one element (a 4-row group that straddles a section / rank boundary is drawn element by element)
+__device__ __noinline__ float noise1_call(uint32_t k0, uint32_t k1, int local_row, uint32_t col, uint32_t step, uint32_t tid,
+                                          int dp_bloc, int dp_bg, int dp_rank) {
+  AdamHyper hp; hp.dp_bloc = dp_bloc; hp.dp_bg = dp_bg; hp.dp_rank = dp_rank;
+  const uint32_t gr = (uint32_t)global_row(local_row, hp);
+  float n[4];
+  normal4(k0, k1, gr >> 2, col, step, tid, n);
+  const uint32_t e = gr & 3u;
+  return e == 0 ? n[0] : (e == 1 ? n[1] : (e == 2 ? n[2] : n[3]));
 }
 
 __device__ __forceinline__ float normal1(uint32_t k0, uint32_t k1, uint32_t row, uint32_t col,
@@ -125,18 +157,15 @@ __device__ __forceinline__ float rna_tf32(float x) {
 //   mode 2 (f16)        : rounded to nearest to fp16 into the SHADOW arena -- one __half per float of the handle's arena
 //                         at the same element index (hbase[p - fbase]), so pitches and descriptor offsets carry over.
 //                         Gradient-side operands (dZ) are stored multiplied by the loss scale `gscale` (a power of two;
-//                         every consumer is linear, the Adam update divides it out again).
-//                         Alternative (grad_bf16 = 1, MRGAN_GRAD_BF16=1): gradient-side operands are stored as bf16 without
-//                         any scale -- fp32's exponent range, so tiny gradients keep their sign (Adam's first steps are
-//                         sign-like), at 8 instead of 11 significant bits; kind::f16 takes f16 and bf16 operands mixed.
-struct OperandMode { int mode; float gscale; const float* fbase; __half* hbase; int grad_bf16; };
-
-__device__ __forceinline__ void put_grad16(__half* dst, float x, const OperandMode& om) {
-  if (om.grad_bf16) *reinterpret_cast<__nv_bfloat16*>(dst) = __float2bfloat16_rn(x);
-  else *dst = __float2half_rn(x);
-}
+//                         every consumer is linear, the Adam update divides it out again) and saturate at the largest
+//                         fp16 instead of overflowing to infinity.  (kind::f16 does not take an f16 operand together with
+//                         a bf16 one -- measured: illegal instruction -- so unscaled bf16 gradients are not an option
+//                         while weights and activations are fp16.)
+struct OperandMode { int mode; float gscale; const float* fbase; __half* hbase; };
 
 #define MRGAN_F16_LOSS_SCALE 4096.0f
+
+__device__ __forceinline__ __half grad_to_half(float x) { return __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f)); }
 
 __device__ __forceinline__ void put_operand(float* p, float x, const OperandMode& om) {
   if (om.mode == 2) om.hbase[p - om.fbase] = __float2half_rn(x);
@@ -144,7 +173,7 @@ __device__ __forceinline__ void put_operand(float* p, float x, const OperandMode
 }
 // gradient-side operand produced from an UNSCALED value (loss heads, BatchNorm backward)
 __device__ __forceinline__ void put_grad_operand(float* p, float x, const OperandMode& om) {
-  if (om.mode == 2) put_grad16(om.hbase + (p - om.fbase), x * om.gscale, om);
+  if (om.mode == 2) om.hbase[p - om.fbase] = grad_to_half(x * om.gscale);
   else put_operand(p, x, om);
 }
 
@@ -159,6 +188,14 @@ __device__ __forceinline__ void put_grad_operand(float* p, float x, const Operan
 __device__ __forceinline__ float softplusf(float x) {
   // log(1+e^x), stable on both tails (K.softplus)
   return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x)));
+}
+
+// tensor-core path: two MUFU ops instead of the libm expf / log1pf sequences (which unroll to ~100 instructions per
+// element in the GEMM epilogues); |error| < 1e-7 absolute: log(1 + e) by its series where 1 + e would round
+__device__ __forceinline__ float softplus_fast(float x) {
+  const float e = __expf(-fabsf(x));
+  const float l = e < 1e-3f ? e * fmaf(e, fmaf(e, 0.33333333f, -0.5f), 1.0f) : __logf(1.0f + e);
+  return fmaxf(x, 0.0f) + l;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

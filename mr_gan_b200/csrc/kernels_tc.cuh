@@ -33,13 +33,19 @@ struct alignas(64) TcOp {
   int net;                    // 0 = discriminator, 1 = generator (which lr_t the fused Adam uses)
   int ws_stride;              // split-K (large-batch dW): floats between the partial products of two contraction slices
   float* ws;                  // ... and their workspace, laid out like C; k_splitk_reduce sums the slices in a fixed order
-  int esz;                    // operand element size: 4 (or 0) = fp32 read as tf32, 2 = fp16 (kind::f16, fp32 accumulation)
-  int afmt, bfmt;             // esz == 2: element format of the A / B operand, 0 = f16, 1 = bf16 (gradient-side operands, optional)
-  int pad_[1];
+  int esz;                    // operand element size: 4 (or 0) = fp32 read as tf32, 2 = fp16 copies (kind::f16, fp32 accumulation)
+  int pad_[3];
 };
 
 #define TC_KBLK 32            // contraction elements per stage (one 128-byte swizzle row of fp32)
 #define TC_SPIN_LIMIT (1ll << 31)   // cycles; a stuck barrier traps instead of hanging the GPU
+
+#ifdef MRGAN_PHASE_TIMING
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define PT_MARK(i) do { pt[i] = gtimer(); } while (0)
+#else
+#define PT_MARK(i) do { } while (0)
+#endif
 
 namespace tc {
 
@@ -115,6 +121,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Asynchronous TMEM loads: issue any number, wait once, then pass each destination array through tmem_fence16 -- an empty
+// volatile asm that "modifies" the registers, so no use of them can be scheduled ahead of the wait.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence16(uint32_t (&r)[16]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                    "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]) :: "memory");
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float v[8]) {
   uint32_t r[8];
   asm volatile(
@@ -153,20 +174,79 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 }  // namespace tc
 
-// A_MN / B_MN: operand is MN-major (its MMA M/N dimension is the memory-contiguous one).
-// STAGES: depth of the TMA->MMA ring; TMEM_COLS: accumulator columns allocated (power of 2 >= bn);
-// MINB: CTAs per SM the register allocation must allow (dW uses 2 so that one CTA's Adam epilogue
-// streams HBM while the other loads operands and runs its MMAs).
-// EPW: epilogue warps (4 or 8; with 8 the accumulator columns are split between two warp groups).
+
+// ---- epilogue row processors: one 16-row chunk of one feature (= thread).  Everything that is uniform over the launch
+// (activation, which outputs exist, operand formats) is a template parameter, so a row costs ~10 instructions instead
+// of ~60 of branchy code; the chunk loops dispatch once per chunk.  Pointers walk down the rows by the pitch.
+template <bool F16, int ACT, bool HAS_C, bool HAS_C2>
+__device__ __forceinline__ void fwd_rows(const uint32_t (&va)[16], const float (&nz)[16], int nrows, float* pC, __half* hC, int ldc,
+                                         bool c_op, float* pC2, __half* hC2, int ldc2, bool c2_op, float sigma) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float x = __uint_as_float(va[j]);
+    if (!F16) x *= TF32_TRUNC_DEBIAS;
+    if (ACT == ACT_RELU) x = fmaxf(x, 0.f);
+    else if (ACT == ACT_SOFTPLUS) x = softplus_fast(x);
+    const bool ok = j < nrows;
+    if (HAS_C) {                // clean activation: kept in fp32 (act' of the backward pass, feature matching, logits) ...
+      if (F16) {
+        if (ok) { *pC = x; if (c_op) *hC = __float2half_rn(x); }      // ... plus its 16-bit operand copy where a GEMM reads it
+        hC += ldc;
+      } else if (ok) *pC = c_op ? rna_tf32(x) : x;
+      pC += ldc;
+    }
+    if (HAS_C2) {               // noisy activation: only ever a GEMM operand
+      const float y = fmaf(sigma, nz[j], x);
+      if (F16) {
+        if (ok) { if (c2_op) *hC2 = __float2half_rn(y); else *pC2 = y; }
+        hC2 += ldc2;
+      } else if (ok) *pC2 = c2_op ? rna_tf32(y) : y;
+      pC2 += ldc2;
+    }
+  }
+}
+
+template <bool F16, int ACT>
+__device__ __forceinline__ void dx_rows(const uint32_t (&va)[16], const float (&av)[16], int nrows, float* pC, __half* hC, int ldc, bool op_only) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float x = __uint_as_float(va[j]);
+    if (!F16) x *= TF32_TRUNC_DEBIAS;
+    if (ACT == ACT_RELU) x = (av[j] > 0.f) ? x : 0.f;
+    else if (ACT == ACT_SOFTPLUS) x *= 1.0f - __expf(-av[j]);
+    if (j < nrows) {
+      if (F16 && op_only) *hC = grad_to_half(x);             // operand only: 16-bit copy, loss-scaled like the accumulator
+      else *pC = (!F16 && op_only) ? rna_tf32(x) : x;
+    }
+    pC += ldc;
+    if (F16) hC += ldc;
+  }
+}
+
+// A_MN / B_MN: operand is MN-major (its MMA M/N dimension is the memory-contiguous one).  The pair also selects the role:
+//   A_MN && !B_MN  forward   (EPI_FWD)      !A_MN && !B_MN  dX (EPI_DX)      A_MN && B_MN  dW (EPI_ADAM or EPI_STORE)
+// STAGES: depth of the TMA->MMA ring; TMEM_COLS: TMEM columns allocated (power of 2 >= MT x bn);
+// MINB: CTAs per SM the register allocation must allow; EPW: epilogue warps (4 or 8; with 8 and MT == 1 the accumulator
+// columns are split between two warp groups).
 // MT: feature sub-tiles of 128 per CTA (1 or 2).  With MT = 2 the CTA computes 256 features against ONE copy of the
-// batch-side operand tile (two accumulators in TMEM, 2 x 4 MMAs per stage), which halves the activation bytes every
-// SM has to ingest -- the forward / dX mainloops are bound by L2->SM traffic, not by HBM or the tensor pipe -- and each
-// warp group of the epilogue owns one sub-tile.  MT = 2 requires EPW = 8 and TMEM_COLS = 512.
-template <bool A_MN, bool B_MN, int STAGES, int TMEM_COLS, int MINB, int EPW, int MT>
+// batch-side operand tile (two accumulators in TMEM, 2 x 4 MMAs per stage), which cuts the activation bytes every SM has to
+// ingest -- the forward / dX mainloops run at the L2->SM ingest limit (measured 0.9 - 1.0 us per 52 KB stage and SM) -- and
+// each warp group of the epilogue owns one sub-tile.  MT = 2 requires EPW = 8 and TMEM_COLS = 512.
+// F16: operands are 16-bit copies (kind::f16: fp16 weights / activations / loss-scaled gradients): a 128-byte swizzle row
+// holds 64 contraction elements, an MMA covers K = 16, an MN-major box is 64 elements x 64 contraction rows (plain 128B
+// swizzle, UMMA layout 2, SBO 1024 B, LBO 8192 B); otherwise fp32 operands read as tf32 (32 elements per row, K = 8 per
+// MMA, MN-major boxes of 32 x 32 with the 32-byte-atom swizzle, UMMA layout 1, SBO 512 B, LBO 4096 B).  Compile-time,
+// so every descriptor constant folds and the single-thread producer / issuer loops unroll.
+template <bool A_MN, bool B_MN, int STAGES, int TMEM_COLS, int MINB, int EPW, int MT, bool F16>
 __global__ void __launch_bounds__(64 + 32 * EPW, MINB)
 k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_override, AdamHyper hp, OperandMode om) {
   using namespace tc;
   pdl_launch_dependents();
+#ifdef MRGAN_PHASE_TIMING
+  const unsigned long long pt_t0 = gtimer();
+#endif
+  constexpr int KBLK = F16 ? 64 : 32;                 // contraction elements per stage (one 128-byte row)
+  constexpr uint32_t MN_BOX = F16 ? 8192u : 4096u;    // bytes of one MN-major box (KBLK elements x KBLK contraction rows)
   // dW (B_MN) kernels take the number of contraction slices in `rows_override`: blockIdx.z = fold * ksplit + slice, each
   // slice stores its partial product to op.ws (deterministic split-K: a fold's dW of the narrow layers is one or two
   // tiles, which would leave a large-batch contraction of thousands of rows on one or two SMs)
@@ -187,13 +267,13 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   uint64_t* empty = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+#ifdef MRGAN_PHASE_TIMING
+  unsigned long long* pt = reinterpret_cast<unsigned long long*>(bars + 16);     // inside the 256-byte slack after the barriers
+  if (threadIdx.x == 0) pt[0] = pt_t0;
+#endif
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // 16-bit operands: a 128-byte swizzle row holds 64 contraction elements, an MMA covers K = 16, an MN-major box is
-  // 64 elements x 64 contraction rows (plain 128B swizzle, UMMA layout 2, SBO = 1024 B, LBO = 8192 B)
-  const bool f16 = op.esz == 2;
-  const int kblk = f16 ? 64 : TC_KBLK;
-  const int nkb_all = (KE + kblk - 1) / kblk;
+  const int nkb_all = (KE + KBLK - 1) / KBLK;
   const int kb_per = (nkb_all + ksplit - 1) / ksplit;
   const int kb0 = kslice * kb_per;                           // the host picks ksplit so that no slice is empty
   const int nkb = min(nkb_all, kb0 + kb_per) - kb0;
@@ -214,6 +294,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   fence_after();
   const uint32_t tmem_base = *tmem_holder;
   pdl_wait();                             // everything above overlapped the previous kernel's tail
+  if (threadIdx.x == 0) PT_MARK(1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -225,16 +306,16 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         mbar_expect_tx(&full[s], stage_bytes);
         uint8_t* sa = smem + (size_t)s * stage_bytes;
         uint8_t* sb = sa + a_bytes;
-        const int k0 = (kb0 + kb) * kblk;
-        const int bbytes = f16 ? 8192 : 4096;        // one MN-major box: kblk elements wide x kblk contraction rows
+        const int k0 = (kb0 + kb) * KBLK;
         if (A_MN) {
-          for (int b = 0; b < (128 / kblk) * MT; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * bbytes, m0 + kblk * b, k0);
+#pragma unroll
+          for (int b = 0; b < (128 / KBLK) * MT; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * MN_BOX, m0 + KBLK * b, k0);
         } else {
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) tma_load_2d(&op.mapA, &full[s], sa + mt * 16384, k0, m0 + 128 * mt);
         }
         if (B_MN) {
-          for (int b = 0; b < bn / kblk; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * bbytes, n0 + kblk * b, k0);
+          for (int b = 0; b < bn / KBLK; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * MN_BOX, n0 + KBLK * b, k0);
         } else {
           tma_load_2d(&op.mapB, &full[s], sb, k0, n0);
         }
@@ -243,34 +324,36 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      // instruction descriptor operand formats: 0 = f16, 1 = bf16, 2 = tf32; D format 1 = f32
-      const uint32_t fmtA = f16 ? (uint32_t)op.afmt : 2u, fmtB = f16 ? (uint32_t)op.bfmt : 2u;
-      const uint32_t idesc = (1u << 4) | (fmtA << 7) | (fmtB << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+      // instruction descriptor: D format f32 (1 << 4); operand formats (bits 7-9 / 10-12): 0 = f16, 2 = tf32; majors; N >> 3; M >> 4
+      constexpr uint32_t fmt = F16 ? 0u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t mn_lbo = f16 ? 8192u : 4096u, mn_sbo = f16 ? 1024u : 512u, mn_lay = f16 ? 2u : 1u, mn_step = f16 ? 2048u : 1024u;
-      const uint32_t lboA = A_MN ? mn_lbo : 16u, lboB = B_MN ? mn_lbo : 16u;
-      const uint32_t sboA = A_MN ? mn_sbo : 1024u, sboB = B_MN ? mn_sbo : 1024u;
-      const uint32_t layA = A_MN ? mn_lay : 2u, layB = B_MN ? mn_lay : 2u;
-      const uint32_t stepA = A_MN ? mn_step : 32u, stepB = B_MN ? mn_step : 32u;   // bytes per MMA (8 tf32 / 16 f16 contraction elements)
+      constexpr uint32_t mn_lbo = MN_BOX, mn_sbo = F16 ? 1024u : 512u, mn_lay = F16 ? 2u : 1u, mn_step = F16 ? 2048u : 1024u;
+      constexpr uint32_t lboA = A_MN ? mn_lbo : 16u, lboB = B_MN ? mn_lbo : 16u;
+      constexpr uint32_t sboA = A_MN ? mn_sbo : 1024u, sboB = B_MN ? mn_sbo : 1024u;
+      constexpr uint32_t layA = A_MN ? mn_lay : 2u, layB = B_MN ? mn_lay : 2u;
+      constexpr uint32_t stepA = A_MN ? mn_step : 32u, stepB = B_MN ? mn_step : 32u;   // bytes per MMA (8 tf32 / 16 f16 contraction elements)
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&full[s], ph);
+        if (kb == 0) PT_MARK(2);
         fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
 #pragma unroll
-        for (int k = 0; k < TC_KBLK / 8; ++k) {
+        for (int k = 0; k < 4; ++k) {            // 4 MMAs per stage and sub-tile in both formats
           const uint64_t db = smem_desc(sb + k * stepB, lboB, sboB, layB);
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {      // sub-tile mt: A block at +16 KB, accumulator at TMEM column 256 * mt
             const uint64_t da = smem_desc(sa + mt * 16384u + k * stepA, lboA, sboA, layA);
-            if (f16) mma_f16(tmem_base + 256u * mt, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (F16) mma_f16(tmem_base + 256u * mt, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             else mma_tf32(tmem_base + 256u * mt, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
         }
         mma_commit(&empty[s]);            // frees the smem stage when these MMAs retire
       }
       mma_commit(tmem_full);              // accumulator complete
+      PT_MARK(3);
     }
   } else {
     // ===================== epilogue (EPW warps; a warp may only touch TMEM lanes 32*(warp%4)..+31) =====================
@@ -282,195 +365,77 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
     const int f = m0 + 128 * sub + lane_base + lane;      // this thread's feature index (MMA-M)
     const bool f_ok = f < ME;
     const GemmDesc g = op.g;             // by value: descriptor fields must not be re-read from HBM around every store
-    const float debias = f16 ? 1.0f : TF32_TRUNC_DEBIAS;   // fp16 operand copies are rounded to nearest: nothing to remove
-    const int epi = op.epi;
-    float* const adamP = op.P; float* const adamM = op.Mo; float* const adamV = op.Vo;
+    constexpr float debias = F16 ? 1.0f : TF32_TRUNC_DEBIAS;   // fp16 operand copies are rounded to nearest: nothing to remove
     const int ncols = min(min(bn, NE - n0), cbeg + chalf);      // this warp's column range is [cbeg, ncols)
     const uint32_t trow = tmem_base + 256u * sub + ((uint32_t)lane_base << 16);
-    uint32_t key0 = 0, key1 = 0, step = 0;
-    float lr_t = 0.f;
-    const bool noisy = (epi == EPI_FWD) && g.C2 != nullptr && g.sigma != 0.f;
-    if (noisy || epi == EPI_ADAM) {
-      const FoldState& fs = folds[g.fold];
-      key0 = fs.key0; key1 = fs.key1; step = (uint32_t)fs.rng_step; lr_t = fs.lr_t[op.net];
-    }
+    // TMEM columns the accumulators leave free: scratch of this warp group (sub-tile s owns [256 s + bn, 256 s + 256); with
+    // one sub-tile the warp groups share [bn, TMEM_COLS)), in whole 16-column chunks
+    int fbeg, flen;
+    if (MT == 2) { fbeg = 256 * sub + bn; flen = (256 - bn) & ~15; }
+    else { flen = ((TMEM_COLS - bn) / (EPW == 8 ? 2 : 1)) & ~15; fbeg = bn + wg * flen; }
+    const uint32_t tfree = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)fbeg;
+    const int nchunks = (ncols - cbeg + 15) >> 4;               // 16-row chunks of this warp's range (<= 0: nothing to do)
+    const int npark = max(min(flen >> 4, nchunks), 0);          // chunks whose noise / h values fit the free columns
 
-    if (epi == EPI_ADAM) {
-      // Keras-2.0.9 Adam fused into the dW epilogue: the gradient never leaves the SM.  Accumulator D[n = f, k];
-      // the weight tensor is [k, n] row-major, so for a fixed k the 32 lanes touch one 128-byte line of each of
-      // W, m, v.  The three streams are register double-buffered one 16-column chunk ahead, and the first chunk
-      // is requested BEFORE the accumulator is ready, so HBM latency overlaps the TMA/MMA phase.
-      const float b1 = hp.b1, b2 = hp.b2, c1 = 1.0f - hp.b1, c2 = 1.0f - hp.b2, eps = hp.eps;
-      const float ginv_a = (om.mode == 2) ? 1.0f / om.gscale : 1.0f;      // the dZ operand carries the loss scale
-      // 8-column chunks: 2 x 24 prefetch registers keep the kernel under the 2-CTA/SM register budget (no spills,
-      // which would force every load to be waited for immediately)
-      auto fetch = [&](int c0, float (&pw)[8], float (&pm)[8], float (&pv)[8]) {
+    if constexpr (B_MN) {
+      // ------------------------------------------------------------------ dW: fused Adam (LSU variant) or plain store
+      const int epi = op.epi;
+      if (epi == EPI_ADAM) {
+        // Keras-2.0.9 Adam fused into the dW epilogue: the gradient never leaves the SM.  Accumulator D[n = f, k];
+        // the weight tensor is [k, n] row-major, so for a fixed k the 32 lanes touch one 128-byte line of each of
+        // W, m, v.  The three streams are register double-buffered one 8-column chunk ahead, and the first chunk
+        // is requested BEFORE the accumulator is ready, so HBM latency overlaps the TMA/MMA phase.  (A/B variant of
+        // k_dw_adam_tc, which stages the optimizer state by TMA instead: MRGAN_ADAM_TMA=0.)
+        float* const adamP = op.P; float* const adamM = op.Mo; float* const adamV = op.Vo;
+        const float lr_t = folds[g.fold].lr_t[op.net];
+        const float b1 = hp.b1, b2 = hp.b2, c1 = 1.0f - hp.b1, c2 = 1.0f - hp.b2, eps = hp.eps;
+        const float ginv_a = F16 ? 1.0f / om.gscale : 1.0f;      // the dZ operand carries the loss scale
+        auto fetch = [&](int c0, float (&pw)[8], float (&pm)[8], float (&pv)[8]) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (f_ok && c0 + j < ncols) {
-            const size_t idx = (size_t)(n0 + c0 + j) * g.ldc + f;
-            pw[j] = __ldcs(adamP + idx); pm[j] = __ldcs(adamM + idx); pv[j] = __ldcs(adamV + idx);
-          }
-        }
-      };
-      auto apply = [&](int c0, const float (&v)[8], const float (&pw)[8], const float (&pm)[8], const float (&pv)[8]) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (f_ok && c0 + j < ncols) {
-            const size_t idx = (size_t)(n0 + c0 + j) * g.ldc + f;
-            const float gr = v[j] * ginv_a;
-            const float m = fmaf(b1, pm[j], c1 * gr), vv = fmaf(b2, pv[j], c2 * gr * gr);
-            __stcs(adamM + idx, m); __stcs(adamV + idx, vv);
-            const float w = pw[j] - lr_t * __fdividef(m, sqrtf(vv) + eps);
-            __stcs(adamP + idx, w);
-            if (om.mode == 2) om.hbase[adamP + idx - om.fbase] = __float2half_rn(w);
-          }
-        }
-      };
-      float pwA[8], pmA[8], pvA[8], pwB[8], pmB[8], pvB[8], v[8];
-      fetch(cbeg, pwA, pmA, pvA);
-      fetch(cbeg + 8, pwB, pmB, pvB);
-      mbar_wait(tmem_full, 0);
-      fence_after();
-      for (int c0 = cbeg; c0 < ncols; c0 += 16) {
-        tmem_ld8(trow + (uint32_t)c0, v);
-        apply(c0, v, pwA, pmA, pvA);
-        if (c0 + 16 < ncols) fetch(c0 + 16, pwA, pmA, pvA);
-        if (c0 + 8 < ncols) {
-          tmem_ld8(trow + (uint32_t)(c0 + 8), v);
-          apply(c0 + 8, v, pwB, pmB, pvB);
-          if (c0 + 24 < ncols) fetch(c0 + 24, pwB, pmB, pvB);
-        }
-      }
-    } else if (epi == EPI_DX) {
-      // dZ_prev[r, f] = acc * act'(h_prev[r, f]); h is prefetched one chunk ahead (and before the accumulator is ready)
-      auto fetch = [&](int c0, float (&av)[16]) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          av[j] = (f_ok && g.act != ACT_NONE && c0 + j < ncols) ? __ldg(g.aux + (size_t)(n0 + c0 + j) * g.ldaux + f) : 1.0f;
-      };
-      auto apply = [&](int c0, const float (&v)[16], const float (&av)[16]) {
-        if (!f_ok) return;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          if (c0 + j >= ncols) break;
-          float x = v[j] * debias;
-          if (g.act == ACT_RELU) x = (av[j] > 0.f) ? x : 0.f;
-          else if (g.act == ACT_SOFTPLUS) x *= 1.0f - __expf(-av[j]);
-          float* const pc = g.C + (size_t)(n0 + c0 + j) * g.ldc + f;
-          if (om.mode == 2 && (g.rnd & 1)) put_grad16(om.hbase + (pc - om.fbase), x, om);    // operand only: 16-bit copy, loss-scaled like acc
-          else *pc = (g.rnd & 1) ? rna_tf32(x) : x;
-        }
-      };
-      // The h values do not depend on the accumulator either: whole 16-row chunks of them are loaded while the mainloop
-      // runs and parked in the free TMEM columns (same split as the forward epilogue's noise); what does not fit is
-      // register-prefetched one chunk ahead as before.
-      float avA[16], avB[16], v[16];
-      int cpk = cbeg;                                   // rows [cbeg, cpk) of this thread's range are parked
-      uint32_t taux = 0;
-      if (g.act != ACT_NONE) {
-        int fbeg, flen;
-        if (MT == 2) { fbeg = 256 * sub + bn; flen = 256 - bn; }
-        else { flen = ((TMEM_COLS - bn) / (EPW == 8 ? 2 : 1)) & ~15; fbeg = bn + wg * flen; }
-        const int nchunk = min(flen >> 4, (ncols - cbeg + 15) >> 4);
-        taux = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)fbeg;
-        if (nchunk > 0) {
-          fetch(cbeg, avA);
-          for (int k = 0; k < nchunk; k += 2) {
-            if (k + 1 < nchunk) fetch(cbeg + 16 * (k + 1), avB);
-            tmem_st16(taux + 16u * (uint32_t)k, avA);
-            if (k + 1 < nchunk) {
-              if (k + 2 < nchunk) fetch(cbeg + 16 * (k + 2), avA);
-              tmem_st16(taux + 16u * (uint32_t)(k + 1), avB);
+          for (int j = 0; j < 8; ++j) {
+            if (f_ok && c0 + j < ncols) {
+              const size_t idx = (size_t)(n0 + c0 + j) * g.ldc + f;
+              pw[j] = __ldcs(adamP + idx); pm[j] = __ldcs(adamM + idx); pv[j] = __ldcs(adamV + idx);
             }
           }
-          tmem_wait_st();
-          cpk = cbeg + 16 * nchunk;
-        }
-      }
-      if (cpk < ncols) fetch(cpk, avA);
-      mbar_wait(tmem_full, 0);
-      fence_after();
-      for (int c0 = cbeg; c0 < min(cpk, ncols); c0 += 16) {
-        tmem_ld16(trow + (uint32_t)c0, v);
-        tmem_ld16(taux + (uint32_t)(c0 - cbeg), avB);
-        apply(c0, v, avB);
-      }
-      for (int c0 = cpk; c0 < ncols; c0 += 32) {
-        tmem_ld16(trow + (uint32_t)c0, v);
-        if (c0 + 16 < ncols) fetch(c0 + 16, avB);
-        apply(c0, v, avA);
-        if (c0 + 16 < ncols) {
-          tmem_ld16(trow + (uint32_t)(c0 + 16), v);
-          if (c0 + 32 < ncols) fetch(c0 + 32, avA);
-          apply(c0 + 16, v, avB);
-        }
-      }
-    } else {
-      // GaussianNoise of the next layer's input (EPI_FWD with C2): the draws do not depend on the accumulator, and the
-      // epilogue warps are idle while the TMA/MMA warps run the mainloop -- so they draw now and park the values in the
-      // TMEM columns the accumulator leaves free (sub-tile s owns columns [256 s + bn, 256 s + 256); with one sub-tile the
-      // two warp groups share [bn, TMEM_COLS)).  Row groups that do not fit are drawn in the epilogue as before.
-      int npre = 0;
-      uint32_t tnoise = 0;
-      if (epi == EPI_FWD && noisy && ((g.row0 + n0 + cbeg) & 3) == 0 && (hp.dp_bg == hp.dp_bloc || (hp.dp_bloc & 3) == 0)) {
-        int fbeg, flen;
-        if (MT == 2) { fbeg = 256 * sub + bn; flen = 256 - bn; }
-        else { flen = ((TMEM_COLS - bn) / (EPW == 8 ? 2 : 1)) & ~3; fbeg = bn + wg * flen; }
-        npre = min(flen >> 2, (ncols - cbeg + 3) >> 2);
-        tnoise = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)fbeg;
-        for (int gi = 0; gi < npre; ++gi) {
-          float nz[4];
-          normal4(key0, key1, (uint32_t)global_row(g.row0 + n0 + cbeg + 4 * gi, hp) >> 2, (uint32_t)f, step, (uint32_t)g.tid, nz);
-          tmem_st4(tnoise + 4u * (uint32_t)gi, nz);
-        }
-        if (npre > 0) tmem_wait_st();
-      }
-      mbar_wait(tmem_full, 0);
-      fence_after();
-      for (int c0 = cbeg; c0 < ncols; c0 += 16) {
-        float v[16];
-        tmem_ld16(trow + (uint32_t)c0, v);                   // warp-collective: every lane takes part
-        if (epi == EPI_FWD) {
-          // rows r = n0 + c0 + j; noise is grouped by 4 consecutive rows of one column (= this feature)
+        };
+        auto apply = [&](int c0, const float (&v)[8], const float (&pw)[8], const float (&pm)[8], const float (&pv)[8]) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int r0 = n0 + c0 + 4 * q;
-            if (r0 >= NE) break;
-            float nz[4] = {0.f, 0.f, 0.f, 0.f};
-            if (noisy) {
-              const int gi = ((c0 - cbeg) >> 2) + q;
-              if (gi < npre)                                 // warp-uniform: the TMEM load stays convergent
-                tmem_ld4(tnoise + 4u * (uint32_t)gi, nz);
-              else if (((g.row0 + r0) & 3) == 0 && (hp.dp_bg == hp.dp_bloc || (hp.dp_bloc & 3) == 0))
-                normal4(key0, key1, (uint32_t)global_row(g.row0 + r0, hp) >> 2, (uint32_t)f, step, (uint32_t)g.tid, nz);
-              else
-                for (int i = 0; i < 4; ++i) nz[i] = normal1(key0, key1, (uint32_t)global_row(g.row0 + r0 + i, hp), (uint32_t)f, step, (uint32_t)g.tid);
-            }
-            if (!f_ok) continue;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = r0 + i;
-              if (r >= NE) break;
-              float x = v[4 * q + i] * debias;
-              if (g.act == ACT_RELU) x = fmaxf(x, 0.f);
-              else if (g.act == ACT_SOFTPLUS) x = softplusf(x);
-              if (g.C) {            // clean activation: kept in fp32 (act' of the backward pass, feature matching) ...
-                float* const pc = g.C + (size_t)r * g.ldc + f;
-                *pc = ((g.rnd & 1) && om.mode == 1) ? rna_tf32(x) : x;
-                if (om.mode == 2 && (g.rnd & 1)) om.hbase[pc - om.fbase] = __float2half_rn(x);     // ... plus its operand copy
-              }
-              if (g.C2) {           // noisy activation: only ever a GEMM operand
-                const float y = x + g.sigma * nz[i];
-                float* const pc2 = g.C2 + (size_t)r * g.ldc2 + f;
-                if (om.mode == 2 && (g.rnd & 2)) om.hbase[pc2 - om.fbase] = __float2half_rn(y);
-                else *pc2 = (g.rnd & 2) ? rna_tf32(y) : y;
-              }
+          for (int j = 0; j < 8; ++j) {
+            if (f_ok && c0 + j < ncols) {
+              const size_t idx = (size_t)(n0 + c0 + j) * g.ldc + f;
+              const float gr = v[j] * ginv_a;
+              const float m = fmaf(b1, pm[j], c1 * gr), vv = fmaf(b2, pv[j], c2 * gr * gr);
+              __stcs(adamM + idx, m); __stcs(adamV + idx, vv);
+              const float w = pw[j] - lr_t * __fdividef(m, sqrtf(vv) + eps);
+              __stcs(adamP + idx, w);
+              if (F16) om.hbase[adamP + idx - om.fbase] = __float2half_rn(w);
             }
           }
-        } else {   // EPI_STORE: dW into the flat gradient buffer (data-parallel mode: all-reduced before Adam)
+        };
+        float pwA[8], pmA[8], pvA[8], pwB[8], pmB[8], pvB[8], v[8];
+        fetch(cbeg, pwA, pmA, pvA);
+        fetch(cbeg + 8, pwB, pmB, pvB);
+        mbar_wait(tmem_full, 0);
+        fence_after();
+        for (int c0 = cbeg; c0 < ncols; c0 += 16) {
+          tmem_ld8(trow + (uint32_t)c0, v);
+          apply(c0, v, pwA, pmA, pvA);
+          if (c0 + 16 < ncols) fetch(c0 + 16, pwA, pmA, pvA);
+          if (c0 + 8 < ncols) {
+            tmem_ld8(trow + (uint32_t)(c0 + 8), v);
+            apply(c0 + 8, v, pwB, pmB, pvB);
+            if (c0 + 24 < ncols) fetch(c0 + 24, pwB, pmB, pvB);
+          }
+        }
+      } else {   // EPI_STORE: dW into the flat gradient buffer (data-parallel / large-batch mode: all-reduced before Adam)
+        mbar_wait(tmem_full, 0);
+        fence_after();
+        float* const dst = ksplit > 1 ? op.ws + (size_t)kslice * op.ws_stride : g.C;
+        for (int c0 = cbeg; c0 < ncols; c0 += 16) {
+          float v[16];
+          tmem_ld16(trow + (uint32_t)c0, v);                   // warp-collective: every lane takes part
           if (!f_ok) continue;
-          float* const dst = ksplit > 1 ? op.ws + (size_t)kslice * op.ws_stride : g.C;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int k = n0 + c0 + j;
@@ -479,15 +444,164 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
           }
         }
       }
+    } else if constexpr (!A_MN) {
+      // ------------------------------------------------------------------ dX: dZ_prev[r, f] = acc * act'(h_prev[r, f])
+      // The h values do not depend on the accumulator: whole 16-row chunks of them are loaded while the mainloop runs and
+      // parked in the free TMEM columns; chunks that do not fit are register-prefetched one chunk ahead.  Per chunk the
+      // accumulator and the parked values are fetched with two TMEM loads behind ONE wait.
+      const bool has_act = g.act != ACT_NONE;
+      auto fetch = [&](int c0, float (&av)[16]) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          av[j] = (f_ok && has_act && c0 + j < ncols) ? __ldg(g.aux + (size_t)(n0 + c0 + j) * g.ldaux + f) : 1.0f;
+      };
+      float avA[16], avB[16];
+      const int npk = has_act ? npark : 0;
+      if (npk > 0) {
+        fetch(cbeg, avA);
+        for (int k = 0; k < npk; k += 2) {
+          if (k + 1 < npk) fetch(cbeg + 16 * (k + 1), avB);
+          tmem_st16(tfree + 16u * (uint32_t)k, avA);
+          if (k + 1 < npk) {
+            if (k + 2 < npk) fetch(cbeg + 16 * (k + 2), avA);
+            tmem_st16(tfree + 16u * (uint32_t)(k + 1), avB);
+          }
+        }
+        tmem_wait_st();
+      }
+      if (has_act && npk < nchunks) fetch(cbeg + 16 * npk, avA);
+      mbar_wait(tmem_full, 0);
+      fence_after();
+      __half* const hC = F16 ? om.hbase + (g.C - om.fbase) : nullptr;
+      const bool op_only = (g.rnd & 1) != 0;                      // the result is only ever a GEMM operand
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int c0 = cbeg + 16 * ch;
+        uint32_t va[16], vh[16];
+        tmem_ld16_issue(trow + (uint32_t)c0, va);
+        if (ch < npk) tmem_ld16_issue(tfree + 16u * (uint32_t)ch, vh);
+        tmem_wait_ld();
+        tmem_fence16(va);
+        float av[16];
+        if (ch < npk) {
+          tmem_fence16(vh);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) av[j] = __uint_as_float(vh[j]);
+        } else if (has_act) {
+          const bool odd = ((ch - npk) & 1) != 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) av[j] = odd ? avB[j] : avA[j];
+          if (ch + 1 < nchunks) { if (odd) fetch(c0 + 16, avA); else fetch(c0 + 16, avB); }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) av[j] = 1.0f;
+        }
+        if (!f_ok) continue;
+        const size_t o0 = (size_t)(n0 + c0) * g.ldc + f;
+        const int nrows = ncols - c0;
+        float* const pC = g.C + o0;
+        __half* const phC = F16 ? hC + o0 : nullptr;
+        if (g.act == ACT_RELU) dx_rows<F16, ACT_RELU>(va, av, nrows, pC, phC, g.ldc, op_only);
+        else if (g.act == ACT_SOFTPLUS) dx_rows<F16, ACT_SOFTPLUS>(va, av, nrows, pC, phC, g.ldc, op_only);
+        else dx_rows<F16, ACT_NONE>(va, av, nrows, pC, phC, g.ldc, op_only);
+      }
+    } else {
+      // ------------------------------------------------------------------ forward: act, optional clean copy, noisy copy
+      // GaussianNoise of the next layer's input (C2): the draws do not depend on the accumulator, and the epilogue warps are
+      // idle while the TMA / MMA warps run the mainloop -- so they draw now and park whole 16-row chunks in the free TMEM
+      // columns.  Chunks that do not fit are drawn in the epilogue BETWEEN issuing the accumulator's TMEM load and waiting
+      // for it, so the Philox rounds hide the load latency; per chunk there is one wait for both TMEM loads.
+      const bool noisy = g.C2 != nullptr && g.sigma != 0.f;
+      uint32_t key0 = 0, key1 = 0, step = 0;
+      if (noisy) { const FoldState& fs = folds[g.fold]; key0 = fs.key0; key1 = fs.key1; step = (uint32_t)fs.rng_step; }
+      // 4-row noise groups must not straddle row-section or rank boundaries (oracle/philox.py): otherwise per-element draws
+      const bool grp = ((g.row0 + n0 + cbeg) & 3) == 0 && (hp.dp_bg == hp.dp_bloc || (hp.dp_bloc & 3) == 0);
+      auto draw16 = [&](int c0, float (&nz)[16]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int r0 = g.row0 + n0 + c0 + 4 * q;
+          if (grp) {
+            const float4 n4 = noise4_call(key0, key1, r0, (uint32_t)f, step, (uint32_t)g.tid, hp.dp_bloc, hp.dp_bg, hp.dp_rank);
+            nz[4 * q] = n4.x; nz[4 * q + 1] = n4.y; nz[4 * q + 2] = n4.z; nz[4 * q + 3] = n4.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              nz[4 * q + i] = noise1_call(key0, key1, r0 + i, (uint32_t)f, step, (uint32_t)g.tid, hp.dp_bloc, hp.dp_bg, hp.dp_rank);
+          }
+        }
+      };
+      const int npk = (noisy && grp) ? npark : 0;
+      for (int ch = 0; ch < npk; ++ch) {
+        float nz[16];
+        draw16(cbeg + 16 * ch, nz);
+        tmem_st16(tfree + 16u * (uint32_t)ch, nz);
+      }
+      if (npk > 0) tmem_wait_st();
+      if (warp == 2 && lane == 0) PT_MARK(4);
+      mbar_wait(tmem_full, 0);
+      if (warp == 2 && lane == 0) PT_MARK(5);
+      fence_after();
+      __half* const hC = (F16 && g.C) ? om.hbase + (g.C - om.fbase) : nullptr;
+      __half* const hC2 = (F16 && g.C2) ? om.hbase + (g.C2 - om.fbase) : nullptr;
+      const bool c_op = (g.rnd & 1) != 0, c2_op = (g.rnd & 2) != 0;   // C / C2 feed a tensor-core GEMM as operands
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int c0 = cbeg + 16 * ch;
+        uint32_t va[16], vn[16];
+        float nz[16];
+        tmem_ld16_issue(trow + (uint32_t)c0, va);
+        if (ch < npk) tmem_ld16_issue(tfree + 16u * (uint32_t)ch, vn);
+#ifdef MRGAN_EXP_NODRAW
+        else if (noisy) { for (int j = 0; j < 16; ++j) nz[j] = 0.f; }
+#else
+        else if (noisy) draw16(c0, nz);                        // overlaps the accumulator load
+#endif
+        tmem_wait_ld();
+        tmem_fence16(va);
+        if (ch < npk) {
+          tmem_fence16(vn);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) nz[j] = __uint_as_float(vn[j]);
+        }
+        if (!f_ok) continue;
+        const size_t o0 = (size_t)(n0 + c0) * g.ldc + f, o20 = (size_t)(n0 + c0) * g.ldc2 + f;
+        const int nrows = ncols - c0;
+        float* const pC = g.C ? g.C + o0 : nullptr;
+        float* const pC2 = g.C2 ? g.C2 + o20 : nullptr;
+        __half* const phC = hC ? hC + o0 : nullptr;
+        __half* const phC2 = hC2 ? hC2 + o20 : nullptr;
+        if (!noisy) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) nz[j] = 0.f;
+        }
+#define FWD_ROWS(ACT, HC, HC2) fwd_rows<F16, ACT, HC, HC2>(va, nz, nrows, pC, phC, g.ldc, c_op, pC2, phC2, g.ldc2, c2_op, g.sigma)
+#define FWD_ACT(HC, HC2)                                                     \
+        do {                                                                 \
+          if (g.act == ACT_RELU) FWD_ROWS(ACT_RELU, HC, HC2);                \
+          else if (g.act == ACT_SOFTPLUS) FWD_ROWS(ACT_SOFTPLUS, HC, HC2);   \
+          else FWD_ROWS(ACT_NONE, HC, HC2);                                  \
+        } while (0)
+        if (g.C && g.C2) FWD_ACT(true, true);
+        else if (g.C) FWD_ACT(true, false);
+        else if (g.C2) FWD_ACT(false, true);
+#undef FWD_ACT
+#undef FWD_ROWS
+      }
     }
   }
 
+  if (warp == 2 && lane == 0) PT_MARK(6);
   fence_before();
   __syncthreads();
   if (warp == 1) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
   }
+#ifdef MRGAN_PHASE_TIMING
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && (blockIdx.z % 24) == 0) {
+    const unsigned long long te = gtimer();
+    printf("PT z=%d grid=(%d,%d,%d) nkb=%d t0=%llu setup=%llu first=%llu mma_issued=%llu noise=%llu acc=%llu epi=%llu end=%llu\n", (int)blockIdx.z,
+           (int)gridDim.x, (int)gridDim.y, (int)gridDim.z, nkb, pt[0], pt[1] - pt[0], pt[2] - pt[0], pt[3] - pt[0], pt[4] - pt[0], pt[5] - pt[0], pt[6] - pt[0], te - pt[0]);
+  }
+#endif
 }
 
 // Sums the `ks` contraction slices of a split-K dW in slice order (bitwise reproducible) into the gradient tensor.
@@ -514,24 +628,23 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const TcOp* __restrict__ 
 // W, m and v tiles never go through the LSU: one thread streams them HBM -> smem -> HBM in [KC rows x 128 cols]
 // chunks with cp.async.bulk.tensor (full 128-byte lines, deep queues); the 4 epilogue warps combine each chunk
 // with the matching 8 accumulator columns from TMEM in shared memory.  24 B per parameter of HBM traffic, which
-// is the algorithmic minimum for Adam; the gradient never leaves the SM.
-//   smem: 2 operand stages x 32 KB + NB chunk buffers x (3 x KC x 512 B); 2 CTAs per SM.
+// is the algorithmic minimum for Adam; the gradient never leaves the SM.  F16 (operand-copy mode): the operands are the
+// 16-bit copies (64 contraction rows per stage) and every chunk also carries the fp16 copy of the UPDATED weights that the
+// next forward / dX pass reads (written to smem by the epilogue, stored by TMA: +2 B per parameter).
+//   smem: 2 operand stages x 32 KB + NB chunk buffers x (3 x KC x 512 B [+ KC x 256 B]); 2 CTAs per SM.
 // ====================================================================================================
 struct alignas(64) TcAdamOp {
-  CUtensorMap mapA, mapB;          // dZ[r, n] and A[r, k], both MN-major operands (32-byte-atom 128B swizzle)
+  CUtensorMap mapA, mapB;          // dZ[r, n] and A[r, k], both MN-major operands
   CUtensorMap mapP, mapM, mapV;    // Waug, m, v as [rows k, cols n], box = 128 cols x KC rows, no swizzle
+  CUtensorMap mapH;                // fp16 copy of Waug, same geometry (F16 only)
   int ME, NE, KE;                  // out-features n, in-features(+1) k, contraction rows r
   int fold;
   int net;
-  int esz;                         // operand element size (4 = tf32, 2 = fp16 copies)
-  int afmt;                        // esz == 2: format of the dZ operand (0 = f16, 1 = bf16); the activation operand is f16
-  int ldh;                         // pitch of W and of its fp16 operand copy
-  float ginv;                      // 1 / loss scale carried by the dZ operand (1 unless fp16)
-  __half* Ph;                      // fp16 operand copy of W, refreshed with every update (null unless fp16)
+  float ginv;                      // 1 / loss scale carried by the dZ operand (1 unless fp16 copies)
 };
 
 #define TCA_KC 8
-#define TCA_NB 4
+#define TCA_NB 4                   // dedicated chunk buffers (tf32); the F16 variant's chunks are 2 KB larger and it takes 3
 
 namespace tc {
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
@@ -546,17 +659,27 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 }  // namespace tc
 
+template <bool F16> struct TcAdamCfg {
+  static constexpr int STAGES = 2, KC = TCA_KC, NB = F16 ? 3 : TCA_NB;
+  static constexpr uint32_t STAGE_BYTES = 2 * 128 * 128;                    // A + B operand tiles
+  static constexpr uint32_t ARR_BYTES = KC * 128 * 4;                       // one array (W, m or v) of one chunk
+  static constexpr uint32_t HALF_BYTES = F16 ? KC * 128 * 2 : 0;            // fp16 copy of the chunk's updated weights
+  static constexpr uint32_t CHUNK_BYTES = 3 * ARR_BYTES + HALF_BYTES;
+  static constexpr int NX = (STAGES * STAGE_BYTES) / CHUNK_BYTES;           // chunk buffers carved out of the operand stages later
+  static constexpr int NBUF = NB + NX;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (size_t)NB * CHUNK_BYTES + 256;
+};
+
+template <bool F16>
 __global__ void __launch_bounds__(192, 2)
 k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, AdamHyper hp) {
   using namespace tc;
+  using Cfg = TcAdamCfg<F16>;
   pdl_launch_dependents();
-  constexpr int STAGES = 2, KC = TCA_KC, NB = TCA_NB;
-  constexpr uint32_t STAGE_BYTES = 2 * 128 * 128;            // A (4 x 4 KB blocks) + B (4 x 4 KB blocks)
-  constexpr uint32_t ARR_BYTES = KC * 128 * 4;               // one array (W, m or v) of one chunk
-  constexpr uint32_t CHUNK_BYTES = 3 * ARR_BYTES;
-  // chunk buffers: NB dedicated ones + NX carved out of the operand stages once the MMAs have consumed them
-  constexpr int NX = (STAGES * STAGE_BYTES) / CHUNK_BYTES;
-  constexpr int NBUF = NB + NX;
+  constexpr int STAGES = Cfg::STAGES, KC = Cfg::KC, NB = Cfg::NB, NBUF = Cfg::NBUF;
+  constexpr uint32_t STAGE_BYTES = Cfg::STAGE_BYTES, ARR_BYTES = Cfg::ARR_BYTES, CHUNK_BYTES = Cfg::CHUNK_BYTES;
+  constexpr int KBLK = F16 ? 64 : 32;
+  constexpr uint32_t MN_BOX = F16 ? 8192u : 4096u;
   const TcAdamOp& op = ops[blockIdx.z];
   const int ME = op.ME, NE = op.NE, KE = op.KE;
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;     // n-feature tile (lanes), k-feature tile (columns)
@@ -576,14 +699,13 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
   auto buf_ptr = [&](int b) -> uint8_t* { return b < NB ? cbuf + (size_t)b * CHUNK_BYTES : smem + (size_t)(b - NB) * CHUNK_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool f16 = op.esz == 2;                 // see k_gemm_tc: 64 contraction rows per stage, 8 KB MN-major boxes
-  const int kblk = f16 ? 64 : TC_KBLK;
-  const int nkb = (KE + kblk - 1) / kblk;
+  const int nkb = (KE + KBLK - 1) / KBLK;
   const int ncols = min(128, NE - n0);
   const int nch = (ncols + KC - 1) / KC;
 
   if (warp == 0 && lane == 0) {
     prefetch_map(&op.mapA); prefetch_map(&op.mapB); prefetch_map(&op.mapP); prefetch_map(&op.mapM); prefetch_map(&op.mapV);
+    if (F16) prefetch_map(&op.mapH);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     for (int b = 0; b < NBUF; ++b) { mbar_init(&cfull[b], 1); mbar_init(&cdone[b], 128); }
@@ -605,7 +727,7 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
       auto load_chunk = [&](int c) {
         const int b = c % NBUF;
         uint8_t* dst = buf_ptr(b);
-        mbar_expect_tx(&cfull[b], CHUNK_BYTES);
+        mbar_expect_tx(&cfull[b], 3 * ARR_BYTES);
         tma_load_2d(&op.mapP, &cfull[b], dst, m0, n0 + c * KC);
         tma_load_2d(&op.mapM, &cfull[b], dst + ARR_BYTES, m0, n0 + c * KC);
         tma_load_2d(&op.mapV, &cfull[b], dst + 2 * ARR_BYTES, m0, n0 + c * KC);
@@ -618,10 +740,11 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
         mbar_expect_tx(&full[s], STAGE_BYTES);
         uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
         uint8_t* sb = sa + 128 * 128;
-        const int k0 = kb * kblk;
-        const int bbytes = f16 ? 8192 : 4096;
-        for (int b = 0; b < 128 / kblk; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * bbytes, m0 + kblk * b, k0);
-        for (int b = 0; b < 128 / kblk; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * bbytes, n0 + kblk * b, k0);
+        const int k0 = kb * KBLK;
+#pragma unroll
+        for (int b = 0; b < 128 / KBLK; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * MN_BOX, m0 + KBLK * b, k0);
+#pragma unroll
+        for (int b = 0; b < 128 / KBLK; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * MN_BOX, n0 + KBLK * b, k0);
       }
       // the MMAs have consumed every operand stage once the accumulator is complete: the operand region now takes
       // NX more chunks in flight
@@ -636,6 +759,7 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
         tma_store_2d(&op.mapP, src, m0, n0 + c * KC);
         tma_store_2d(&op.mapM, src + ARR_BYTES, m0, n0 + c * KC);
         tma_store_2d(&op.mapV, src + 2 * ARR_BYTES, m0, n0 + c * KC);
+        if (F16) tma_store_2d(&op.mapH, src + 3 * ARR_BYTES, m0, n0 + c * KC);
         bulk_commit();
         if (c >= 1 && c - 1 + NBUF < nch) {
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -646,9 +770,9 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t fmtA = f16 ? (uint32_t)op.afmt : 2u, fmtB = f16 ? 0u : 2u;
-      const uint32_t idesc = (1u << 4) | (fmtA << 7) | (fmtB << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t lbo = f16 ? 8192u : 4096u, sbo = f16 ? 1024u : 512u, lay = f16 ? 2u : 1u, kstep = f16 ? 2048u : 1024u;
+      constexpr uint32_t fmt = F16 ? 0u : 2u;
+      constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      constexpr uint32_t lbo = MN_BOX, sbo = F16 ? 1024u : 512u, lay = F16 ? 2u : 1u, kstep = F16 ? 2048u : 1024u;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
@@ -658,7 +782,7 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t da = smem_desc(sa + k * kstep, lbo, sbo, lay), db = smem_desc(sb + k * kstep, lbo, sbo, lay);
-          if (f16) mma_f16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          if (F16) mma_f16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           else mma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         }
         mma_commit(&empty[s]);
@@ -673,9 +797,6 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
     const float lr_t = folds[op.fold].lr_t[op.net];
     const float b1 = hp.b1, b2 = hp.b2, c1 = 1.0f - hp.b1, c2 = 1.0f - hp.b2, eps = hp.eps;
     const float ginv = op.ginv;
-    __half* const Ph = op.Ph;
-    const int ldh = op.ldh;
-    const bool n_ok = m0 + nl < ME;
     mbar_wait(tmem_full, 0);
     fence_after();
     for (int c = 0; c < nch; ++c) {
@@ -683,20 +804,19 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
       float* sP = reinterpret_cast<float*>(buf_ptr(b));
       float* sM = sP + KC * 128;
       float* sV = sM + KC * 128;
+      __half* sH = reinterpret_cast<__half*>(sV + KC * 128);
       float g[KC];
       tmem_ld8(trow + (uint32_t)(c * KC), g);
       mbar_wait(&cfull[b], (uint32_t)(c / NBUF) & 1u);
 #pragma unroll
       for (int j = 0; j < KC; ++j) {
         const int i = j * 128 + nl;
-        const float gr = g[j] * ginv;
+        const float gr = F16 ? g[j] * ginv : g[j];
         const float m = fmaf(b1, sM[i], c1 * gr), v = fmaf(b2, sV[i], c2 * gr * gr);
         sM[i] = m; sV[i] = v;
         const float w = sP[i] - lr_t * __fdividef(m, sqrtf(v) + eps);
         sP[i] = w;
-        // fp16 operand copy of the updated weights for the next forward / dX (2 more bytes per parameter; a warp writes
-        // 64 contiguous bytes per row).  The TMA store of the fp32 tile clips at the tensor's extents; this store must too.
-        if (Ph && n_ok && c * KC + j < ncols) Ph[(size_t)(n0 + c * KC + j) * ldh + m0 + nl] = __float2half_rn(w);
+        if (F16) sH[i] = __float2half_rn(w);       // operand copy for the next forward / dX (the TMA store clips it like the fp32 tile)
       }
       fence_proxy_async();              // generic-proxy writes -> visible to the bulk store
       mbar_arrive(&cdone[b]);

@@ -97,7 +97,7 @@ struct mrgan_handle {
   cudaStream_t cmain[kMaxChains] = {nullptr}, cside[kMaxChains] = {nullptr};
   char* arena = nullptr; size_t arena_bytes = 0;
   __half* harena = nullptr;           // f16 mode: one __half per float of the arena (operand copies at the same element index)
-  OperandMode om = {0, 1.0f, nullptr, nullptr, 0};
+  OperandMode om = {0, 1.0f, nullptr, nullptr};
   float *P = nullptr, *Mo = nullptr, *Vo = nullptr, *Gr = nullptr; long long n_flat = 0;
   FoldState* d_folds = nullptr; std::vector<FoldState> h_folds;
   GemmDesc* d_descs = nullptr; std::vector<GemmDesc> h_descs;
@@ -211,11 +211,9 @@ __global__ void k_scale_buf(float* p, size_t n, float mul) {
 }
 
 // f16 mode, test hook: operand-only buffers exist as fp16 copies only; expand one (times `mul`) into a float scratch
-__global__ void k_from_half(const float* src, float* dst, size_t n, float mul, OperandMode om, int bf16) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const __half* p = om.hbase + (src + i - om.fbase);
-    dst[i] = (bf16 ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(p)) : __half2float(*p)) * mul;
-  }
+__global__ void k_from_half(const float* src, float* dst, size_t n, float mul, OperandMode om) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __half2float(om.hbase[src + i - om.fbase]) * mul;
 }
 
 // ---- buffer layout (run twice: sizing pass with base == nullptr, then for real) ----
@@ -848,19 +846,25 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 #define TC_DW_STAGES 2
 #define TC_FWD_THREADS (64 + 32 * 8)
 #define TC_DW_THREADS (64 + 32 * 4)
-#define K_TC_FWD k_gemm_tc<true, false, TC_FWD_STAGES, 256, 1, 8, 1>
-#define K_TC_FWD_N k_gemm_tc<true, false, TC_FWD_STAGES, 512, 1, 8, 1>   // all 512 TMEM columns: room to park the epilogue's noise
-#define K_TC_DX k_gemm_tc<false, false, TC_FWD_STAGES, 256, 1, 8, 1>
-#define K_TC_FWD2 k_gemm_tc<true, false, TC_FWD_STAGES, 512, 1, 8, 2>     // 256 features per CTA (layers >= 500 wide)
-#define K_TC_DX_N k_gemm_tc<false, false, TC_FWD_STAGES, 512, 1, 8, 1>
-#define K_TC_DX2 k_gemm_tc<false, false, TC_FWD_STAGES, 512, 1, 8, 2>
-#define K_TC_DW k_gemm_tc<true, true, TC_DW_STAGES, 128, 2, 4, 1>
+// kernel instantiations, indexed by the operand format F (false: fp32 operands as tf32, true: fp16 operand copies)
+#define K_TC_FWD(F) k_gemm_tc<true, false, TC_FWD_STAGES, 256, 1, 8, 1, F>
+#define K_TC_FWD_N(F) k_gemm_tc<true, false, TC_FWD_STAGES, 512, 1, 8, 1, F>   // all 512 TMEM columns: room to park the epilogue's noise
+#define K_TC_DX(F) k_gemm_tc<false, false, TC_FWD_STAGES, 256, 1, 8, 1, F>
+#define K_TC_FWD2(F) k_gemm_tc<true, false, TC_FWD_STAGES, 512, 1, 8, 2, F>     // 256 features per CTA (layers >= 500 wide)
+#define K_TC_DX_N(F) k_gemm_tc<false, false, TC_FWD_STAGES, 512, 1, 8, 1, F>
+#define K_TC_DX2(F) k_gemm_tc<false, false, TC_FWD_STAGES, 512, 1, 8, 2, F>
+#define K_TC_DW(F) k_gemm_tc<true, true, TC_DW_STAGES, 128, 2, 4, 1, F>
 // large-batch regime (more than 256 batch rows: data-parallel config 5): 256 x 256 tiles, 3-stage ring of 64 KB stages
 #define TC_BIG_STAGES 3
-#define K_TC_FWD_BIG k_gemm_tc<true, false, TC_BIG_STAGES, 512, 1, 8, 2>
-#define K_TC_DX_BIG k_gemm_tc<false, false, TC_BIG_STAGES, 512, 1, 8, 2>
-#define K_TC_DW_BIG k_gemm_tc<true, true, TC_BIG_STAGES, 512, 1, 8, 2>
-#define TCA_SMEM_BYTES (2 * 2 * 128 * 128 + TCA_NB * 3 * TCA_KC * 128 * 4 + 256)
+#define K_TC_FWD_BIG(F) k_gemm_tc<true, false, TC_BIG_STAGES, 512, 1, 8, 2, F>
+#define K_TC_DX_BIG(F) k_gemm_tc<false, false, TC_BIG_STAGES, 512, 1, 8, 2, F>
+#define K_TC_DW_BIG(F) k_gemm_tc<true, true, TC_BIG_STAGES, 512, 1, 8, 2, F>
+// launches K(false) or K(true) with identical arguments
+#define TC_LAUNCH(h, f16, K, grid, block, smem, st, ...)                          \
+  do {                                                                            \
+    if (f16) launch_k(h, K(true), grid, block, smem, st, __VA_ARGS__);            \
+    else launch_k(h, K(false), grid, block, smem, st, __VA_ARGS__);               \
+  } while (0)
 size_t tc_smem_bytes(int bn, int stages, int mt = 1) { return 1024 + (size_t)stages * ((size_t)mt * 128 * 128 + (size_t)bn * 128) + 256; }
 // two feature sub-tiles per CTA when the layer is wide enough and the 4-stage ring still fits in 227 KB
 bool tc_use_mt2(int maxME, int bn) { return maxME >= 500 && tc_smem_bytes(bn, TC_FWD_STAGES, 2) <= 227 * 1024; }
@@ -875,19 +879,20 @@ EncodeTiledFn tc_encoder() {
   return fn;
 }
 
-void tc_set_smem_attr() {
-  cudaFuncSetAttribute(K_TC_FWD, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
-  cudaFuncSetAttribute(K_TC_FWD_N, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
-  cudaFuncSetAttribute(K_TC_DX, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
-  cudaFuncSetAttribute(K_TC_DX_N, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
-  cudaFuncSetAttribute(K_TC_FWD_BIG, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(K_TC_DX_BIG, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(K_TC_DW_BIG, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(K_TC_FWD2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(K_TC_DX2, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(K_TC_DW, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(128, TC_DW_STAGES));
-  cudaFuncSetAttribute(k_dw_adam_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCA_SMEM_BYTES);
+template <bool F> void tc_set_smem_attr_fmt() {
+  cudaFuncSetAttribute(K_TC_FWD(F), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
+  cudaFuncSetAttribute(K_TC_FWD_N(F), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
+  cudaFuncSetAttribute(K_TC_DX(F), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
+  cudaFuncSetAttribute(K_TC_DX_N(F), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
+  cudaFuncSetAttribute(K_TC_FWD_BIG(F), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(K_TC_DX_BIG(F), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(K_TC_DW_BIG(F), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(K_TC_FWD2(F), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(K_TC_DX2(F), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(K_TC_DW(F), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(128, TC_DW_STAGES));
+  cudaFuncSetAttribute(k_dw_adam_tc<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcAdamCfg<F>::SMEM);
 }
+void tc_set_smem_attr() { tc_set_smem_attr_fmt<false>(); tc_set_smem_attr_fmt<true>(); }
 
 // fills the tcgen05 view of one GEMM (shapes in the fp32 path's convention); mode 0 fwd, 1 dX, 2 dW
 // esz = 2: g.A / g.B point at fp16 operand copies (pitches in elements); the epilogue side of g is unchanged.
@@ -921,10 +926,11 @@ int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g, int esz) {
   CK(cudaMemcpyAsync(d, &t, sizeof(t), cudaMemcpyHostToDevice, h->stream));
   tc_set_smem_attr();
   dim3 grid((t.ME + 127) / 128, (t.NE + t.bn - 1) / t.bn, 1);
-  if (mode == 0) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
-  else if (mode == 1) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
-  else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(d, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
-  h->launches++;
+  const OperandMode om0{0, 1.0f, nullptr, nullptr};
+  const bool f16 = esz == 2;
+  if (mode == 0) TC_LAUNCH(h, f16, K_TC_FWD, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream, (const TcOp*)d, h->d_folds, 0, h->hp, om0);
+  else if (mode == 1) TC_LAUNCH(h, f16, K_TC_DX, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream, (const TcOp*)d, h->d_folds, 0, h->hp, om0);
+  else TC_LAUNCH(h, f16, K_TC_DW, grid, dim3(TC_DW_THREADS), tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream, (const TcOp*)d, h->d_folds, 0, h->hp, om0);
   CK(cudaStreamSynchronize(h->stream));
   cudaFree(d);
   return MRGAN_OK;
@@ -953,9 +959,6 @@ int tc_setup(mrgan_handle* h) {
         gh.B = reinterpret_cast<const float*>(h->harena + (g.B - h->om.fbase));
         if (!tc_fill_op(fn, t, gh, mode, 2)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled (fp16 operands) failed");
         t.g = g;                // the epilogue keeps addressing the fp32 buffers (and derives the copies' addresses itself)
-        // which operand is gradient-side: dX contracts dZ (MMA-B) with W, dW contracts dZ^T (MMA-A) with the activations
-        t.afmt = (mode == 2) ? h->om.grad_bf16 : 0;
-        t.bfmt = (mode == 1) ? h->om.grad_bf16 : 0;
       } else if (!tc_fill_op(fn, t, g, mode)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
       t.net = (op == OP_GW1 || op == OP_GW2 || op == OP_GW3) ? 1 : 0;
       if (mode == 2) {
@@ -1013,9 +1016,10 @@ int tc_setup(mrgan_handle* h) {
         const TcOp& t = ops[(size_t)op * nf + f];
         TcAdamOp& a = aops[(size_t)op * nf + f];
         a.mapA = t.mapA; a.mapB = t.mapB; a.ME = t.ME; a.NE = t.NE; a.KE = t.KE; a.fold = t.g.fold; a.net = t.net;
-        a.esz = h->om.mode == 2 ? 2 : 4; a.ldh = t.g.ldc; a.afmt = t.afmt;
         a.ginv = h->om.mode == 2 ? 1.0f / h->om.gscale : 1.0f;
-        a.Ph = h->om.mode == 2 ? h->harena + (t.P - h->om.fbase) : nullptr;
+        // fp16 operand copy of W (refreshed with every update), same geometry as the fp32 tensor
+        if (h->om.mode == 2 && !make_map(fn, &a.mapH, h->harena + (t.P - h->om.fbase), t.ME, t.NE, t.g.ldc, TCA_KC, false, 128, 2))
+          return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled (fp16 weight copy) failed");
         // W / m / v as [rows = in+1, cols = out] with the tensor's pitch; box 128 cols x KC rows, clipped at the logical extents
         if (!make_map(fn, &a.mapP, t.P, t.ME, t.NE, t.g.ldc, TCA_KC, false, 128) ||
             !make_map(fn, &a.mapM, t.Mo, t.ME, t.NE, t.g.ldc, TCA_KC, false, 128) ||
@@ -1059,6 +1063,7 @@ void tc_params_changed(mrgan_handle*, int, int) {}   // fp32 master weights are 
 
 bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override, cudaStream_t st) {
   const OpInfo& oi = h->ops[op];
+  const bool f16 = h->om.mode == 2;
   const int bn = h->tc_bn[op];
   int NE = h->tc_maxNE[op];
   if (rows_override > 0 && !oi.at) NE = rows_override;
@@ -1070,37 +1075,41 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
     if (oi.at) {
       const int ks = h->tc_ksplit[op] > 1 ? h->tc_ksplit[op] : 1;
       grid.z = nfl * ks;
-      launch_k(h, K_TC_DW_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, ks, h->hp, h->om);
+      TC_LAUNCH(h, f16, K_TC_DW_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, ks, h->hp, h->om);
       if (ks > 1) {
         const int n4 = h->tc_maxNE[op] * pitch8(h->tc_maxME[op]) / 4;
         launch_k(h, k_splitk_reduce, dim3(std::min((n4 + 255) / 256, 64), nfl, 1), dim3(256), 0, st, d, ks);
       }
-    } else if (!oi.bt) launch_k(h, K_TC_FWD_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
-    else launch_k(h, K_TC_DX_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
+    } else if (!oi.bt) TC_LAUNCH(h, f16, K_TC_FWD_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
+    else TC_LAUNCH(h, f16, K_TC_DX_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
     return true;
   }
   if (!oi.at && h->tc_mt2 && tc_use_mt2(h->tc_maxME[op], bn)) {
     grid.x = (h->tc_maxME[op] + 255) / 256;
     const size_t smem = tc_smem_bytes(bn, TC_FWD_STAGES, 2);
-    if (!oi.bt) launch_k(h, K_TC_FWD2, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
-    else launch_k(h, K_TC_DX2, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
+    if (!oi.bt) TC_LAUNCH(h, f16, K_TC_FWD2, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
+    else TC_LAUNCH(h, f16, K_TC_DX2, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
     return true;
   }
   if (!oi.at && !oi.bt) {
     // one CTA per SM anyway once the stages exceed half the shared memory: take the whole TMEM then (noise parking)
     if (2 * tc_smem_bytes(bn, TC_FWD_STAGES) > 227 * 1024)
-      launch_k(h, K_TC_FWD_N, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp, h->om);
+      TC_LAUNCH(h, f16, K_TC_FWD_N, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp, h->om);
     else
-      launch_k(h, K_TC_FWD, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp, h->om);
+      TC_LAUNCH(h, f16, K_TC_FWD, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp, h->om);
   }
   else if (!oi.at && oi.bt) {
     if (2 * tc_smem_bytes(bn, TC_FWD_STAGES) > 227 * 1024)
-      launch_k(h, K_TC_DX_N, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp, h->om);
+      TC_LAUNCH(h, f16, K_TC_DX_N, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp, h->om);
     else
-      launch_k(h, K_TC_DX, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp, h->om);
+      TC_LAUNCH(h, f16, K_TC_DX, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp, h->om);
   }
-  else if (h->d_tcadam) launch_k(h, k_dw_adam_tc, grid, dim3(192), (size_t)TCA_SMEM_BYTES, st, (const TcAdamOp*)(h->d_tcadam + (size_t)op * h->nf + f0), h->d_folds, h->hp);
-  else launch_k(h, K_TC_DW, grid, dim3(TC_DW_THREADS), tc_smem_bytes(bn, TC_DW_STAGES), st, d, h->d_folds, 0, h->hp, h->om);
+  else if (h->d_tcadam) {
+    const TcAdamOp* ad = h->d_tcadam + (size_t)op * h->nf + f0;
+    if (f16) launch_k(h, k_dw_adam_tc<true>, grid, dim3(192), TcAdamCfg<true>::SMEM, st, ad, h->d_folds, h->hp);
+    else launch_k(h, k_dw_adam_tc<false>, grid, dim3(192), TcAdamCfg<false>::SMEM, st, ad, h->d_folds, h->hp);
+  }
+  else TC_LAUNCH(h, f16, K_TC_DW, grid, dim3(TC_DW_THREADS), tc_smem_bytes(bn, TC_DW_STAGES), st, d, h->d_folds, 0, h->hp, h->om);
   return true;
 }
 
@@ -1197,19 +1206,16 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   if (e != cudaSuccess) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, std::string("cudaMemset: ") + cudaGetErrorString(e)));
   Arena real; real.base = h->arena;
   layout_buffers(h, real);
-  h->om = OperandMode{cfg->precision, 1.0f, reinterpret_cast<const float*>(h->arena), nullptr, 0};
+  h->om = OperandMode{cfg->precision, 1.0f, reinterpret_cast<const float*>(h->arena), nullptr};
   if (cfg->precision == MRGAN_PREC_F16) {      // operand copies: one __half per float of the arena, zero like the arena
     e = cudaMalloc(&h->harena, h->arena_bytes / 2);
     if (e == cudaSuccess) e = cudaMemset(h->harena, 0, h->arena_bytes / 2);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return cleanup(fail(nullptr, MRGAN_ERR_CUDA, std::string("cudaMalloc fp16 operand arena: ") + cudaGetErrorString(e)));
     h->om.hbase = h->harena;
-    // gradient-side operands: unscaled bf16 (fp32's exponent range: tiny gradients keep their sign, which Adam's sign-like
-    // first steps need; no overflow whatever the batch size).  MRGAN_GRAD_BF16=0 selects loss-scaled fp16 instead (A/B).
-    h->om.grad_bf16 = 1; h->om.gscale = 1.0f;
-    if (const char* gb = getenv("MRGAN_GRAD_BF16")) {
-      if (atoi(gb) == 0) { h->om.grad_bf16 = 0; h->om.gscale = MRGAN_F16_LOSS_SCALE; }
-    }
+    // gradient-side operands: fp16 times a loss scale (saturating; see OperandMode).  MRGAN_LOSS_SCALE overrides the default.
+    h->om.gscale = MRGAN_F16_LOSS_SCALE;
+    if (const char* ls = getenv("MRGAN_LOSS_SCALE")) { const float v = (float)atof(ls); if (v >= 1.0f) h->om.gscale = v; }
   }
   bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) == cudaSuccess;
@@ -1445,7 +1451,7 @@ int mrgan_prepare_fold(mrgan_handle* h, int fold, int slot, const int32_t* train
   const int gx = (s.D + 127) / 128;
   k_col_stats<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows, s.n_train, s.D, h->d_prep_stats);
   k_scale_gather<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows, s.n_train, s.D, h->d_prep_stats, s.n_train,
-                                                     b.xtr, pitch8(s.D), ds.y, b.ytr, OperandMode{0, 1.0f, nullptr, nullptr, 0});
+                                                     b.xtr, pitch8(s.D), ds.y, b.ytr, OperandMode{0, 1.0f, nullptr, nullptr});
   k_scale_gather<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows + s.n_train, s.n_test, s.D, h->d_prep_stats, s.n_train,
                                                      b.xte, b.lda[0], ds.y, b.yte, h->om);
   h->launches += 3;
@@ -1806,8 +1812,7 @@ int mrgan_debug_buffer(mrgan_handle* h, int fold, int which, float* dst, int row
     const bool grad_only = (which >= 21 && which <= 25) || which == 31 || which == 32 || which == 44 || which == 46;
     if (act_only || grad_only) {
       CK(cudaMalloc(&tmp, (size_t)rows * ld * sizeof(float)));
-      k_from_half<<<256, 256, 0, h->stream>>>(src, tmp, (size_t)rows * ld, grad_only ? 1.0f / h->om.gscale : 1.0f, h->om,
-                                              grad_only && h->om.grad_bf16);
+      k_from_half<<<256, 256, 0, h->stream>>>(src, tmp, (size_t)rows * ld, grad_only ? 1.0f / h->om.gscale : 1.0f, h->om);
       src = tmp;
     } else if (which == 45) {   // du stays fp32 but carries the loss scale
       CK(cudaMalloc(&tmp, (size_t)rows * ld * sizeof(float)));
@@ -1912,9 +1917,10 @@ int mrgan_debug_gemm_time(mrgan_handle* h, int mode, int M, int N, int K, int gr
   const TcOp& t = ops[0];
   dim3 grid((t.ME + 127) / 128, (t.NE + t.bn - 1) / t.bn, groups);
   auto once = [&]() {
-    if (mode == 0) K_TC_FWD<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
-    else if (mode == 1) K_TC_DX<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
-    else K_TC_DW<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, OperandMode{0, 1.0f, nullptr, nullptr, 0});
+    const OperandMode om0{0, 1.0f, nullptr, nullptr};
+    if (mode == 0) K_TC_FWD(false)<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, om0);
+    else if (mode == 1) K_TC_DX(false)<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, om0);
+    else K_TC_DW(false)<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, om0);
   };
   once();
   CK(cudaEventRecord(h->ev0, h->stream));
