@@ -1,21 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- GAN train step-pairs/s (one D step + one G step, mr_gan.py:204-213) on 1..8 B200.
 
-Workload (BASELINE.json configs[2] slice, compact MREO shape): a group of `--folds`
-independent table-1 fold-trainings per GPU (force+temperature modality, D=1200, N_train=6000,
-N_test=1200, B=50), synthetic data, random-init weights.  One bench "step" = ONE EPOCH of the
-group = 120 D+G step-pairs per fold x folds, launched as one CUDA graph (plus the batch-wise
-test pass of mr_gan.py:219-223).  Folds shard over GPUs with no collective (weak scaling).
+Workload (BASELINE.json configs[2] slice, compact MREO shape): a group of `--folds` independent table-1
+fold-trainings per GPU (force+temperature modality, D=1200, N_train=6000, N_test=1200, B=50), synthetic data,
+random-init weights.  One bench "step" = ONE EPOCH of the group = 120 D+G step-pairs per fold x folds, launched as
+one CUDA graph (plus the batch-wise test pass of mr_gan.py:219-223).  Folds shard over GPUs with no collective
+(weak scaling).
 
-  value  : step-pairs/s, device time (CUDA events on the launching stream), fold data and the
-           epoch's index arrays already resident in HBM.
-  e2e    : the same metric through the public host API (load_fold + train_epoch with HOST
-           numpy buffers + stats read-back + final eval), wall clock, H2D/D2H inside.
-  --impl reference : the restated CPU baseline (oracle/torch_twin.py, torch CPU fp32, all host
-           threads) -- Keras 2.0.9/Theano 0.9 cannot be installed here.
+  value     : step-pairs/s, device time (CUDA events on the launching stream), fold data and the epoch's index arrays
+              already resident in HBM.
+  e2e       : the same metric through the public host API (dataset upload + device-side fold preparation + train_epoch
+              with HOST numpy index arrays + statistics read-back + final eval), wall clock, H2D / D2H inside.
+  roofline  : the kernel with the largest share of the step (dW of D layer 1 with the Adam update fused in), live;
+  rooflines : the same arithmetic for every kernel class (forward, dX, dW+Adam), worst first -- the first entry is the
+              LIMITING class; step_roofline is the whole step against the algorithmic bytes of SURVEY.md 8(d).
+  modes     : the other precision modes on the same workload (short runs), so the fp32 parity mode is on record too.
+  dp        : (N > 1 only) BASELINE config 5 measured in the same launch: ONE fold at a large global batch split over
+              the N ranks (NCCL all-reduces over NVLink), with its parity against the single-GPU step.
+  --impl reference : the restated CPU baseline (oracle/torch_twin.py, torch CPU fp32): one fold per host core, all
+              cores busy -- the way a CPU user would run the sweep.  Keras 2.0.9 / Theano 0.9 cannot be installed here
+              (SURVEY.md 8c).
+  --workload table1 : the whole table-1 sweep (294 fold-trainings, 7 widths) through the drop-in's scheduler, wall clock.
 """
 import argparse
 import json
+import multiprocessing as mp
 import os
 import subprocess
 import sys
@@ -30,6 +39,7 @@ if ROOT not in sys.path:
 
 METRIC = "gan_train_step_pairs_per_sec"
 UNIT = "step-pairs/s"
+DTYPE = {"fp32": "f32", "tf32": "tf32", "f16": "f16"}      # arithmetic type of the GEMM operands (accumulation is f32)
 
 
 def algo_work(D, B=50):
@@ -56,15 +66,15 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
+    def __init__(self, gpu_index, period_ms=200):
+        self.gpu, self.period = gpu_index, period_ms
         self.rows = []
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", str(self.period), "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -75,7 +85,7 @@ class ClockSampler:
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -110,8 +120,10 @@ def make_jobs(D_modality, n_folds, seed):
     return X, y.astype(np.int32), folds
 
 
+# ------------------------------------------------------------------ CPU arm (the oracle's torch twin; test infrastructure
+# used here only as the measured CPU baseline, never on the product path)
 def cpu_pairs_per_sec(D, B, n_pairs, warm=3, threads=None):
-    """Restated CPU baseline: torch-CPU fp32 twin, Python loop, two calls per iteration, host noise."""
+    """Restated CPU baseline: torch-CPU fp32 twin, Python loop, two calls per iteration, host noise (mr_gan.py:204-213)."""
     import torch
     from oracle import gan_oracle as O, torch_twin as T
     # torchrun exports OMP_NUM_THREADS=1: use every host thread unless a thread count is asked for
@@ -120,6 +132,7 @@ def cpu_pairs_per_sec(D, B, n_pairs, warm=3, threads=None):
     m = T.TorchGan(O.init_disc_params(D, rng), O.init_gen_params(D, rng), dtype=torch.float32)
     X = rng.standard_normal((6000, D)).astype(np.float32)
     y = rng.integers(0, 6, 6000)
+
     def pair(t):
         sl = slice((t % 100) * B, (t % 100 + 1) * B)
         noise = np.random.normal(0, 1, size=[B, 100]).astype(np.float32)
@@ -135,67 +148,110 @@ def cpu_pairs_per_sec(D, B, n_pairs, warm=3, threads=None):
     return n_pairs / dt, torch.get_num_threads()
 
 
+def _core_worker(args):
+    D, B, warm_pairs, n_pairs, barrier = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    import torch
+    from oracle import gan_oracle as O, torch_twin as T
+    torch.set_num_threads(1)
+    rng = np.random.default_rng(os.getpid())
+    m = T.TorchGan(O.init_disc_params(D, rng), O.init_gen_params(D, rng), dtype=torch.float32)
+    X = rng.standard_normal((6000, D)).astype(np.float32)
+    y = rng.integers(0, 6, 6000)
+
+    def pair(t):
+        sl = slice((t % 100) * B, (t % 100 + 1) * B)
+        m.disc_step(X[sl], y[sl], X[sl], np.random.normal(0, 1, size=[B, 100]).astype(np.float32))
+        m.gen_step(X[sl], np.random.normal(0, 1, size=[B, 100]).astype(np.float32))
+    for t in range(max(1, warm_pairs)):
+        pair(t)
+    barrier.wait()
+    t0 = time.perf_counter()
+    for t in range(n_pairs):
+        pair(t)
+    return n_pairs, time.perf_counter() - t0
+
+
+def cpu_fold_per_core(D, B, warm_pairs, n_pairs, cores=None):
+    """One independent fold-training per host core (torch threads = 1 each), all cores busy at once: how the reference's
+    table sweeps would be spread over a CPU box.  Returns (aggregate step-pairs/s, cores, slowest worker's seconds)."""
+    cores = cores or max(1, os.cpu_count() or 1)
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        barrier = mgr.Barrier(cores)
+        with ctx.Pool(cores) as pool:
+            res = pool.map(_core_worker, [(D, B, warm_pairs, n_pairs, barrier)] * cores)
+    slowest = max(s for _, s in res)
+    return sum(n for n, _ in res) / slowest, cores, slowest
+
+
 def run_reference(args, rank):
     if rank != 0:
         return 0
     D, B = args.width, 50
-    pairs_per_step = args.ref_pairs
-    cpu_pairs_per_sec(D, B, max(1, args.warmup) * pairs_per_step, warm=0)       # warm-up steps
     t0 = time.perf_counter()
-    import torch
-    from oracle import gan_oracle as O, torch_twin as T  # noqa: F401
-    v, threads = cpu_pairs_per_sec(D, B, args.steps * pairs_per_step, warm=0)
-    dt = time.perf_counter() - t0
-    sample = "%d step-pairs per step of one fold (D=%d, B=%d), torch-CPU fp32 twin of the oracle" % (pairs_per_step, D, B)
+    v, cores, secs = cpu_fold_per_core(D, B, max(1, args.warmup) * args.ref_pairs, args.steps * args.ref_pairs)
+    v_one, threads = cpu_pairs_per_sec(D, B, max(4, args.ref_pairs), warm=2)
+    sample = ("one fold per host core: %d cores x %d steps x %d step-pairs (D=%d, B=%d), torch-CPU fp32 twin of the oracle, "
+              "1 thread per fold" % (cores, args.steps, args.ref_pairs, D, B))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * pairs_per_step / v, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "wall_ms": 1e3 * dt,
-            "config": {"workload": "mr_gan table-1 fold, force+temperature D=%d, B=50 (CPU sample)" % D},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                             "host_cpus": os.cpu_count()},
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "wall_ms": 1e3 * (time.perf_counter() - t0),
+            "config": {"workload": "mr_gan table-1 folds, force+temperature D=%d, B=50, one fold per host core (CPU sample)" % D},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "host_cpus": os.cpu_count(),
+                             "value_one_fold_all_threads": v_one, "threads_one_fold": threads},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
-def run_dp(args, rank, world, local, barrier):
-    """BASELINE.json config 5: one fold at a large global batch, batch rows split over the ranks, BN / feature-matching
-    statistics and the flat gradient all-reduced with NCCL over NVLink (strong scaling: the global batch is fixed)."""
+# ------------------------------------------------------------------ data-parallel large-batch measurement (config 5)
+def measure_dp(args, precision, rank, world, local, barrier, min_seconds=1.5, parity=True):
+    """ONE fold at a large global batch, batch rows split over the ranks; BN / feature-matching statistics and the flat
+    gradient all-reduced with NCCL over NVLink (strong scaling: the global batch is fixed).  Returns the record dict."""
     import torch
     import torch.distributed as dist
     from mr_gan_b200.engine import FoldGroup
     from mr_gan_b200.model import init_disc, init_gen
-    D, Bg = args.dp_width, args.dp_batch
-    Bl, nb = Bg // world, 4
-    W, K = max(args.warmup, 3), args.steps
-    rng = np.random.default_rng(0)
+    D, Bg, nb = args.dp_width, args.dp_batch, 2
+    Bl = Bg // world
+    rng = np.random.default_rng(0)                      # identical on every rank: weights and the GLOBAL batches
     pD, pG = init_disc(D, rng), init_gen(D, rng)
-    ntr = nb * Bl
-    X = np.random.default_rng(100 + rank).standard_normal((ntr, D)).astype(np.float32)
-    y = (np.arange(ntr) % 6).astype(np.int32)
-    fg = FoldGroup([(D, ntr, 600, 4242)], precision=args.precision, batch=Bl, device=local, eval_each_epoch=False)
+    Xg = rng.standard_normal((nb * Bg, D), dtype=np.float32)
+    yg = (np.arange(nb * Bg) % 6).astype(np.int32)
+    rows = np.concatenate([np.arange(t * Bg + rank * Bl, t * Bg + (rank + 1) * Bl) for t in range(nb)])
+    fg = FoldGroup([(D, nb * Bl, 600, 4242)], precision=precision, batch=Bl, device=local, eval_each_epoch=False)
     if world > 1:
         uid = [FoldGroup.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         fg.dp_init(rank, world, uid[0])
     fg.set_params(0, 1, pG)
     fg.set_params(0, 0, pD)
-    fg.load_fold(0, X, y, X[:600], y[:600])
-    idx = np.arange(ntr, dtype=np.int32)[None, :]
-    sampler = ClockSampler(local)
-    for w in range(W):
+    fg.load_fold(0, Xg[rows], yg[rows], Xg[:600], yg[:600])
+    idx = np.arange(nb * Bl, dtype=np.int32)[None, :]
+    first = fg.train_epoch(idx, idx, idx)[0]            # epoch 0 from the initial weights: the parity sample
+    for w in range(2):
         fg.train_epoch(idx, idx, idx)
+    sampler = ClockSampler(local, period_ms=100)
     sampler.start()
     barrier()
     l0 = fg.kernel_launches
     t0 = time.perf_counter()
-    dev_ms = 0.0
-    for k in range(K):
+    dev_ms, K = 0.0, 0
+    while K < 3 or time.perf_counter() - t0 < min_seconds:
         st = fg.train_epoch(idx, idx, idx)
         dev_ms += fg.last_device_ms
+        K += 1
+        if world > 1:                                   # every rank must stop after the same epoch
+            flag = torch.tensor([K >= 3 and time.perf_counter() - t0 >= min_seconds], dtype=torch.int32, device="cuda")
+            dist.broadcast(flag, src=0)
+            if int(flag.item()):
+                break
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop()
+    launches = fg.kernel_launches - l0
+    fg.close()
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -205,21 +261,80 @@ def run_dp(args, rank, world, local, barrier):
     hbm, tf, how = peaks()
     value = pairs / (dev_ms * 1e-3)
     ach = flops * value / 1e12
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32" if args.precision == "fp32" else "tf32",
-            "data": "synthetic",
-            "config": {"workload": "mr_gan.py table-5 fold at large batch, data-parallel: D=%d (1 s contact mic), global batch %d "
-                                   "(%d per GPU); 1 step = %d D+G step-pairs" % (D, Bg, Bl, nb),
-                       "parallelism": "dp%d, NCCL all-reduce of BN/FM statistics and flat gradients (%.0f MB D + %.0f MB G per pair)"
-                                      % (world, 4e-6 * N_D, 4e-6 * N_G), "precision": args.precision},
-            "e2e": {"value": pairs / (wall_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(3 * 4 * ntr),
-                    "d2h_bytes_per_step": 32, "wall_ms": wall_ms},
-            "gpu_launches": int(fg.kernel_launches - l0),
-            "roofline": {"kernel": "whole step pair (tcgen05 GEMMs dominate at this batch)", "bound": "tensor", "achieved": ach,
-                         "peak": tf * world, "unit": "TFLOP/s", "frac": ach / (tf * world), "traffic": None, "peak_source": how,
-                         "note": "tf32 operands: the tf32 tensor peak is half the bf16 figure used as denominator"},
-            "clocks": clocks, "sanity": {"last_loss_lab": float(st[0, 0]), "last_loss_gen": float(st[0, 3])}}
-    fg.close()
+    rec = {"value": value, "unit": UNIT, "ms_per_pair": dev_ms / pairs, "epochs_timed": K, "pairs_per_epoch": nb,
+           "workload": "mr_gan.py table-5 fold at large batch, data-parallel: D=%d (1 s contact mic), global batch %d (%d per GPU)"
+                       % (D, Bg, Bl),
+           "parallelism": "dp%d, NCCL all-reduce of BN / feature-matching statistics and flat gradients (%.0f MB D + %.0f MB G per pair)"
+                          % (world, 4e-6 * N_D, 4e-6 * N_G),
+           "precision": precision, "scaling": "strong", "e2e_value": pairs / (wall_ms * 1e-3), "gpu_launches": int(launches),
+           "achieved_tflops": ach, "tensor_frac_of_bf16_peak": ach / (tf * world), "peak_source": how, "clocks": clocks,
+           "last_loss_lab": float(st[0, 0]), "last_loss_gen": float(st[0, 3])}
+    if parity and world > 1:
+        # the same global batches through ONE GPU's large-batch step, from the same weights: epoch 0 must agree
+        ref = None
+        if rank == 0:
+            with FoldGroup([(D, nb * Bg, 600, 4242)], precision=precision, batch=Bg, device=local, eval_each_epoch=False) as f1:
+                f1.set_params(0, 1, pG)
+                f1.set_params(0, 0, pD)
+                f1.load_fold(0, Xg, yg, Xg[:600], yg[:600])
+                i1 = np.arange(nb * Bg, dtype=np.int32)[None, :]
+                ref = f1.train_epoch(i1, i1, i1)[0]
+            rel = np.abs(first[[0, 1, 3]] - ref[[0, 1, 3]]) / np.abs(ref[[0, 1, 3]])
+            rec["parity_vs_single_gpu"] = {"max_rel_err_losses": float(rel.max()), "train_err_abs_diff": float(abs(first[2] - ref[2])),
+                                           "dp": [float(x) for x in first[:4]], "single_gpu": [float(x) for x in ref[:4]]}
+        barrier()
+    return rec
+
+
+def run_dp(args, rank, world, local, barrier):
+    import torch.distributed as dist
+    rec = measure_dp(args, args.precision, rank, world, local, barrier, min_seconds=max(1.5, 0.05 * args.steps))
+    hbm, tf, how = peaks()
+    line = {"metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": rec["epochs_timed"], "warmup": 3,
+            "ms_per_step": rec["ms_per_pair"] * rec["pairs_per_epoch"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": DTYPE[args.precision], "data": "synthetic",
+            "config": {"workload": rec["workload"], "parallelism": rec["parallelism"], "precision": args.precision},
+            "e2e": {"value": rec["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": int(3 * 4 * rec["pairs_per_epoch"] * args.dp_batch // world),
+                    "d2h_bytes_per_step": 32},
+            "gpu_launches": rec["gpu_launches"],
+            "roofline": {"kernel": "whole step pair (tcgen05 GEMMs dominate at this batch)", "bound": "tensor",
+                         "achieved": rec["achieved_tflops"], "peak": tf * world, "unit": "TFLOP/s",
+                         "frac": rec["tensor_frac_of_bf16_peak"], "traffic": None, "peak_source": how,
+                         "note": "denominator = measured bf16 cuBLAS throughput; tf32 operands run at half that rate"},
+            "clocks": rec["clocks"], "dp": rec}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# ------------------------------------------------------------------ the whole table-1 sweep through the drop-in scheduler
+def run_table1(args, rank, world, local, barrier):
+    import torch.distributed as dist
+    from mr_gan_b200 import mr_gan as mg, sweep
+    t0 = time.perf_counter()
+    seed = 0
+    percents = [1, 2, 4, 8, 16, 50, 100]
+    jobs = []
+    for modality in range(len(mg.MODALITIES)):
+        X, y = mg.dataset(modalities=modality, seed=seed, synthetic_data=True)
+        jobs += [j for p in percents for j in mg._kfold_jobs(X, y, seed + p, percentlabeled=p)]
+    for i, j in enumerate(jobs):
+        j['job_id'] = i
+    t_data = time.perf_counter() - t0
+    errors = sweep.run_sharded(jobs, lambda js, dev: mg.train_gan_folds(js, epochs=args.epochs, seed=seed, precision=args.precision, device=dev),
+                               group_size=args.group, key=mg.job_rows, cost=mg.job_width, init_dist=False)
+    barrier()
+    wall = time.perf_counter() - t0
+    pairs = sum((mg.job_rows(j)[0] // 50) * args.epochs for j in jobs)
+    line = {"metric": "table1_sweep_wall_seconds", "value": wall, "unit": "s", "n_gpus": world, "steps": 1, "warmup": 0,
+            "ms_per_step": 1e3 * wall, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": DTYPE[args.precision], "data": "synthetic",
+            "config": {"workload": "mr_gan.py --tables 1: %d fold-trainings (7 modalities x 7 labeled fractions x 6 folds), %d epochs, "
+                                   "widths 400..3632, through the drop-in scheduler (data synthesis %.1f s included)"
+                                   % (len(jobs), args.epochs, t_data), "group": args.group, "precision": args.precision},
+            "step_pairs_total": pairs, "step_pairs_per_sec_wall": pairs / wall, "mean_test_error": float(np.mean(errors))}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -235,14 +350,19 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--folds", type=int, default=74, help="fold-trainings grouped per GPU (table 1 has 294 = 4 x 73.5; 74 = 148/2 keeps every kernel at whole waves)")
     ap.add_argument("--modality", type=int, default=2, help="2 = force+temperature (D=1200)")
-    ap.add_argument("--precision", default=os.environ.get("MRGAN_PRECISION", "tf32"), choices=["fp32", "tf32", "f16"])
-    ap.add_argument("--ref-pairs", type=int, default=12)
+    ap.add_argument("--precision", default=os.environ.get("MRGAN_PRECISION", "f16"), choices=["fp32", "tf32", "f16"])
+    ap.add_argument("--ref-pairs", type=int, default=6, help="--impl reference: step-pairs per fold and step (bounded CPU sample)")
     ap.add_argument("--cpu-pairs", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--workload", default="sweep", choices=["sweep", "dp"],
-                    help="sweep: fold-sharded table-1 group (headline); dp: ONE fold at large batch, data-parallel (config 5)")
+    ap.add_argument("--no-modes", action="store_true", help="skip the short runs of the other precision modes")
+    ap.add_argument("--no-dp", action="store_true", help="N > 1: skip the data-parallel sub-record")
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "dp", "table1"],
+                    help="sweep: fold-sharded table-1 group (headline); dp: ONE fold at large batch, data-parallel (config 5); "
+                         "table1: the whole table-1 sweep, wall clock")
     ap.add_argument("--dp-batch", type=int, default=8192, help="global batch of the dp workload")
     ap.add_argument("--dp-width", type=int, default=12032, help="input width of the dp workload (1 s contact mic, table 5)")
+    ap.add_argument("--epochs", type=int, default=100, help="table1 workload: epochs per fold")
+    ap.add_argument("--group", type=int, default=42, help="table1 workload: folds per handle")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -271,27 +391,34 @@ def main():
 
     if args.workload == "dp":
         return run_dp(args, rank, world, local, barrier)
+    if args.workload == "table1":
+        return run_table1(args, rank, world, local, barrier)
 
     D, B, G = args.width, 50, args.folds
     W, K = max(args.warmup, 3), args.steps
     X, y, folds = make_jobs(args.modality, G, seed=1000 * rank)
     ntr, nte = len(folds[0][0].train_rows), len(folds[0][0].test_rows)
     nb = ntr // B
-    fg = FoldGroup([(D, ntr, nte, fold_key(rank, i)) for i in range(G)], precision=args.precision, device=local)
-
-    def load_all():          # dataset upload (once) + device-side fold preparation of every fold (scaler, gather)
-        fg.load_dataset(0, X, y)
-        for i, (f, rng) in enumerate(folds):
-            fg.prepare_fold(i, 0, f.train_rows, f.test_rows)
 
     def draw():
         per = [foldprep.epoch_indices(rng, ntr, f.lab_rows, f.unl_rows) for f, rng in folds]
         return [np.stack([p[s] for p in per]) for s in range(3)]
 
-    for i, (f, rng) in enumerate(folds):
-        fg.set_params(i, 1, init_gen(D, rng))
-        fg.set_params(i, 0, init_disc(D, rng))
-    load_all()
+    def open_group(precision):
+        fg = FoldGroup([(D, ntr, nte, fold_key(rank, i)) for i in range(G)], precision=precision, device=local)
+        for i, (f, rng) in enumerate(folds):
+            r2 = np.random.default_rng([7, rank, i])
+            fg.set_params(i, 1, init_gen(D, r2))
+            fg.set_params(i, 0, init_disc(D, r2))
+        return fg
+
+    def load_all(fg):        # dataset upload (once) + device-side fold preparation of every fold (scaler, gather)
+        fg.load_dataset(0, X, y)
+        for i, (f, rng) in enumerate(folds):
+            fg.prepare_fold(i, 0, f.train_rows, f.test_rows)
+
+    fg = open_group(args.precision)
+    load_all(fg)
     pre = [draw() for _ in range(W + K)]
 
     sampler = ClockSampler(local)
@@ -312,7 +439,7 @@ def main():
     # ---- region 2: end to end through the host API -----------------------------------------
     barrier()
     t0 = time.perf_counter()
-    load_all()                                            # H2D of the dataset + per-fold index arrays, fold prep on the device
+    load_all(fg)                                          # H2D of the dataset + per-fold index arrays, fold prep on the device
     t_load = time.perf_counter() - t0
     nxt = draw()
     for k in range(K):
@@ -335,37 +462,56 @@ def main():
     value = pairs / (dev_ms * 1e-3)
     e2e = pairs / (wall2_ms * 1e-3)
 
-    # ---- live roofline probe of the dominant kernel (CUDA events on the launching stream) ----
+    # ---- live roofline probes, one per kernel class (CUDA events on the launching stream; they mutate the state, so
+    #      they run after the measured regions) ----
     flops, nbytes, N_D, N_G = algo_work(D, B)
     hbm, tf, how = peaks()
-    probe = {k: fg.time_op(k, reps=10) for k in ("adam_d", "dw1", "fwd1", "adam_g")}
+    tensor = args.precision != "fp32"
+    wbytes = 2 if args.precision == "f16" else 4            # bytes per weight the forward / dX passes read
+    probe = {k: fg.time_op(k, reps=10) for k in ("adam_d", "dw1", "fwd1", "dx1", "adam_g")}
     step_ms = {k: fg.time_op(k, reps=3) for k in ("disc_step", "gen_step")}
-    dom = max(("adam_d", "dw1", "fwd1"), key=lambda k: probe[k])
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")       # dram__bytes_read+write per launch from `ncu --set full`
-    if os.path.exists(tpath):
-        tj = json.load(open(tpath)).get("%s/%s" % (dom, args.precision), {})
-        if tj.get("folds") == G and tj.get("D") == D:
-            traffic = tj["bytes"]
-    if dom == "adam_d" or (dom == "dw1" and args.precision == "tf32"):
-        # HBM-bound: layer-1 dW with the Adam update fused in its epilogue (tf32) / the flat Adam kernel (fp32).
-        # algorithmic bytes = W, m, v read + written once (24 B per parameter); gradients stay on chip
-        n_par = (D + 1) * 1000 if dom == "dw1" else N_D
-        ach = 24.0 * n_par * G / (probe[dom] * 1e-3) / 1e9
-        name = "k_gemm_tc<dW + fused Adam> of D layer 1" if dom == "dw1" else "k_adam (flat, D net)"
-        roof = {"kernel": name + ", all folds", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                "frac": ach / hbm, "traffic": traffic, "algorithmic_bytes_per_launch": 24.0 * n_par * G}
+    n1 = (D + 1) * 1000                                       # parameters of D layer 1 (augmented: bias row included)
+    adam_bytes = 24.0 + (2.0 if args.precision == "f16" else 0.0)   # W, m, v read + written (+ the fp16 operand copy written)
+
+    def hbm_entry(name, kernel, ms, per_param, n_par, note):
+        ach = per_param * n_par * G / (ms * 1e-3) / 1e9
+        return {"class": name, "kernel": kernel, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                "launch_ms": ms, "algorithmic_bytes_per_launch": per_param * n_par * G, "bytes_per_parameter": per_param,
+                "peak_source": how, "note": note}
+
+    if tensor:
+        classes = [
+            hbm_entry("dW + fused Adam", "k_dw_adam_tc, D layer 1, all folds", probe["dw1"], adam_bytes, n1,
+                      "W, m, v streamed once each way; the gradient never leaves the SM"),
+            hbm_entry("forward", "k_gemm_tc<forward>, D layer 1, all folds", probe["fwd1"], wbytes, n1,
+                      "weights read once; the 150-row activation tile is L2-resident and not counted"),
+            hbm_entry("dX", "k_gemm_tc<dX>, dFake = dZ1 W1^T, all folds", probe["dx1"], wbytes, D * 1000,
+                      "weights read once; 50 gradient rows L2-resident"),
+        ]
     else:
-        fl = 2.0 * 3 * B * (D + 1) * 1000 * G
-        ach = fl / (probe[dom] * 1e-3) / 1e12
-        roof = {"kernel": ("dW" if dom == "dw1" else "forward") + " GEMM of D layer 1, all folds", "bound": "tensor",
-                "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf, "traffic": traffic}
-    roof["peak_source"] = how
-    roof["launch_ms"] = probe[dom]
+        classes = [
+            hbm_entry("flat Adam", "k_adam, discriminator, all folds", probe["adam_d"], 24.0, N_D,
+                      "W, m, v read + written; the gradient read (4 B) is not algorithmic"),
+            {"class": "forward", "kernel": "k_gemm_simt, D layer 1, all folds", "bound": "fp32 FFMA", "launch_ms": probe["fwd1"],
+             "achieved": 2.0 * 3 * B * n1 * G / (probe["fwd1"] * 1e-3) / 1e12, "unit": "TFLOP/s", "peak": None, "frac": None},
+        ]
+    rooflines = sorted([c for c in classes if c.get("frac") is not None], key=lambda c: c["frac"])
+    dominant = dict(classes[0])                               # largest share of the step (profiles/: launch list)
+    # dram__bytes_read + dram__bytes_write of that kernel from `ncu --set full`, valid only for the library it was captured
+    # on (keyed by the source hash): a stale constant is worse than null
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        from mr_gan_b200 import build as _b
+        tj = json.load(open(tpath)).get("dw1/%s" % args.precision, {})
+        if tj.get("folds") == G and tj.get("D") == D and tj.get("source_hash") == _b.source_hash():
+            traffic = tj["bytes"]
+    dominant["traffic"] = traffic
+    dominant["limiting_class"] = rooflines[0]["class"] if rooflines else None
     step_gbs = nbytes * value / world / 1e9
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+            "dtype": DTYPE[args.precision], "data": "synthetic",
             "config": {"workload": "mr_gan.py table-1 fold group: %d folds/GPU, force+temperature D=%d, N_train=%d, "
                                    "N_test=%d, B=%d; 1 step = 1 epoch = %d D+G step-pairs per fold + test pass"
                                    % (G, D, ntr, nte, B, nb),
@@ -379,20 +525,49 @@ def main():
                     "note": "includes the dataset upload and device-side fold preparation once, host permutations, final eval"},
             "gpu_launches": int(launches), "wall_ms_region1": wall1_ms,
             "fold_trainings_per_hour": value / (100 * nb) * 3600.0,
-            "roofline": roof,
+            "roofline": dominant, "rooflines": rooflines,
             "step_roofline": {"bound": "hbm", "achieved": step_gbs, "peak": hbm, "unit": "GB/s", "frac": step_gbs / hbm,
                               "algorithmic_bytes_per_pair": nbytes, "algorithmic_flops_per_pair": flops,
                               "achieved_tflops": flops * value / world / 1e12},
             "kernel_ms": probe, "step_ms": step_ms, "clocks": clocks,
             "sanity": {"final_test_err_mean": float(np.mean(errs)), "last_loss_lab": float(st[:, 0].mean())}}
+    fg.close()
+
+    # ---- the other precision modes on the same workload (short: 1 warm-up epoch beyond the graph build, 2 timed) ----
+    if not args.no_modes:
+        modes = {args.precision: {"value": value, "steps": K}}
+        for prec in ("f16", "tf32", "fp32"):
+            if prec == args.precision:
+                continue
+            f2 = open_group(prec)
+            load_all(f2)
+            f2.train_epoch(*pre[0])
+            f2.train_epoch(*pre[1])
+            barrier()
+            ms = 0.0
+            for k in range(2):
+                f2.train_epoch(*pre[2 + k])
+                ms += f2.last_device_ms
+            tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            v2 = 2 * nb * G * world / (float(tt.item()) * 1e-3)
+            modes[prec] = {"value": v2, "steps": 2, "step_roofline_frac": nbytes * v2 / world / 1e9 / hbm}
+            f2.close()
+        line["modes"] = modes
+
     if rank == 0 and world == 1 and not args.no_cpu:
         v, threads = cpu_pairs_per_sec(D, B, args.cpu_pairs)
-        v1, _ = cpu_pairs_per_sec(D, B, max(2, args.cpu_pairs // 6), warm=1, threads=1)     # 1 thread and all threads
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
-                                "value_1thread": v1,
-                                "sample": "%d D+G step-pairs of one fold (D=%d, B=%d), torch-CPU fp32 twin of the oracle "
-                                          "(restated baseline, not Keras 2.0.9/Theano 0.9)" % (args.cpu_pairs, D, B)}
-    fg.close()
+        vc, cores, _ = cpu_fold_per_core(D, B, 2, max(4, args.cpu_pairs // 3))
+        line["cpu_baseline"] = {"value": vc, "unit": UNIT, "cores": cores, "kind": "port", "host_cpus": os.cpu_count(),
+                                "value_one_fold_all_threads": v, "threads_one_fold": threads,
+                                "sample": "one fold per host core, %d D+G step-pairs each (D=%d, B=%d), torch-CPU fp32 twin of the "
+                                          "oracle, 1 thread per fold (restated baseline, not Keras 2.0.9/Theano 0.9); "
+                                          "value_one_fold_all_threads = %d step-pairs of ONE fold on all threads"
+                                          % (max(4, args.cpu_pairs // 3), D, B, args.cpu_pairs)}
+    if world > 1 and not args.no_dp:
+        dp_prec = args.precision
+        line["dp"] = measure_dp(args, dp_prec, rank, world, local, barrier)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

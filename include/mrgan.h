@@ -143,6 +143,11 @@ int  mrgan_eval(mrgan_handle* h, int fold, float* err);
  *   mrgan_nccl_unique_id: 128 bytes from ncclGetUniqueId (call on rank 0, broadcast with any host transport). */
 int  mrgan_nccl_unique_id(void* id128);
 int  mrgan_dp_init(mrgan_handle* h, int rank, int world, const void* id128);
+/* The same data-parallel path with VIRTUAL ranks on one GPU (test / single-GPU validation of everything but the
+ * transport): the handle must hold exactly `world` folds of identical shape and noise key; fold r plays rank r
+ * (its resident rows are rank r's slice of the global batch) and every collective is a rank-ordered local sum over
+ * the folds' buffers.  Train with mrgan_train_epoch; the per-fold step calls are rejected in this mode. */
+int  mrgan_dp_init_virtual(mrgan_handle* h, int world);
 
 /* mr_nn.py:114-118 twins (handle created with MRGAN_MODEL_NN):
  *   one model.fit batch: x[n,D], labels[n] -> {mse loss, accuracy}; n <= batch */
@@ -161,7 +166,8 @@ int  mrgan_adam_flat(mrgan_handle* h, float* p, float* m, float* v, const float*
  * kernel of the step over ALL folds of the handle -- the live roofline probe bench.py uses.
  * Mutates the training state (run it after the measured region). */
 enum { MRGAN_TIME_ADAM_D = 0, MRGAN_TIME_ADAM_G = 1, MRGAN_TIME_DW1 = 2, MRGAN_TIME_FWD1 = 3,
-       MRGAN_TIME_DISC_STEP = 4, MRGAN_TIME_GEN_STEP = 5 };
+       MRGAN_TIME_DISC_STEP = 4, MRGAN_TIME_GEN_STEP = 5,
+       MRGAN_TIME_DX1 = 6 };   /* dFake = dZ1 W1^T of the generator step: the dX pass over the widest layer */
 int  mrgan_time_op(mrgan_handle* h, int which, int reps, float* ms_avg);
 /* Debug/test hook: copy an intermediate buffer of the last step of one fold to the host
  * (dst is [rows, cols] dense).  which: 0..5 = noisy layer inputs a[l], 10+l = post-ReLU h[l],

@@ -57,6 +57,7 @@ SYMBOLS = {
     "mrgan_eval": (C.c_int, [_H, C.c_int, _fp]),
     "mrgan_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mrgan_dp_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
+    "mrgan_dp_init_virtual": (C.c_int, [_H, C.c_int]),
     "mrnn_step": (C.c_int, [_H, C.c_int, _fp, _ip, C.c_int, _fp]),
     "mrnn_train_epoch": (C.c_int, [_H, _ip, C.c_int, _fp]),
     "mrnn_evaluate": (C.c_int, [_H, C.c_int, _fp]),

@@ -58,10 +58,12 @@ struct AdamHyper { float lr, b1, b2, eps; int shared_t; int dp_bloc, dp_bg, dp_r
 // Stacked-row index of this rank -> stacked-row index of the GLOBAL batch (identity unless data-parallel): sections
 // [labeled | unlabeled | fake] of dp_bg rows each, of which this rank holds rows [rank*bloc, (rank+1)*bloc).  The noise
 // stream is keyed by the global index, so W ranks draw exactly what one GPU would draw for the same global batch.
-__host__ __device__ inline int global_row(int L, const AdamHyper& hp) {
+// dp_rank < 0 selects the VIRTUAL-rank mode (mrgan_dp_init_virtual): the folds of one handle play the ranks, so the rank
+// of a row is the index of the fold it belongs to -- the whole data-parallel path then runs, and is tested, on ONE GPU.
+__host__ __device__ inline int global_row(int L, const AdamHyper& hp, int fold = 0) {
   if (hp.dp_bg == hp.dp_bloc) return L;
   const int sec = L / hp.dp_bloc;
-  return sec * hp.dp_bg + hp.dp_rank * hp.dp_bloc + (L - sec * hp.dp_bloc);
+  return sec * hp.dp_bg + (hp.dp_rank < 0 ? fold : hp.dp_rank) * hp.dp_bloc + (L - sec * hp.dp_bloc);
 }
 
 // Programmatic dependent launch: every kernel of the step chain lets its successor be scheduled as soon as all of its own

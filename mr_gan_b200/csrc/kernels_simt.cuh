@@ -136,9 +136,9 @@ k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ fo
     float nz[4] = {0.f, 0.f, 0.f, 0.f};
     if (noisy) {
       if (((d.row0 + mb) & 3) == 0 && (hp.dp_bg == hp.dp_bloc || (hp.dp_bloc & 3) == 0)) {
-        normal4(k0, k1, (uint32_t)global_row(d.row0 + mb, hp) >> 2, (uint32_t)n, step, (uint32_t)d.tid, nz);
+        normal4(k0, k1, (uint32_t)global_row(d.row0 + mb, hp, d.fold) >> 2, (uint32_t)n, step, (uint32_t)d.tid, nz);
       } else {
-        for (int i = 0; i < 4; ++i) nz[i] = normal1(k0, k1, (uint32_t)global_row(d.row0 + mb + i, hp), (uint32_t)n, step, (uint32_t)d.tid);
+        for (int i = 0; i < 4; ++i) nz[i] = normal1(k0, k1, (uint32_t)global_row(d.row0 + mb + i, hp, d.fold), (uint32_t)n, step, (uint32_t)d.tid);
       }
     }
 #pragma unroll
@@ -208,8 +208,8 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
       xv[i] = __ldg(src + c);
     }
     float nz[4];
-    if (aligned) normal4(key0, key1, (uint32_t)global_row(rg * 4, hp) >> 2, (uint32_t)c, step, 0u, nz);
-    else for (int i = 0; i < 4; ++i) nz[i] = normal1(key0, key1, (uint32_t)global_row(rg * 4 + i, hp), (uint32_t)c, step, 0u);
+    if (aligned) normal4(key0, key1, (uint32_t)global_row(rg * 4, hp, fold_base + (int)blockIdx.z) >> 2, (uint32_t)c, step, 0u, nz);
+    else for (int i = 0; i < 4; ++i) nz[i] = normal1(key0, key1, (uint32_t)global_row(rg * 4 + i, hp, fold_base + (int)blockIdx.z), (uint32_t)c, step, 0u);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = rg * 4 + i;
@@ -221,8 +221,8 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
   if (mode != 2 && c < noise_dim) {       // generator input z (mr_gan.py:206,212)
     float nz[4] = {0.f, 0.f, 0.f, 0.f};
     if (!from_stage) {
-      if (aligned) normal4(fs.key0, fs.key1, (uint32_t)global_row(rg * 4, hp) >> 2, (uint32_t)c, step, MRGAN_TID_Z, nz);
-      else for (int i = 0; i < 4; ++i) nz[i] = normal1(fs.key0, fs.key1, (uint32_t)global_row(rg * 4 + i, hp), (uint32_t)c, step, MRGAN_TID_Z);
+      if (aligned) normal4(fs.key0, fs.key1, (uint32_t)global_row(rg * 4, hp, fold_base + (int)blockIdx.z) >> 2, (uint32_t)c, step, MRGAN_TID_Z, nz);
+      else for (int i = 0; i < 4; ++i) nz[i] = normal1(fs.key0, fs.key1, (uint32_t)global_row(rg * 4 + i, hp, fold_base + (int)blockIdx.z), (uint32_t)c, step, MRGAN_TID_Z);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -681,9 +681,12 @@ __global__ void k_fill_normal(float* __restrict__ dst, const FoldState* __restri
 
 
 // ------------------------------------------------------------------ device-side fold preparation (mr_gan.py:96-101)
-// StandardScaler.fit over the training rows of a fold: per-column sum and sum of squares in float64.
+// StandardScaler.fit over the training rows of a fold: per-column sum and sum of squares in float64.  Each of the
+// gridDim.y row slices writes its own partial sums ([slice][2 * D]); the consumer adds the slices in slice order, so the
+// statistics are bit-identical from run to run and whatever else shares the GPU (no floating-point atomics).
+#define PREP_SLICES 64
 __global__ void __launch_bounds__(128)
-k_col_stats(const float* __restrict__ X, int ldx, const int* __restrict__ rows, int n_rows, int D, double* __restrict__ stats) {
+k_col_stats(const float* __restrict__ X, int ldx, const int* __restrict__ rows, int n_rows, int D, double* __restrict__ partials) {
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= D) return;
   double s = 0.0, q = 0.0;
@@ -691,18 +694,20 @@ k_col_stats(const float* __restrict__ X, int ldx, const int* __restrict__ rows, 
     const double x = (double)X[(size_t)rows[i] * ldx + c];
     s += x; q += x * x;
   }
-  atomicAdd(&stats[c], s);
-  atomicAdd(&stats[D + c], q);
+  partials[(size_t)blockIdx.y * 2 * D + c] = s;
+  partials[(size_t)blockIdx.y * 2 * D + D + c] = q;
 }
 
 // StandardScaler.transform + row gather: out[i, c] = float((X[rows[i], c] - mean_c) / std_c), std 0 -> 1 (sklearn).
 __global__ void __launch_bounds__(128)
-k_scale_gather(const float* __restrict__ X, int ldx, const int* __restrict__ rows, int n_rows, int D, const double* __restrict__ stats,
-               int n_fit, float* __restrict__ out, int ldo, const int* __restrict__ y_src, int* __restrict__ y_out, OperandMode om) {
+k_scale_gather(const float* __restrict__ X, int ldx, const int* __restrict__ rows, int n_rows, int D, const double* __restrict__ partials,
+               int n_slices, int n_fit, float* __restrict__ out, int ldo, const int* __restrict__ y_src, int* __restrict__ y_out, OperandMode om) {
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= D) return;
-  const double mean = stats[c] / n_fit;
-  double var = stats[D + c] / n_fit - mean * mean;
+  double sum = 0.0, sq = 0.0;
+  for (int sl = 0; sl < n_slices; ++sl) { sum += partials[(size_t)sl * 2 * D + c]; sq += partials[(size_t)sl * 2 * D + D + c]; }
+  const double mean = sum / n_fit;
+  double var = sq / n_fit - mean * mean;
   if (var < 0.0) var = 0.0;
   double sd = sqrt(var);
   if (sd < 1e-300 || var <= 10.0 * 2.220446049250313e-16 * fabs(mean) * fabs(mean)) sd = 1.0;   // constant column

@@ -515,18 +515,25 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
       if (noisy) { const FoldState& fs = folds[g.fold]; key0 = fs.key0; key1 = fs.key1; step = (uint32_t)fs.rng_step; }
       // 4-row noise groups must not straddle row-section or rank boundaries (oracle/philox.py): otherwise per-element draws
       const bool grp = ((g.row0 + n0 + cbeg) & 3) == 0 && (hp.dp_bg == hp.dp_bloc || (hp.dp_bloc & 3) == 0);
+      const bool dp = hp.dp_bg != hp.dp_bloc;
+      const int dprank = hp.dp_rank < 0 ? g.fold : hp.dp_rank;      // virtual-rank mode: the fold is the rank
       auto draw16 = [&](int c0, float (&nz)[16]) {
+        const int r0 = g.row0 + n0 + c0;
+        if (grp && !dp) {
+          // the common case: four independent Philox chains, inlined so the compiler interleaves them (the epilogue warps
+          // are latency-bound here: 2 warps per scheduler)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int r0 = g.row0 + n0 + c0 + 4 * q;
-          if (grp) {
-            const float4 n4 = noise4_call(key0, key1, r0, (uint32_t)f, step, (uint32_t)g.tid, hp.dp_bloc, hp.dp_bg, hp.dp_rank);
+          for (int q = 0; q < 4; ++q) normal4(key0, key1, (uint32_t)(r0 + 4 * q) >> 2, (uint32_t)f, step, (uint32_t)g.tid, &nz[4 * q]);
+        } else if (grp) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 n4 = noise4_call(key0, key1, r0 + 4 * q, (uint32_t)f, step, (uint32_t)g.tid, hp.dp_bloc, hp.dp_bg, dprank);
             nz[4 * q] = n4.x; nz[4 * q + 1] = n4.y; nz[4 * q + 2] = n4.z; nz[4 * q + 3] = n4.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              nz[4 * q + i] = noise1_call(key0, key1, r0 + i, (uint32_t)f, step, (uint32_t)g.tid, hp.dp_bloc, hp.dp_bg, hp.dp_rank);
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            nz[j] = noise1_call(key0, key1, r0 + j, (uint32_t)f, step, (uint32_t)g.tid, hp.dp_bloc, hp.dp_bg, dprank);
         }
       };
       const int npk = (noisy && grp) ? npark : 0;

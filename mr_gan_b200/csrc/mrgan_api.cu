@@ -121,6 +121,7 @@ struct mrgan_handle {
   struct Dataset { float* x = nullptr; int* y = nullptr; int n = 0, D = 0, ld = 0; } datasets[8];
   double* d_prep_stats = nullptr; int* d_prep_rows = nullptr; int prep_rows_cap = 0, prep_stats_cap = 0;
   int dp_world = 1, dp_rank = 0;
+  bool dp_virtual = false;            // the handle's folds play the ranks (mrgan_dp_init_virtual): collectives are local sums
   void* nccl_comm = nullptr;
   float* d_dpmem = nullptr; DpBufs* d_dpbufs = nullptr;
   float *dp_bnf = nullptr, *dp_bnb = nullptr, *dp_fm = nullptr;   // [nf][2*500], [nf][2*500], [nf][2*250]
@@ -480,9 +481,26 @@ bool nccl_load() {
   return true;
 }
 
+// Virtual-rank stand-in for the collective: `buf` holds W equal segments (one per fold = rank); every segment becomes the
+// element-wise sum over the segments, added in rank order (what ncclAllReduce(sum) leaves on every rank).
+__global__ void k_virtual_allreduce(float* __restrict__ buf, size_t seg, int W) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < seg; i += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < W; ++w) s += buf[(size_t)w * seg + i];
+    for (int w = 0; w < W; ++w) buf[(size_t)w * seg + i] = s;
+  }
+}
+
 // in-stream sum all-reduce of fp32 (ncclFloat32 = 7, ncclSum = 0); no-op outside the data-parallel mode
 void dp_allreduce(mrgan_handle* h, float* buf, size_t n) {
   if (h->dp_world <= 1 || n == 0) return;
+  if (h->dp_virtual) {
+    const size_t seg = n / (size_t)h->dp_world;
+    const int blocks = (int)std::min<size_t>((seg + 255) / 256, 1184);
+    k_virtual_allreduce<<<blocks, 256, 0, h->stream>>>(buf, seg, h->dp_world);
+    h->launches++;
+    return;
+  }
   const int rc = g_nccl.AllReduce(buf, buf, n, 7, 0, h->nccl_comm, h->stream);
   if (rc != 0 && !h->sticky) {
     h->sticky = MRGAN_ERR_CUDA;
@@ -1439,20 +1457,19 @@ int mrgan_prepare_fold(mrgan_handle* h, int fold, int slot, const int32_t* train
     CK(cudaMalloc(&h->d_prep_rows, (size_t)nrows * sizeof(int)));
     h->prep_rows_cap = nrows;
   }
-  if (2 * s.D > h->prep_stats_cap) {
+  if (2 * s.D > h->prep_stats_cap) {      // per-slice partial column sums: [PREP_SLICES][2 * D] doubles
     if (h->d_prep_stats) cudaFree(h->d_prep_stats);
-    CK(cudaMalloc(&h->d_prep_stats, (size_t)2 * s.D * sizeof(double)));
+    CK(cudaMalloc(&h->d_prep_stats, (size_t)PREP_SLICES * 2 * s.D * sizeof(double)));
     h->prep_stats_cap = 2 * s.D;
   }
   FoldBuffers& b = h->fb[fold];
   CK(cudaMemcpyAsync(h->d_prep_rows, train_rows, (size_t)s.n_train * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->d_prep_rows + s.n_train, test_rows, (size_t)s.n_test * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemsetAsync(h->d_prep_stats, 0, (size_t)2 * s.D * sizeof(double), h->stream));
   const int gx = (s.D + 127) / 128;
-  k_col_stats<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows, s.n_train, s.D, h->d_prep_stats);
-  k_scale_gather<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows, s.n_train, s.D, h->d_prep_stats, s.n_train,
+  k_col_stats<<<dim3(gx, PREP_SLICES), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows, s.n_train, s.D, h->d_prep_stats);
+  k_scale_gather<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows, s.n_train, s.D, h->d_prep_stats, PREP_SLICES, s.n_train,
                                                      b.xtr, pitch8(s.D), ds.y, b.ytr, OperandMode{0, 1.0f, nullptr, nullptr});
-  k_scale_gather<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows + s.n_train, s.n_test, s.D, h->d_prep_stats, s.n_train,
+  k_scale_gather<<<dim3(gx, 64), 128, 0, h->stream>>>(ds.x, ds.ld, h->d_prep_rows + s.n_train, s.n_test, s.D, h->d_prep_stats, PREP_SLICES, s.n_train,
                                                      b.xte, b.lda[0], ds.y, b.yte, h->om);
   h->launches += 3;
   CK(cudaStreamSynchronize(h->stream));     // the pageable index arrays are borrowed only for the call
@@ -1466,6 +1483,7 @@ int mrgan_disc_step(mrgan_handle* h, int fold, const float* x_lab, const int32_t
   int rc = check_fold(h, fold); if (rc) return rc;
   if (h->cfg.model != MRGAN_MODEL_GAN) return fail(h, MRGAN_ERR_STATE, "disc_step needs a GAN handle");
   if (!x_lab || !labels || !x_unl || !z || !out) return fail(h, MRGAN_ERR_ARG, "disc_step: null pointer");
+  if (h->dp_virtual) return fail(h, MRGAN_ERR_STATE, "disc_step: virtual ranks step together: use mrgan_train_epoch");
   CK(cudaSetDevice(h->cfg.device));
   rc = finish_pending(h); if (rc) return rc;
   const int B = h->cfg.batch, D = h->shapes[fold].D, nd = h->cfg.noise_dim;
@@ -1489,6 +1507,7 @@ int mrgan_gen_step(mrgan_handle* h, int fold, const float* x_unl, const float* z
   int rc = check_fold(h, fold); if (rc) return rc;
   if (h->cfg.model != MRGAN_MODEL_GAN) return fail(h, MRGAN_ERR_STATE, "gen_step needs a GAN handle");
   if (!x_unl || !z || !out) return fail(h, MRGAN_ERR_ARG, "gen_step: null pointer");
+  if (h->dp_virtual) return fail(h, MRGAN_ERR_STATE, "gen_step: virtual ranks step together: use mrgan_train_epoch");
   CK(cudaSetDevice(h->cfg.device));
   rc = finish_pending(h); if (rc) return rc;
   const int B = h->cfg.batch, D = h->shapes[fold].D, nd = h->cfg.noise_dim;
@@ -1711,7 +1730,7 @@ int mrgan_time_op(mrgan_handle* h, int which, int reps, float* ms_avg) {
   if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
   if (!ms_avg || reps < 1) return fail(h, MRGAN_ERR_ARG, "time_op: bad argument");
   const bool gan = h->cfg.model == MRGAN_MODEL_GAN;
-  if (!gan && (which == MRGAN_TIME_ADAM_G || which == MRGAN_TIME_GEN_STEP)) return fail(h, MRGAN_ERR_STATE, "time_op: no generator in this model");
+  if (!gan && (which == MRGAN_TIME_ADAM_G || which == MRGAN_TIME_GEN_STEP || which == MRGAN_TIME_DX1)) return fail(h, MRGAN_ERR_STATE, "time_op: no generator in this model");
   for (int f = 0; f < h->nf; ++f)
     if (!h->fb[f].loaded) return fail(h, MRGAN_ERR_STATE, "time_op before mrgan_load_fold");
   CK(cudaSetDevice(h->cfg.device));
@@ -1724,10 +1743,11 @@ int mrgan_time_op(mrgan_handle* h, int which, int reps, float* ms_avg) {
       case MRGAN_TIME_FWD1: launch_gemm(h, OP_D1, 0, h->nf, 0); break;
       case MRGAN_TIME_DISC_STEP: if (gan) enqueue_disc_step(h, 0, h->nf, 0, 0); else enqueue_nn_step(h, 0, h->nf, 0, 0, h->cfg.batch); break;
       case MRGAN_TIME_GEN_STEP: enqueue_gen_step(h, 0, h->nf, 0, 0); break;
+      case MRGAN_TIME_DX1: launch_gemm(h, OP_DX1G, 0, h->nf, 0); break;
       default: break;
     }
   };
-  if (which < 0 || which > MRGAN_TIME_GEN_STEP) return fail(h, MRGAN_ERR_ARG, "time_op: unknown op");
+  if (which < 0 || which > MRGAN_TIME_DX1) return fail(h, MRGAN_ERR_ARG, "time_op: unknown op");
   once();                                   // warm-up
   CK(cudaEventRecord(h->ev0, h->stream));
   for (int i = 0; i < reps; ++i) once();
@@ -1754,7 +1774,6 @@ int mrgan_dp_init(mrgan_handle* h, int rank, int world, const void* id128) {
   if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
   if (world < 1 || rank < 0 || rank >= world || !id128) return fail(h, MRGAN_ERR_ARG, "dp_init: bad rank / world / id");
   if (h->cfg.model != MRGAN_MODEL_GAN) return fail(h, MRGAN_ERR_STATE, "dp_init: data-parallel mode is implemented for the GAN model");
-  if (h->cfg.precision == MRGAN_PREC_F16) return fail(h, MRGAN_ERR_STATE, "dp_init: the fp16 operand mode is single-GPU for now");
   if (h->dp_world > 1 || h->nccl_comm) return fail(h, MRGAN_ERR_STATE, "dp_init called twice");
   if (world == 1) return MRGAN_OK;
   if (h->cfg.batch % 4) return fail(h, MRGAN_ERR_ARG, "dp_init: the local batch must be a multiple of 4 (noise row groups)");
@@ -1767,6 +1786,33 @@ int mrgan_dp_init(mrgan_handle* h, int rank, int world, const void* id128) {
   rc = alloc_split_bufs(h); if (rc) return rc;
   h->dp_world = world; h->dp_rank = rank;
   h->hp.dp_bloc = h->cfg.batch; h->hp.dp_bg = h->cfg.batch * world; h->hp.dp_rank = rank;
+#ifdef MRGAN_WITH_TC
+  if (h->cfg.precision != MRGAN_PREC_FP32) {   // gradients must be all-reduced before Adam: dW stores them, k_adam applies
+    tc_teardown(h);
+    h->tc_fused_adam = false;
+    rc = tc_setup(h); if (rc) return rc;
+  }
+#endif
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  h->graphs.clear(); h->graph_nodes.clear();
+  CK(cudaDeviceSynchronize());
+  return MRGAN_OK;
+}
+
+int mrgan_dp_init_virtual(mrgan_handle* h, int world) {
+  if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
+  if (h->cfg.model != MRGAN_MODEL_GAN) return fail(h, MRGAN_ERR_STATE, "dp_init_virtual: data-parallel mode is implemented for the GAN model");
+  if (h->dp_world > 1 || h->nccl_comm) return fail(h, MRGAN_ERR_STATE, "dp_init called twice");
+  if (world < 2 || world != h->nf) return fail(h, MRGAN_ERR_ARG, "dp_init_virtual: the handle must hold exactly `world` folds (one per virtual rank)");
+  if (h->cfg.batch % 4) return fail(h, MRGAN_ERR_ARG, "dp_init_virtual: the local batch must be a multiple of 4 (noise row groups)");
+  for (int f = 1; f < h->nf; ++f)
+    if (h->shapes[f].D != h->shapes[0].D || h->shapes[f].seed != h->shapes[0].seed)
+      return fail(h, MRGAN_ERR_ARG, "dp_init_virtual: virtual ranks are replicas: same input width and noise key");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = finish_pending(h); if (rc) return rc;
+  rc = alloc_split_bufs(h); if (rc) return rc;
+  h->dp_world = world; h->dp_rank = 0; h->dp_virtual = true;
+  h->hp.dp_bloc = h->cfg.batch; h->hp.dp_bg = h->cfg.batch * world; h->hp.dp_rank = -1;     // -1: rank = fold index (common.cuh)
 #ifdef MRGAN_WITH_TC
   if (h->cfg.precision != MRGAN_PREC_FP32) {   // gradients must be all-reduced before Adam: dW stores them, k_adam applies
     tc_teardown(h);

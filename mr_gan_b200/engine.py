@@ -81,6 +81,12 @@ class FoldGroup:
         self._chk(self.lib.mrgan_dp_init(self._h, int(rank), int(world), buf))
         self.dp_rank, self.dp_world = int(rank), int(world)
 
+    def dp_init_virtual(self, world):
+        """The data-parallel path with the handle's `world` folds playing the ranks on ONE GPU (collectives become
+        rank-ordered local sums); fold r's resident rows are rank r's slice of the global batch."""
+        self._chk(self.lib.mrgan_dp_init_virtual(self._h, int(world)))
+        self.dp_rank, self.dp_world = -1, int(world)
+
     # ------------------------------------------------------------------ plumbing
     def _chk(self, rc, h="self"):
         if rc != 0:
@@ -289,7 +295,7 @@ class FoldGroup:
         self._chk(self.lib.mrgan_debug_gemm_time(self._h, mode, M, N, K, groups, reps, _lib.fptr(out)))
         return float(out[0])
 
-    TIME_OPS = {"adam_d": 0, "adam_g": 1, "dw1": 2, "fwd1": 3, "disc_step": 4, "gen_step": 5}
+    TIME_OPS = {"adam_d": 0, "adam_g": 1, "dw1": 2, "fwd1": 3, "disc_step": 4, "gen_step": 5, "dx1": 6}
 
     def time_op(self, which, reps=20):
         """Average device ms of one kernel (or one whole step) over all folds; mutates training state."""
