@@ -53,7 +53,11 @@ struct GemmDesc {
 
 // Per-step constants passed by value to the kernels: Adam hyper-parameters and, for the data-parallel mode, the
 // batch geometry (dp_bloc rows per section on this rank, dp_bg rows per section globally, this rank's index).
-struct AdamHyper { float lr, b1, b2, eps; int shared_t; int dp_bloc, dp_bg, dp_rank; };
+struct AdamHyper {
+  float lr, b1, b2, eps; int shared_t; int dp_bloc, dp_bg, dp_rank;
+  // constants of the loss / BatchNorm heads fused into GEMM epilogues, and the batch index of the step being enqueued
+  float w_unl, bn_eps; int n_classes, t;
+};
 
 // Stacked-row index of this rank -> stacked-row index of the GLOBAL batch (identity unless data-parallel): sections
 // [labeled | unlabeled | fake] of dp_bg rows each, of which this rank holds rows [rank*bloc, (rank+1)*bloc).  The noise
@@ -203,6 +207,12 @@ __device__ __forceinline__ float softplus_fast(float x) {
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
 

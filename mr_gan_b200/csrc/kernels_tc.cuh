@@ -22,6 +22,14 @@
 #include "common.cuh"
 
 enum { EPI_ADAM = 3 };
+// Reductions fused into the epilogue of the GEMM that produces their input (thread = feature, the batch is in TMEM columns,
+// so batch statistics are thread-local):
+//   HEAD_DISC    forward of the logit layer: Salimans supervised / unsupervised losses, training error, logit gradients
+//                (mr_gan.py:146-149,161), and K.update_add(iterations, 1) of the discriminator step
+//   HEAD_FM      forward of D layer 5 in the generator step: feature-matching loss and its gradient (mr_gan.py:152-154)
+//   HEAD_BN      forward of G layer 1: BatchNormalization with batch statistics (mr_gan.py:112)
+//   HEAD_BN_BWD  dX into G layer 1: BatchNorm backward, softplus', and the Adam update of gamma / beta
+enum { HEAD_NONE = 0, HEAD_DISC = 1, HEAD_FM = 2, HEAD_BN = 3, HEAD_BN_BWD = 4 };
 
 struct alignas(64) TcOp {
   CUtensorMap mapA, mapB;
@@ -34,7 +42,12 @@ struct alignas(64) TcOp {
   int ws_stride;              // split-K (large-batch dW): floats between the partial products of two contraction slices
   float* ws;                  // ... and their workspace, laid out like C; k_splitk_reduce sums the slices in a fixed order
   int esz;                    // operand element size: 4 (or 0) = fp32 read as tf32, 2 = fp16 copies (kind::f16, fp32 accumulation)
-  int pad_[3];
+  int head;                   // HEAD_*: reduction fused into this GEMM's epilogue
+  int advance;                // the head also advances the fold's step counters (no k_adam launch follows)
+  int stats_stride;           // floats between the statistics blocks of two batches of the epoch
+  const void* hd;             // the fold's LossDesc (HEAD_DISC / HEAD_FM) or BnDesc (HEAD_BN / HEAD_BN_BWD)
+  float* stats;               // the fold's block of 4 step statistics at batch 0
+  long long mo_off, vo_off;   // Adam slots of a parameter p: p + mo_off, p + vo_off (HEAD_BN_BWD: gamma / beta)
 };
 
 #define TC_KBLK 32            // contraction elements per stage (one 128-byte swizzle row of fp32)
@@ -223,6 +236,184 @@ __device__ __forceinline__ void dx_rows(const uint32_t (&va)[16], const float (&
   }
 }
 
+
+// ---- fused heads: a second pass over the finished accumulator (TMEM reads are cheap) by the epilogue warps -----------
+// One 16-row chunk of this thread's feature from TMEM, as the activation the forward epilogue stored.
+template <bool F16, int ACT>
+__device__ __forceinline__ void head_chunk(uint32_t taddr, float (&x)[16]) {
+  tc::tmem_ld16(taddr, x);
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (!F16) x[j] *= TF32_TRUNC_DEBIAS;
+    if (ACT == ACT_RELU) x[j] = fmaxf(x[j], 0.f);
+    else if (ACT == ACT_SOFTPLUS) x[j] = softplus_fast(x[j]);
+  }
+}
+
+// HEAD_DISC: Salimans-style supervised + unsupervised losses on the stacked rows [labeled | unlabeled | fake]
+// (mr_gan.py:146-149,161) and the closed-form logit gradients.  The K logits of a row sit in lanes 0..K-1
+// of the quadrant-0 warps; they are transposed through shared memory (the operand stages are free once the accumulator
+// is complete) so that one THREAD handles one row, all epilogue warps in parallel.  Per-warp partial sums of (loss_lab,
+// loss_unl, errors) go to part[3 * warp]; the caller adds them in warp order.
+template <bool F16, int EPW>
+__device__ __forceinline__ void head_disc(uint32_t trow, int cbeg, int ncols, int nall, int lane_base, int lane, int ewarp,
+                                          const LossDesc& L, const AdamHyper& hp, const OperandMode& om, float* sl, float* part) {
+  const int K = hp.n_classes, B = hp.dp_bloc;
+  const float Bg = (float)hp.dp_bg;
+  if (lane_base == 0) {
+    for (int c0 = cbeg; c0 < ncols; c0 += 16) {
+      float v[16];
+      head_chunk<F16, ACT_NONE>(trow + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (lane < K && c0 + j < ncols) sl[(c0 + j) * K + lane] = v[j];
+    }
+  }
+  asm volatile("bar.sync 1, %0;" ::"r"(32 * EPW) : "memory");      // the epilogue warps only
+  float s_lab = 0.f, s_unl = 0.f, s_err = 0.f;
+  for (int r = ewarp * 32 + lane; r < nall; r += 32 * EPW) {
+    const float* l = sl + r * K;
+    float mx = l[0]; int am = 0;
+    for (int k = 1; k < K; ++k) if (l[k] > mx) { mx = l[k]; am = k; }
+    float se = 0.f;
+    for (int k = 0; k < K; ++k) se += expf(l[k] - mx);
+    const float lse = mx + logf(se), inv = 1.0f / se;
+    float* dl = L.dlogits + (size_t)r * L.ld;
+    if (r < B) {
+      const int y = L.labels[r];
+      s_lab += lse - l[y];
+      s_err += (am != y) ? 1.f : 0.f;
+      for (int k = 0; k < K; ++k) put_grad_operand(dl + k, (expf(l[k] - mx) * inv - (k == y ? 1.f : 0.f)) / Bg, om);
+    } else {
+      const float sp = softplusf(lse), sg = 1.0f / (1.0f + expf(-lse));
+      float coef;
+      if (r < 2 * B) { s_unl += 0.5f * (sp - lse); coef = 0.5f * (sg - 1.0f); }
+      else           { s_unl += 0.5f * sp;         coef = 0.5f * sg; }
+      coef *= hp.w_unl / Bg;
+      for (int k = 0; k < K; ++k) put_grad_operand(dl + k, coef * expf(l[k] - mx) * inv, om);
+    }
+  }
+  s_lab = warp_sum(s_lab); s_unl = warp_sum(s_unl); s_err = warp_sum(s_err);
+  if (lane == 0) { part[3 * ewarp] = s_lab; part[3 * ewarp + 1] = s_unl; part[3 * ewarp + 2] = s_err; }
+}
+
+// HEAD_FM: rows [0,B) = fake, [B,2B) = real post-ReLU activations of D layer 5; this thread's feature f (MT = 2: the warp
+// group owns all rows of its sub-tile).  Writes the warp's partial of sum_f diff_f^2 to *red and dZ5 (already multiplied by
+// ReLU') for the fake rows (mr_gan.py:152-154).
+template <bool F16>
+__device__ __forceinline__ void head_fm(uint32_t trow, int ncols, int f, bool f_ok, int lane, const LossDesc& L, const AdamHyper& hp,
+                                        const OperandMode& om, float* red) {
+  const int B = hp.dp_bloc;
+  float mg = 0.f, mr = 0.f;
+  for (int c0 = 0; c0 < ncols; c0 += 16) {
+    float x[16];
+    head_chunk<F16, ACT_RELU>(trow + (uint32_t)c0, x);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int r = c0 + j;
+      if (r < B) mg += x[j]; else if (r < ncols) mr += x[j];
+    }
+  }
+  const float diff = (mg - mr) / B;
+  const float part = warp_sum(f_ok ? diff * diff : 0.f);
+  if (lane == 0) *red = part;
+  float g = 2.0f * diff / ((float)L.Wmid * B);
+  if (!F16) g = rna_tf32(g);
+  for (int c0 = 0; c0 < B; c0 += 16) {
+    float x[16];
+    head_chunk<F16, ACT_RELU>(trow + (uint32_t)c0, x);
+    if (!f_ok) continue;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int r = c0 + j;
+      if (r < B) put_grad_operand(L.dmid + (size_t)r * L.lddmid + f, x[j] > 0.f ? g : 0.f, om);
+    }
+  }
+}
+
+// HEAD_BN: BatchNormalization(epsilon) of G layer 1's softplus output in training phase (biased batch variance,
+// mr_gan.py:112).  Statistics over ALL nall rows of this thread's feature (with one sub-tile per CTA both warp groups
+// compute them, redundantly) in one pass of shifted sums (shift = the first row's value, which keeps E[d^2] - E[d]^2 well
+// conditioned); xhat, 1/std and the GEMM operand u = gamma xhat + beta are written for rows [cbeg, ncols).
+template <bool F16>
+__device__ __forceinline__ void head_bn(uint32_t trow, int cbeg, int ncols, int nall, int f, bool f_ok, const BnDesc& Bd,
+                                        const AdamHyper& hp, const OperandMode& om) {
+  float s = 0.f, q = 0.f, x0 = 0.f;
+  for (int c0 = 0; c0 < nall; c0 += 16) {
+    float x[16];
+    head_chunk<F16, ACT_SOFTPLUS>(trow + (uint32_t)c0, x);
+    if (c0 == 0) x0 = x[0];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (c0 + j < nall) { const float d = x[j] - x0; s += d; q = fmaf(d, d, q); }
+  }
+  const float md = s / nall, mu = x0 + md;
+  const float istd = rsqrtf(fmaxf(q / nall - md * md, 0.f) + hp.bn_eps);
+  float ga = 0.f, be = 0.f;
+  if (f_ok) { if (cbeg == 0) Bd.istd[f] = istd; ga = Bd.gamma[f]; be = Bd.beta[f]; }
+  for (int c0 = cbeg; c0 < ncols; c0 += 16) {
+    float x[16];
+    head_chunk<F16, ACT_SOFTPLUS>(trow + (uint32_t)c0, x);
+    if (!f_ok) continue;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int r = c0 + j;
+      if (r >= ncols) break;
+      const float xh = (x[j] - mu) * istd;
+      Bd.xhat[(size_t)r * Bd.ld + f] = xh;
+      put_operand(Bd.u + (size_t)r * Bd.ldu + f, fmaf(ga, xh, be), om);
+    }
+  }
+}
+
+// HEAD_BN_BWD: the accumulator is dU (gradient w.r.t. the BatchNorm output) of this thread's feature: BatchNorm backward,
+// softplus' of G layer 1 for rows [cbeg, ncols), and Keras Adam on gamma_f, beta_f (their gradients are the two
+// thread-local sums over all nall rows; the warp group with cbeg == 0 applies the update).
+template <bool F16>
+__device__ __forceinline__ void head_bn_bwd(uint32_t trow, int cbeg, int ncols, int nall, int f, bool f_ok, const BnDesc& Bd,
+                                            const AdamHyper& hp, const OperandMode& om, float lr_t, long long mo_off, long long vo_off) {
+  const float ginv = F16 ? 1.0f / om.gscale : 1.0f;            // the dZ operand carried the loss scale into the accumulator
+  float s1 = 0.f, s2 = 0.f;
+  for (int c0 = 0; c0 < nall; c0 += 16) {
+    float du[16];
+    head_chunk<F16, ACT_NONE>(trow + (uint32_t)c0, du);
+    if (!f_ok) continue;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int r = c0 + j;
+      if (r >= nall) break;
+      const float d = du[j] * ginv;
+      s1 += d;
+      s2 = fmaf(d, Bd.xhat[(size_t)r * Bd.ld + f], s2);
+    }
+  }
+  float ga = 0.f, istd = 0.f;
+  if (f_ok) { ga = Bd.gamma[f]; istd = Bd.istd[f]; }
+  const float invB = 1.0f / nall;
+  for (int c0 = cbeg; c0 < ncols; c0 += 16) {
+    float du[16];
+    head_chunk<F16, ACT_NONE>(trow + (uint32_t)c0, du);
+    if (!f_ok) continue;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int r = c0 + j;
+      if (r >= ncols) break;
+      const float xh = Bd.xhat[(size_t)r * Bd.ld + f];
+      const float dxh = du[j] * ginv * ga;
+      const float dh1 = istd * (dxh - invB * ga * s1 - xh * invB * ga * s2);
+      put_grad_operand(Bd.dz1 + (size_t)r * Bd.ld + f, dh1 * (1.0f - expf(-Bd.h1[(size_t)r * Bd.ld + f])), om);
+    }
+  }
+  if (f_ok && cbeg == 0) {      // Adam.get_updates for gamma (gradient s2) and beta (gradient s1), mr_gan.py:167
+    const float b1 = hp.b1, b2 = hp.b2, c1 = 1.0f - hp.b1, c2 = 1.0f - hp.b2;
+    float* const pg = const_cast<float*>(Bd.gamma) + f;
+    float* const pb = const_cast<float*>(Bd.beta) + f;
+    float m = fmaf(b1, pg[mo_off], c1 * s2), v = fmaf(b2, pg[vo_off], c2 * s2 * s2);
+    pg[mo_off] = m; pg[vo_off] = v; *pg = ga - lr_t * m / (sqrtf(v) + hp.eps);
+    m = fmaf(b1, pb[mo_off], c1 * s1); v = fmaf(b2, pb[vo_off], c2 * s1 * s1);
+    pb[mo_off] = m; pb[vo_off] = v; *pb -= lr_t * m / (sqrtf(v) + hp.eps);
+  }
+}
+
 // A_MN / B_MN: operand is MN-major (its MMA M/N dimension is the memory-contiguous one).  The pair also selects the role:
 //   A_MN && !B_MN  forward   (EPI_FWD)      !A_MN && !B_MN  dX (EPI_DX)      A_MN && B_MN  dW (EPI_ADAM or EPI_STORE)
 // STAGES: depth of the TMA->MMA ring; TMEM_COLS: TMEM columns allocated (power of 2 >= MT x bn);
@@ -267,6 +458,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   uint64_t* empty = bars + STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * STAGES;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* const red = reinterpret_cast<float*>(bars + 24);    // 16 floats of head scratch at the end of the 256-byte barrier block
 #ifdef MRGAN_PHASE_TIMING
   unsigned long long* pt = reinterpret_cast<unsigned long long*>(bars + 16);     // inside the 256-byte slack after the barriers
   if (threadIdx.x == 0) pt[0] = pt_t0;
@@ -504,6 +696,9 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         else if (g.act == ACT_SOFTPLUS) dx_rows<F16, ACT_SOFTPLUS>(va, av, nrows, pC, phC, g.ldc, op_only);
         else dx_rows<F16, ACT_NONE>(va, av, nrows, pC, phC, g.ldc, op_only);
       }
+      if (op.head == HEAD_BN_BWD)
+        head_bn_bwd<F16>(trow, cbeg, ncols, min(bn, NE - n0), f, f_ok, *static_cast<const BnDesc*>(op.hd), hp, om, folds[g.fold].lr_t[1],
+                         op.mo_off, op.vo_off);
     } else {
       // ------------------------------------------------------------------ forward: act, optional clean copy, noisy copy
       // GaussianNoise of the next layer's input (C2): the draws do not depend on the accumulator, and the epilogue warps are
@@ -592,6 +787,16 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
 #undef FWD_ACT
 #undef FWD_ROWS
       }
+      // ---- reductions fused into this GEMM (the host selects them only for single-tile batches outside the DP mode) ----
+      if (op.head == HEAD_DISC) {       // scratch: operand stage 0 (every MMA has retired); partial sums behind the logits
+        float* const sl = reinterpret_cast<float*>(smem);
+        head_disc<F16, EPW>(trow, cbeg, ncols, min(bn, NE - n0), lane_base, lane, warp - 2, *static_cast<const LossDesc*>(op.hd), hp, om,
+                            sl, sl + 8192);
+      } else if (op.head == HEAD_FM) {  // MT == 2 (host): this warp group owns its sub-tile's features and all rows
+        head_fm<F16>(trow, ncols, f, f_ok, lane, *static_cast<const LossDesc*>(op.hd), hp, om, red + (warp - 2));
+      } else if (op.head == HEAD_BN) {
+        head_bn<F16>(trow, cbeg, ncols, min(bn, NE - n0), f, f_ok, *static_cast<const BnDesc*>(op.hd), hp, om);
+      }
     }
   }
 
@@ -601,6 +806,27 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
   if (warp == 1) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+  if (!B_MN && A_MN && threadIdx.x == 0 && (op.head == HEAD_DISC || op.head == HEAD_FM)) {
+    // publish the step statistics (partials added in a fixed order) and, when no k_adam launch follows, advance
+    // K.update_add(iterations, 1) and the noise step: nothing later in this step reads either
+    float* const st = op.stats + (size_t)hp.t * op.stats_stride;
+    if (op.head == HEAD_DISC) {
+      const float Bg = (float)hp.dp_bg;
+      const float* part = reinterpret_cast<const float*>(smem) + 8192;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      for (int w = 0; w < EPW; ++w) { a0 += part[3 * w]; a1 += part[3 * w + 1]; a2 += part[3 * w + 2]; }
+      st[0] = a0 / Bg; st[1] = a1 / Bg; st[2] = a2 / Bg;
+    } else {
+      float sum = 0.f;
+      for (int w = 0; w < EPW; ++w) sum += red[w];
+      st[3] = sum / static_cast<const LossDesc*>(op.hd)->Wmid;
+    }
+    if (op.advance) {
+      FoldState& fs = folds[op.g.fold];
+      if (hp.shared_t) fs.iterations += 1; else fs.it_net[op.head == HEAD_DISC ? 0 : 1] += 1;
+      fs.rng_step += 1;
+    }
   }
 #ifdef MRGAN_PHASE_TIMING
   if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && (blockIdx.z % 24) == 0) {

@@ -133,6 +133,9 @@ struct mrgan_handle {
   bool tc_fused_adam = true;          // dW epilogue applies Adam in place (no gradient round trip)
   bool tc_mt2 = true;                 // forward / dX: 256 features per CTA where the layer is wide enough (MRGAN_MT2=0 disables)
   bool tc_adam_tma = true;            // ... with W/m/v staged through smem by TMA (k_dw_adam_tc) instead of the LSU
+  int tc_heads = 0;                   // losses / feature matching / BatchNorm fused into GEMM epilogues (set by tc_setup), bit mask:
+                                      // 1 = HEAD_DISC (no k_loss_disc, no k_adam of D), 2 = HEAD_FM (no k_fm), 4 = HEAD_BN (no k_bn_fwd),
+                                      // 8 = HEAD_BN_BWD (no k_bn_bwd); 2 and 8 together also retire the generator's k_adam
   TcAdamOp* d_tcadam = nullptr;       // [NUM_OPS][nf]
   AdamRange* d_ranges_tc[2] = {nullptr, nullptr};   // what is left for k_adam: BN gamma/beta (G), nothing (D)
 #endif
@@ -578,7 +581,7 @@ void launch_prep(mrgan_handle* h, int f0, int nfl, int mode, int from_stage, int
            h->om);
 }
 
-void launch_adam(mrgan_handle* h, int f0, int nfl, int net) {
+void launch_adam(mrgan_handle* h, int f0, int nfl, int net, bool counters_only = false) {
   long long nmax = 0;
   for (int f = f0; f < f0 + nfl; ++f) nmax = h->net[net][f].n > nmax ? h->net[net][f].n : nmax;
   int blocks = (int)((nmax / 4 + 255) / 256);
@@ -586,7 +589,7 @@ void launch_adam(mrgan_handle* h, int f0, int nfl, int net) {
   if (blocks < 1) blocks = 1;
   const AdamRange* ranges = h->d_ranges[net];
 #ifdef MRGAN_WITH_TC
-  if (h->cfg.precision != MRGAN_PREC_FP32 && h->tc_fused_adam) { ranges = h->d_ranges_tc[net]; blocks = 1; }
+  if (h->cfg.precision != MRGAN_PREC_FP32 && h->tc_fused_adam) { ranges = h->d_ranges_tc[counters_only ? 0 : net]; blocks = 1; }
 #endif
   // f16 mode: the gradient buffer carries the loss scale, and every parameter update refreshes the fp16 operand copy
   const float ginv = h->om.mode == 2 ? 1.0f / h->om.gscale : 1.0f;
@@ -601,9 +604,22 @@ void launch_adam(mrgan_handle* h, int f0, int nfl, int net) {
 // double-buffered activations).
 bool deferred_join(const mrgan_handle*) { return false; }
 
+int heads_on(const mrgan_handle* h) {
+#ifdef MRGAN_WITH_TC
+  return h->cfg.precision != MRGAN_PREC_FP32 ? h->tc_heads : 0;
+#else
+  return 0;
+#endif
+}
+
 void enqueue_gen_fwd(mrgan_handle* h, int f0, int nfl, int op_g3) {
   if (deferred_join(h)) join_side(h);          // generator weights of the previous G step (GW1..3 on the side stream)
   launch_gemm(h, OP_G1, f0, nfl, 0);
+  if (heads_on(h) & 4) {                       // BatchNorm ran in G1's epilogue
+    launch_gemm(h, OP_G2, f0, nfl, 0);
+    launch_gemm(h, op_g3, f0, nfl, 0);
+    return;
+  }
   const dim3 bnf((kGH + BN_COLS - 1) / BN_COLS, 1, nfl);
   const dim3 bnt(h->cfg.batch > 256 ? 1024 : 256);     // 32 columns x 8 (reference batch) or 32 (large batch) row slices
   const OperandMode tf32 = h->om;
@@ -623,11 +639,14 @@ void enqueue_gen_fwd(mrgan_handle* h, int f0, int nfl, int op_g3) {
 void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   const mrgan_config& c = h->cfg;
   const int B = c.batch;
+  const bool heads = (heads_on(h) & 1) != 0;
+  h->hp.t = t;
   launch_prep(h, f0, nfl, 0, from_stage, t, 2 * B);
   enqueue_gen_fwd(h, f0, nfl, OP_G3D);
   for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 0);
-  launch_k(h, k_loss_disc, dim3(1, 1, nfl), dim3(256), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, B,
-           c.n_classes, c.unlabeled_weight, h->om, h->hp.dp_bg);
+  if (!heads)        // otherwise the logit layer's epilogue computed the losses, their gradients and advanced the counters
+    launch_k(h, k_loss_disc, dim3(1, 1, nfl), dim3(256), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, B,
+             c.n_classes, c.unlabeled_weight, h->om, h->hp.dp_bg);
   for (int l = 6; l >= 1; --l) {      // dX first: it reads W_l, which the fused-Adam dW epilogue overwrites
     if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
     fork_side(h);                     // dW_l (+Adam) streams HBM on the side while main continues the dX chain
@@ -635,7 +654,7 @@ void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) 
   }
   if (!deferred_join(h) || from_stage) join_side(h);   // deferred: dW1+Adam overlaps the next G step's generator forward
   dp_allreduce_grads(h, 0);
-  launch_adam(h, f0, nfl, 0);
+  if (!heads) launch_adam(h, f0, nfl, 0);
   if (from_stage) dp_allreduce(h, h->d_step_stats + ((size_t)t * h->nf + f0) * 4, (size_t)nfl * 4);
 }
 
@@ -643,6 +662,8 @@ void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) 
 void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   const mrgan_config& c = h->cfg;
   const int B = c.batch;
+  const int hm = heads_on(h);
+  h->hp.t = t;
   launch_prep(h, f0, nfl, 1, from_stage, t, 2 * B);
   enqueue_gen_fwd(h, f0, nfl, OP_G3G);
   if (deferred_join(h)) join_side(h);          // discriminator weights updated by the D step's dW+Adam kernels
@@ -654,7 +675,7 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
     k_fm_apply<<<fmg, fmt, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, h->d_step_stats, f0, h->nf, t, B,
                                            h->om, h->hp.dp_bg, h->dp_world);
     h->launches += 2;
-  } else {
+  } else if (!(hm & 2)) {   // otherwise D layer 5's epilogue computed the feature-matching loss, its gradient, and advanced the counters
     launch_k(h, k_fm, dim3(1, 1, nfl), dim3(1024), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, B,
              h->om);
   }
@@ -672,14 +693,14 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
     dp_allreduce(h, h->dp_bnb + (size_t)f0 * 2 * kGH, (size_t)nfl * 2 * kGH);
     k_bn_bwd_apply<<<bng, bnt, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, h->om, h->hp.dp_bg);
     h->launches += 2;
-  } else {
+  } else if (!(hm & 8)) {   // otherwise GX2's epilogue did BatchNorm backward and the Adam update of gamma / beta
     launch_k(h, k_bn_bwd, bng, bnt, 0, h->stream, (const BnDesc*)(h->d_bn + f0), h->om);
   }
   fork_side(h);
   launch_gemm(h, OP_GW1, f0, nfl, 0, h->side);
   if (!deferred_join(h) || from_stage) join_side(h);
   dp_allreduce_grads(h, 1);
-  launch_adam(h, f0, nfl, 1);
+  if ((hm & 10) != 10) launch_adam(h, f0, nfl, 1, (hm & 8) != 0);      // gamma / beta and the counters, unless heads took both over
   dp_allreduce(h, h->d_step_stats + ((size_t)t * h->nf + f0) * 4, (size_t)nfl * 4);
 }
 
@@ -688,6 +709,7 @@ void enqueue_nn_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage, in
   const mrgan_config& c = h->cfg;
   // a ragged batch (n < batch) runs at full height: k_loss_mse zeroes the gradient rows >= n, so the
   // stale rows contribute nothing to dW/db and every GEMM keeps its static shape
+  h->hp.t = t;
   launch_prep(h, f0, nfl, 2, from_stage, t, n);
   for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 0);
   launch_k(h, k_loss_mse, dim3(1, 1, nfl), dim3(256), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, n, h->R,
@@ -962,6 +984,9 @@ int tc_setup(mrgan_handle* h) {
     g_l2_promo = atoi(pr) == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (atoi(pr) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                  : (atoi(pr) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
   const int nf = h->nf;
+  // reductions fused into GEMM epilogues: the reference batch regime (one batch tile, batch statistics local to the GPU)
+  h->tc_heads = (h->cfg.model == MRGAN_MODEL_GAN && h->tc_fused_adam && !h->d_dpbufs && h->R <= 256 && h->cfg.n_classes <= 32) ? 15 : 0;
+  if (const char* hv = getenv("MRGAN_HEADS")) h->tc_heads &= atoi(hv);      // A/B switch (bit mask)
   std::vector<TcOp> ops((size_t)NUM_OPS * nf);
   memset(ops.data(), 0, ops.size() * sizeof(TcOp));
   for (int op = 0; op < NUM_OPS; ++op) {
@@ -979,6 +1004,15 @@ int tc_setup(mrgan_handle* h) {
         t.g = g;                // the epilogue keeps addressing the fp32 buffers (and derives the copies' addresses itself)
       } else if (!tc_fill_op(fn, t, g, mode)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
       t.net = (op == OP_GW1 || op == OP_GW2 || op == OP_GW3) ? 1 : 0;
+      if (h->tc_heads) {
+        t.stats = h->d_step_stats + (size_t)f * 4;
+        t.stats_stride = nf * 4;
+        t.mo_off = h->Mo - h->P; t.vo_off = h->Vo - h->P;
+        if (op == OP_D6 && (h->tc_heads & 1)) { t.head = HEAD_DISC; t.hd = h->d_loss + f; t.advance = 1; }
+        else if (op == OP_D5G && (h->tc_heads & 2)) { t.head = HEAD_FM; t.hd = h->d_loss + f; t.advance = (h->tc_heads & 8) ? 1 : 0; }
+        else if (op == OP_G1 && (h->tc_heads & 4)) { t.head = HEAD_BN; t.hd = h->d_bn + f; }
+        else if (op == OP_GX2 && (h->tc_heads & 8)) { t.head = HEAD_BN_BWD; t.hd = h->d_bn + f; }
+      }
       if (mode == 2) {
         if (h->tc_fused_adam) t.epi = EPI_ADAM;
         const size_t off = (size_t)(g.C - h->Gr);
@@ -1102,7 +1136,8 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
     else TC_LAUNCH(h, f16, K_TC_DX_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
     return true;
   }
-  if (!oi.at && h->tc_mt2 && tc_use_mt2(h->tc_maxME[op], bn)) {
+  const bool head_mt2 = (h->tc_heads & 2) && op == OP_D5G;      // feature matching: one CTA sums the loss over all 250 features
+  if (!oi.at && ((h->tc_mt2 && tc_use_mt2(h->tc_maxME[op], bn)) || head_mt2)) {
     grid.x = (h->tc_maxME[op] + 255) / 256;
     const size_t smem = tc_smem_bytes(bn, TC_FWD_STAGES, 2);
     if (!oi.bt) TC_LAUNCH(h, f16, K_TC_FWD2, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
@@ -1196,7 +1231,8 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   h->n_train = folds[0].n_train;
   h->shapes.assign(folds, folds + h->nf);
   h->fb.resize(h->nf);
-  h->hp = AdamHyper{cfg->lr, cfg->beta1, cfg->beta2, cfg->adam_eps, cfg->shared_t, cfg->batch, cfg->batch, 0};
+  h->hp = AdamHyper{cfg->lr, cfg->beta1, cfg->beta2, cfg->adam_eps, cfg->shared_t, cfg->batch, cfg->batch, 0,
+                    cfg->unlabeled_weight, cfg->bn_eps, cfg->n_classes, 0};
   int ne = h->R;
   for (int f = 0; f < h->nf; ++f) ne = folds[f].n_test > ne ? folds[f].n_test : ne;
   h->NE = ne;
