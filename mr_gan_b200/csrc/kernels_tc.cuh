@@ -892,9 +892,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 }  // namespace tc
 
-template <bool F16> struct TcAdamCfg {
-  static constexpr int STAGES = 2, KC = TCA_KC, NB = F16 ? 3 : TCA_NB;
-  static constexpr uint32_t STAGE_BYTES = 2 * 128 * 128;                    // A + B operand tiles
+// KROWS: contraction rows (batch rows) per operand stage.  F16 with KROWS = 32 halves the operand stages (2 x 16 KB), which
+// lets THREE CTAs share an SM: a CTA spends its first microseconds on TMEM allocation, barrier set-up and the operand round
+// trips while only its first chunk buffers are in flight -- with three co-resident CTAs two of them are always streaming.
+template <bool F16, int KROWS> struct TcAdamCfg {
+  static_assert(F16 ? (KROWS == 64 || KROWS == 32) : (KROWS == 32 || KROWS == 16), "operand stage geometry");
+  static constexpr bool SMALL = F16 ? KROWS == 32 : KROWS == 16;            // 16 KB operand stages
+  static constexpr int STAGES = 2, KC = TCA_KC, NB = (F16 || SMALL) ? 3 : TCA_NB;
+  static constexpr int MINB = SMALL ? 3 : 2;                                // CTAs per SM
+  static constexpr uint32_t MN_BOX = 128u * KROWS;                          // one MN-major box: 128 bytes (64 fp16 / 32 fp32) x KROWS rows
+  static constexpr uint32_t STAGE_BYTES = (F16 ? 4 : 8) * MN_BOX;           // A + B operand tiles (128 features each)
   static constexpr uint32_t ARR_BYTES = KC * 128 * 4;                       // one array (W, m or v) of one chunk
   static constexpr uint32_t HALF_BYTES = F16 ? KC * 128 * 2 : 0;            // fp16 copy of the chunk's updated weights
   static constexpr uint32_t CHUNK_BYTES = 3 * ARR_BYTES + HALF_BYTES;
@@ -903,16 +910,18 @@ template <bool F16> struct TcAdamCfg {
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + (size_t)NB * CHUNK_BYTES + 256;
 };
 
-template <bool F16>
-__global__ void __launch_bounds__(192, 2)
+template <bool F16, int KROWS>
+__global__ void __launch_bounds__(192, (TcAdamCfg<F16, KROWS>::MINB))
 k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, AdamHyper hp) {
   using namespace tc;
-  using Cfg = TcAdamCfg<F16>;
+  using Cfg = TcAdamCfg<F16, KROWS>;
   pdl_launch_dependents();
   constexpr int STAGES = Cfg::STAGES, KC = Cfg::KC, NB = Cfg::NB, NBUF = Cfg::NBUF;
   constexpr uint32_t STAGE_BYTES = Cfg::STAGE_BYTES, ARR_BYTES = Cfg::ARR_BYTES, CHUNK_BYTES = Cfg::CHUNK_BYTES;
-  constexpr int KBLK = F16 ? 64 : 32;
-  constexpr uint32_t MN_BOX = F16 ? 8192u : 4096u;
+  constexpr int KBLK = KROWS;
+  constexpr uint32_t MN_BOX = Cfg::MN_BOX;
+  constexpr int MN_BOXES = F16 ? 2 : 4;                      // boxes per 128 features (64 fp16 / 32 fp32 elements wide)
+  constexpr int MN_W = F16 ? 64 : 32;                        // elements per box row
   const TcAdamOp& op = ops[blockIdx.z];
   const int ME = op.ME, NE = op.NE, KE = op.KE;
   const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;     // n-feature tile (lanes), k-feature tile (columns)
@@ -972,12 +981,12 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
         mbar_wait(&empty[s], ph ^ 1u);
         mbar_expect_tx(&full[s], STAGE_BYTES);
         uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
-        uint8_t* sb = sa + 128 * 128;
+        uint8_t* sb = sa + STAGE_BYTES / 2;
         const int k0 = kb * KBLK;
 #pragma unroll
-        for (int b = 0; b < 128 / KBLK; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * MN_BOX, m0 + KBLK * b, k0);
+        for (int b = 0; b < MN_BOXES; ++b) tma_load_2d(&op.mapA, &full[s], sa + b * MN_BOX, m0 + MN_W * b, k0);
 #pragma unroll
-        for (int b = 0; b < 128 / KBLK; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * MN_BOX, n0 + KBLK * b, k0);
+        for (int b = 0; b < MN_BOXES; ++b) tma_load_2d(&op.mapB, &full[s], sb + b * MN_BOX, n0 + MN_W * b, k0);
       }
       // the MMAs have consumed every operand stage once the accumulator is complete: the operand region now takes
       // NX more chunks in flight
@@ -1011,9 +1020,9 @@ k_dw_adam_tc(const TcAdamOp* __restrict__ ops, FoldState* __restrict__ folds, Ad
         const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
         mbar_wait(&full[s], ph);
         fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES), sb = sa + 128 * 128;
+        const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES), sb = sa + STAGE_BYTES / 2;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < KROWS / (F16 ? 16 : 8); ++k) {     // MMAs of K = 16 (f16) / 8 (tf32) contraction rows
           const uint64_t da = smem_desc(sa + k * kstep, lbo, sbo, lay), db = smem_desc(sb + k * kstep, lbo, sbo, lay);
           if (F16) mma_f16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           else mma_tf32(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);

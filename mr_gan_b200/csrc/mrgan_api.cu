@@ -133,6 +133,7 @@ struct mrgan_handle {
   bool tc_fused_adam = true;          // dW epilogue applies Adam in place (no gradient round trip)
   bool tc_mt2 = true;                 // forward / dX: 256 features per CTA where the layer is wide enough (MRGAN_MT2=0 disables)
   bool tc_adam_tma = true;            // ... with W/m/v staged through smem by TMA (k_dw_adam_tc) instead of the LSU
+  bool tc_dw_small = true;            // dW+Adam: 16 KB operand stages (32 fp16 / 16 fp32 batch rows) -> three CTAs per SM; MRGAN_DW_SMALL=0: two
   int tc_heads = 0;                   // losses / feature matching / BatchNorm fused into GEMM epilogues (set by tc_setup), bit mask:
                                       // 1 = HEAD_DISC (no k_loss_disc, no k_adam of D), 2 = HEAD_FM (no k_fm), 4 = HEAD_BN (no k_bn_fwd),
                                       // 8 = HEAD_BN_BWD (no k_bn_bwd); 2 and 8 together also retire the generator's k_adam
@@ -930,7 +931,8 @@ template <bool F> void tc_set_smem_attr_fmt() {
   cudaFuncSetAttribute(K_TC_FWD2(F), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(K_TC_DX2(F), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   cudaFuncSetAttribute(K_TC_DW(F), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(128, TC_DW_STAGES));
-  cudaFuncSetAttribute(k_dw_adam_tc<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcAdamCfg<F>::SMEM);
+  cudaFuncSetAttribute(k_dw_adam_tc<F, (F ? 64 : 32)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcAdamCfg<F, (F ? 64 : 32)>::SMEM);
+  cudaFuncSetAttribute(k_dw_adam_tc<F, (F ? 32 : 16)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcAdamCfg<F, (F ? 32 : 16)>::SMEM);
 }
 void tc_set_smem_attr() { tc_set_smem_attr_fmt<false>(); tc_set_smem_attr_fmt<true>(); }
 
@@ -987,6 +989,7 @@ int tc_setup(mrgan_handle* h) {
   // reductions fused into GEMM epilogues: the reference batch regime (one batch tile, batch statistics local to the GPU)
   h->tc_heads = (h->cfg.model == MRGAN_MODEL_GAN && h->tc_fused_adam && !h->d_dpbufs && h->R <= 256 && h->cfg.n_classes <= 32) ? 15 : 0;
   if (const char* hv = getenv("MRGAN_HEADS")) h->tc_heads &= atoi(hv);      // A/B switch (bit mask)
+  if (const char* kr = getenv("MRGAN_DW_SMALL")) h->tc_dw_small = atoi(kr) != 0;
   std::vector<TcOp> ops((size_t)NUM_OPS * nf);
   memset(ops.data(), 0, ops.size() * sizeof(TcOp));
   for (int op = 0; op < NUM_OPS; ++op) {
@@ -1068,6 +1071,18 @@ int tc_setup(mrgan_handle* h) {
         const TcOp& t = ops[(size_t)op * nf + f];
         TcAdamOp& a = aops[(size_t)op * nf + f];
         a.mapA = t.mapA; a.mapB = t.mapB; a.ME = t.ME; a.NE = t.NE; a.KE = t.KE; a.fold = t.g.fold; a.net = t.net;
+        if (h->tc_dw_small) {      // operand boxes of 32 (fp16) / 16 (fp32) batch rows: 16 KB stages
+          const GemmDesc& g = t.g;
+          bool ok;
+          if (h->om.mode == 2) {
+            const __half* hA = h->harena + (g.A - h->om.fbase);
+            const __half* hB = h->harena + (g.B - h->om.fbase);
+            ok = make_map(fn, &a.mapA, hB, g.N, g.K, g.ldb, 32, true, 0, 2) && make_map(fn, &a.mapB, hA, g.M, g.K, g.lda, 32, true, 0, 2);
+          } else {
+            ok = make_map(fn, &a.mapA, g.B, g.N, g.K, g.ldb, 16, true) && make_map(fn, &a.mapB, g.A, g.M, g.K, g.lda, 16, true);
+          }
+          if (!ok) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled (dW operands) failed");
+        }
         a.ginv = h->om.mode == 2 ? 1.0f / h->om.gscale : 1.0f;
         // fp16 operand copy of W (refreshed with every update), same geometry as the fp32 tensor
         if (h->om.mode == 2 && !make_map(fn, &a.mapH, h->harena + (t.P - h->om.fbase), t.ME, t.NE, t.g.ldc, TCA_KC, false, 128, 2))
@@ -1159,8 +1174,11 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
   }
   else if (h->d_tcadam) {
     const TcAdamOp* ad = h->d_tcadam + (size_t)op * h->nf + f0;
-    if (f16) launch_k(h, k_dw_adam_tc<true>, grid, dim3(192), TcAdamCfg<true>::SMEM, st, ad, h->d_folds, h->hp);
-    else launch_k(h, k_dw_adam_tc<false>, grid, dim3(192), TcAdamCfg<false>::SMEM, st, ad, h->d_folds, h->hp);
+    // small operand stages: three CTAs per SM (default); MRGAN_DW_SMALL=0: the two-CTA configuration (A/B)
+    if (f16 && h->tc_dw_small) launch_k(h, k_dw_adam_tc<true, 32>, grid, dim3(192), TcAdamCfg<true, 32>::SMEM, st, ad, h->d_folds, h->hp);
+    else if (f16) launch_k(h, k_dw_adam_tc<true, 64>, grid, dim3(192), TcAdamCfg<true, 64>::SMEM, st, ad, h->d_folds, h->hp);
+    else if (h->tc_dw_small) launch_k(h, k_dw_adam_tc<false, 16>, grid, dim3(192), TcAdamCfg<false, 16>::SMEM, st, ad, h->d_folds, h->hp);
+    else launch_k(h, k_dw_adam_tc<false, 32>, grid, dim3(192), TcAdamCfg<false, 32>::SMEM, st, ad, h->d_folds, h->hp);
   }
   else TC_LAUNCH(h, f16, K_TC_DW, grid, dim3(TC_DW_THREADS), tc_smem_bytes(bn, TC_DW_STAGES), st, d, h->d_folds, 0, h->hp, h->om);
   return true;
