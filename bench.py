@@ -224,7 +224,12 @@ def measure_dp(args, precision, rank, world, local, barrier, min_seconds=1.5, pa
     if world > 1:
         uid = [FoldGroup.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
-        fg.dp_init(rank, world, uid[0])
+
+        def allgather(b):                               # CUDA IPC handles of every rank's arena: fused peer-memory exchange
+            out = [None] * world
+            dist.all_gather_object(out, b)
+            return out
+        fg.dp_init(rank, world, uid[0], allgather=None if os.environ.get("MRGAN_DP_FUSED") == "0" else allgather)
     fg.set_params(0, 1, pG)
     fg.set_params(0, 0, pD)
     fg.load_fold(0, Xg[rows], yg[rows], Xg[:600], yg[:600])
@@ -264,8 +269,10 @@ def measure_dp(args, precision, rank, world, local, barrier, min_seconds=1.5, pa
     rec = {"value": value, "unit": UNIT, "ms_per_pair": dev_ms / pairs, "epochs_timed": K, "pairs_per_epoch": nb,
            "workload": "mr_gan.py table-5 fold at large batch, data-parallel: D=%d (1 s contact mic), global batch %d (%d per GPU)"
                        % (D, Bg, Bl),
-           "parallelism": "dp%d, NCCL all-reduce of BN / feature-matching statistics and flat gradients (%.0f MB D + %.0f MB G per pair)"
-                          % (world, 4e-6 * N_D, 4e-6 * N_G),
+           "parallelism": "dp%d: %s of the flat gradients (%.0f MB D + %.0f MB G per pair); NCCL all-reduce of the BN / "
+                          "feature-matching statistics; epoch captured as one CUDA graph"
+                          % (world, "NCCL all-reduce + full Adam" if os.environ.get("MRGAN_DP_FUSED") == "0" or world == 1 else
+                             "fused peer-memory reduce-scatter + sharded Adam + all-gather (k_dp_exchange)", 4e-6 * N_D, 4e-6 * N_G),
            "precision": precision, "scaling": "strong", "e2e_value": pairs / (wall_ms * 1e-3), "gpu_launches": int(launches),
            "achieved_tflops": ach, "tensor_frac_of_bf16_peak": ach / (tf * world), "peak_source": how, "clocks": clocks,
            "last_loss_lab": float(st[0, 0]), "last_loss_gen": float(st[0, 3])}

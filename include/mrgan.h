@@ -143,6 +143,14 @@ int  mrgan_eval(mrgan_handle* h, int fold, float* err);
  *   mrgan_nccl_unique_id: 128 bytes from ncclGetUniqueId (call on rank 0, broadcast with any host transport). */
 int  mrgan_nccl_unique_id(void* id128);
 int  mrgan_dp_init(mrgan_handle* h, int rank, int world, const void* id128);
+/* Fused gradient exchange over NVLink peer memory (csrc/kernels_dp.cuh): after mrgan_dp_init every rank exports 128 bytes
+ * (CUDA IPC handles of its arenas), the host exchanges them with any transport, and every rank opens all of them.  From
+ * then on the per-step exchange is ONE kernel per rank -- reduce-scatter of the flat gradient by peer loads, Adam on the
+ * owned 1/W shard, all-gather of the updated weights by peer stores -- instead of ncclAllReduce + a full-size Adam
+ * (which remains the path when the handles are not opened, or with MRGAN_DP_FUSED=0).
+ *   handles: world x 128 bytes, rank-major. */
+int  mrgan_dp_ipc_export(mrgan_handle* h, void* out128);
+int  mrgan_dp_ipc_open(mrgan_handle* h, const void* handles, int world);
 /* The same data-parallel path with VIRTUAL ranks on one GPU (test / single-GPU validation of everything but the
  * transport): the handle must hold exactly `world` folds of identical shape and noise key; fold r plays rank r
  * (its resident rows are rank r's slice of the global batch) and every collective is a rank-ordered local sum over

@@ -58,6 +58,8 @@ SYMBOLS = {
     "mrgan_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mrgan_dp_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),
     "mrgan_dp_init_virtual": (C.c_int, [_H, C.c_int]),
+    "mrgan_dp_ipc_export": (C.c_int, [_H, C.c_void_p]),
+    "mrgan_dp_ipc_open": (C.c_int, [_H, C.c_void_p, C.c_int]),
     "mrnn_step": (C.c_int, [_H, C.c_int, _fp, _ip, C.c_int, _fp]),
     "mrnn_train_epoch": (C.c_int, [_H, _ip, C.c_int, _fp]),
     "mrnn_evaluate": (C.c_int, [_H, C.c_int, _fp]),

@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libmrgan.so")
 HASH = LIB + ".hash"
 LOCK = os.path.join(HERE, ".build.lock")
 SOURCES = ["mrgan_api.cu"]
-HEADERS = ["common.cuh", "kernels_simt.cuh", "kernels_tc.cuh", os.path.join("..", "..", "include", "mrgan.h")]
+HEADERS = ["common.cuh", "kernels_simt.cuh", "kernels_tc.cuh", "kernels_dp.cuh", os.path.join("..", "..", "include", "mrgan.h")]
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-shared", "-ldl", "-DMRGAN_WITH_TC", "-lcuda"]
 

@@ -17,6 +17,7 @@
 #ifdef MRGAN_WITH_TC
 #include "kernels_tc.cuh"
 #endif
+#include "kernels_dp.cuh"
 
 namespace {
 
@@ -122,6 +123,11 @@ struct mrgan_handle {
   double* d_prep_stats = nullptr; int* d_prep_rows = nullptr; int prep_rows_cap = 0, prep_stats_cap = 0;
   int dp_world = 1, dp_rank = 0;
   bool dp_virtual = false;            // the handle's folds play the ranks (mrgan_dp_init_virtual): collectives are local sums
+  // fused gradient exchange (kernels_dp.cuh): peer mappings of every rank's arena (cudaIpc), flag blocks, per-net pointer sets
+  bool dp_fused = false;
+  unsigned* d_dpflags = nullptr;      // DP_MAX_RANKS x DP_FLAG_WORDS words inside the arena (zero at creation)
+  char* peer_arena[DP_MAX_RANKS] = {nullptr}; __half* peer_harena[DP_MAX_RANKS] = {nullptr};
+  DpPeers dp_peers[2];                // [net]
   void* nccl_comm = nullptr;
   float* d_dpmem = nullptr; DpBufs* d_dpbufs = nullptr;
   float *dp_bnf = nullptr, *dp_bnb = nullptr, *dp_fm = nullptr;   // [nf][2*500], [nf][2*500], [nf][2*250]
@@ -239,6 +245,7 @@ void layout_buffers(mrgan_handle* h, Arena& ar) {
   h->d_ranges[0] = ar.take<AdamRange>(nf);
   h->d_ranges[1] = ar.take<AdamRange>(nf);
   h->d_step_stats = ar.take<float>((size_t)(h->n_train / B + 1) * nf * 4);
+  h->d_dpflags = ar.take<unsigned>((size_t)DP_MAX_RANKS * DP_FLAG_WORDS);
   h->d_epoch_stats = ar.take<float>((size_t)nf * 8);
   for (int f = 0; f < nf; ++f) {
     FoldBuffers& b = h->fb[f];
@@ -519,6 +526,62 @@ void dp_allreduce_grads(mrgan_handle* h, int net) {
   dp_allreduce(h, h->Gr + h->net[net][0].off, (size_t)n);      // the nets of all folds are contiguous in the flat buffer
 }
 
+void launch_adam(mrgan_handle* h, int f0, int nfl, int net, bool counters_only);
+
+// Pointer sets of the fused exchange.  Real ranks: the same offsets inside every rank's (IPC-mapped) arena.  Virtual ranks:
+// fold r's net inside this handle's own flat buffers.
+void dp_build_peers(mrgan_handle* h) {
+  const float* abase = reinterpret_cast<const float*>(h->arena);
+  for (int net = 0; net < 2; ++net) {
+    DpPeers& pp = h->dp_peers[net];
+    memset(&pp, 0, sizeof(pp));
+    if (h->net[net].empty()) continue;
+    for (int p = 0; p < h->dp_world; ++p) {
+      if (h->dp_virtual) {
+        const long long d = h->net[net][p].off - h->net[net][0].off;
+        pp.P[p] = h->P + d; pp.Gr[p] = h->Gr + d; pp.Mo[p] = h->Mo + d; pp.Vo[p] = h->Vo + d;
+        pp.Ph[p] = h->harena ? h->harena + (h->P - abase) + d : nullptr;
+        pp.flags[p] = h->d_dpflags + (size_t)p * DP_FLAG_WORDS;
+      } else {
+        float* pb = reinterpret_cast<float*>(h->peer_arena[p]);
+        pp.P[p] = pb + (h->P - abase); pp.Gr[p] = pb + (h->Gr - abase); pp.Mo[p] = pb + (h->Mo - abase); pp.Vo[p] = pb + (h->Vo - abase);
+        pp.Ph[p] = h->peer_harena[p] ? h->peer_harena[p] + (h->P - abase) : nullptr;
+        pp.flags[p] = reinterpret_cast<unsigned*>(h->peer_arena[p] + (reinterpret_cast<char*>(h->d_dpflags) - h->arena));
+      }
+    }
+  }
+}
+
+// One kernel per rank: reduce-scatter of the net's flat gradient by peer loads, Adam on the owned shard, all-gather of the
+// updated weights by peer stores, step counters (kernels_dp.cuh).  Replaces ncclAllReduce + the full-size k_adam.
+void dp_exchange(mrgan_handle* h, int net) {
+  long long len = 0;
+  if (h->dp_virtual) len = h->net[net][0].n;
+  else for (int f = 0; f < h->nf; ++f) len += h->net[net][f].n;
+  const long long off = h->net[net][0].off;
+  const int W = h->dp_world;
+  const int bx = h->dp_virtual ? std::max(1, 296 / W) : 296;      // all CTAs co-resident (2 per SM): they wait on one another
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(bx, h->dp_virtual ? W : 1, 1); cfg.blockDim = dim3(256); cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  const float ginv = h->om.mode == 2 ? 1.0f / h->om.gscale : 1.0f;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, k_dp_exchange, h->dp_peers[net], W, h->dp_virtual ? -1 : h->dp_rank, off, len, h->d_folds,
+                                           h->nf, net, h->hp, ginv);
+  if (e != cudaSuccess && !h->sticky) { h->sticky = MRGAN_ERR_CUDA; h->err = std::string("k_dp_exchange launch: ") + cudaGetErrorString(e); }
+  h->launches++;
+}
+
+// gradient exchange + optimizer of one net in the data-parallel mode
+void dp_update(mrgan_handle* h, int f0, int nfl, int net) {
+  if (h->dp_fused) { dp_exchange(h, net); return; }
+  dp_allreduce_grads(h, net);
+  launch_adam(h, f0, nfl, net, false);
+}
+
 // Scratch of the split (statistics -> [all-reduce] -> apply) BatchNorm / feature-matching kernels: used by the data-parallel
 // mode and, on one GPU, by the large-batch regime where one CTA per fold would serialise thousands of rows.
 int alloc_split_bufs(mrgan_handle* h) {
@@ -582,7 +645,7 @@ void launch_prep(mrgan_handle* h, int f0, int nfl, int mode, int from_stage, int
            h->om);
 }
 
-void launch_adam(mrgan_handle* h, int f0, int nfl, int net, bool counters_only = false) {
+void launch_adam(mrgan_handle* h, int f0, int nfl, int net, bool counters_only) {
   long long nmax = 0;
   for (int f = f0; f < f0 + nfl; ++f) nmax = h->net[net][f].n > nmax ? h->net[net][f].n : nmax;
   int blocks = (int)((nmax / 4 + 255) / 256);
@@ -654,8 +717,8 @@ void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) 
     launch_gemm(h, OP_DW1 + l - 1, f0, nfl, 0, h->side);
   }
   if (!deferred_join(h) || from_stage) join_side(h);   // deferred: dW1+Adam overlaps the next G step's generator forward
-  dp_allreduce_grads(h, 0);
-  if (!heads) launch_adam(h, f0, nfl, 0);
+  if (h->dp_world > 1) dp_update(h, f0, nfl, 0);
+  else if (!heads) launch_adam(h, f0, nfl, 0, false);
   if (from_stage) dp_allreduce(h, h->d_step_stats + ((size_t)t * h->nf + f0) * 4, (size_t)nfl * 4);
 }
 
@@ -700,8 +763,8 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   fork_side(h);
   launch_gemm(h, OP_GW1, f0, nfl, 0, h->side);
   if (!deferred_join(h) || from_stage) join_side(h);
-  dp_allreduce_grads(h, 1);
-  if ((hm & 10) != 10) launch_adam(h, f0, nfl, 1, (hm & 8) != 0);      // gamma / beta and the counters, unless heads took both over
+  if (h->dp_world > 1) dp_update(h, f0, nfl, 1);
+  else if ((hm & 10) != 10) launch_adam(h, f0, nfl, 1, (hm & 8) != 0);      // gamma / beta and the counters, unless heads took both over
   dp_allreduce(h, h->d_step_stats + ((size_t)t * h->nf + f0) * 4, (size_t)nfl * 4);
 }
 
@@ -721,7 +784,7 @@ void enqueue_nn_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage, in
     launch_gemm(h, OP_DW1 + l - 1, f0, nfl, 0, h->side);
   }
   join_side(h);
-  launch_adam(h, f0, nfl, 0);
+  launch_adam(h, f0, nfl, 0, false);
 }
 
 // test_batch (mr_gan.py:171): phase 0, no noise
@@ -784,7 +847,7 @@ int build_graph(mrgan_handle* h, int key, int nb, int n_idx_nn) {
   CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   {
     cudaStream_t origin = h->stream, origin_side = h->side;
-    const int nch = h->nchains;
+    const int nch = h->dp_world > 1 ? 1 : h->nchains;      // collectives: one chain, the same order on every rank
     cudaEvent_t e = h->ev_pool[h->ev_next++ & 15];
     cudaEventRecord(e, origin);
     for (int ch = 1; ch < nch; ++ch) cudaStreamWaitEvent(h->cmain[ch], e, 0);
@@ -1347,6 +1410,11 @@ int mrgan_destroy(mrgan_handle* h) {
   if (h->d_prep_stats) cudaFree(h->d_prep_stats);
   if (h->d_prep_rows) cudaFree(h->d_prep_rows);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+  if (!h->dp_virtual)
+    for (int p = 0; p < DP_MAX_RANKS; ++p) {
+      if (h->peer_arena[p] && h->peer_arena[p] != h->arena) cudaIpcCloseMemHandle(h->peer_arena[p]);
+      if (h->peer_harena[p] && h->peer_harena[p] != h->harena) cudaIpcCloseMemHandle(h->peer_harena[p]);
+    }
   if (h->d_dpmem) cudaFree(h->d_dpmem);
   if (h->d_dpbufs) cudaFree(h->d_dpbufs);
 #ifdef MRGAN_WITH_TC
@@ -1647,7 +1715,10 @@ int mrgan_train_epoch(mrgan_handle* h, const int32_t* idx_lab, const int32_t* id
       return fail(h, MRGAN_ERR_ARG, "train_epoch: row index out of range");
   CK(cudaSetDevice(h->cfg.device));
   int rc = finish_pending(h); if (rc) return rc;
-  const bool eager = h->dp_world > 1;      // data-parallel epochs interleave NCCL collectives: enqueue step by step
+  // data-parallel epochs are captured like the others (NCCL collectives and the fused exchange are stream-ordered graph
+  // nodes; one chain, so every rank issues them in the same order); MRGAN_DP_GRAPH=0 enqueues them step by step instead
+  static const bool dp_graph = !(getenv("MRGAN_DP_GRAPH") && atoi(getenv("MRGAN_DP_GRAPH")) == 0);
+  const bool eager = h->dp_world > 1 && !dp_graph;
   if (!eager) { rc = build_graph(h, nb, nb, 0); if (rc) return rc; }
   const int32_t* streams[3] = {idx_lab, idx_unl, idx_unl2};
   rc = upload_indices(h, streams, 3, h->n_train); if (rc) return rc;
@@ -1791,8 +1862,8 @@ int mrgan_time_op(mrgan_handle* h, int which, int reps, float* ms_avg) {
   int rc = finish_pending(h); if (rc) return rc;
   auto once = [&]() {
     switch (which) {
-      case MRGAN_TIME_ADAM_D: launch_adam(h, 0, h->nf, 0); break;
-      case MRGAN_TIME_ADAM_G: launch_adam(h, 0, h->nf, 1); break;
+      case MRGAN_TIME_ADAM_D: launch_adam(h, 0, h->nf, 0, false); break;
+      case MRGAN_TIME_ADAM_G: launch_adam(h, 0, h->nf, 1, false); break;
       case MRGAN_TIME_DW1: launch_gemm(h, OP_DW1, 0, h->nf, 0); break;
       case MRGAN_TIME_FWD1: launch_gemm(h, OP_D1, 0, h->nf, 0); break;
       case MRGAN_TIME_DISC_STEP: if (gan) enqueue_disc_step(h, 0, h->nf, 0, 0); else enqueue_nn_step(h, 0, h->nf, 0, 0, h->cfg.batch); break;
@@ -1827,6 +1898,7 @@ int mrgan_nccl_unique_id(void* id128) {
 int mrgan_dp_init(mrgan_handle* h, int rank, int world, const void* id128) {
   if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
   if (world < 1 || rank < 0 || rank >= world || !id128) return fail(h, MRGAN_ERR_ARG, "dp_init: bad rank / world / id");
+  if (world > DP_MAX_RANKS) return fail(h, MRGAN_ERR_ARG, "dp_init: at most 8 ranks (one NVSwitch domain)");
   if (h->cfg.model != MRGAN_MODEL_GAN) return fail(h, MRGAN_ERR_STATE, "dp_init: data-parallel mode is implemented for the GAN model");
   if (h->dp_world > 1 || h->nccl_comm) return fail(h, MRGAN_ERR_STATE, "dp_init called twice");
   if (world == 1) return MRGAN_OK;
@@ -1853,6 +1925,47 @@ int mrgan_dp_init(mrgan_handle* h, int rank, int world, const void* id128) {
   return MRGAN_OK;
 }
 
+int mrgan_dp_ipc_export(mrgan_handle* h, void* out128) {
+  if (!h || !out128) return fail(h, MRGAN_ERR_ARG, "dp_ipc_export: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  memset(out128, 0, 128);
+  cudaIpcMemHandle_t a;
+  CK(cudaIpcGetMemHandle(&a, h->arena));
+  memcpy(out128, &a, sizeof(a));
+  if (h->harena) {
+    CK(cudaIpcGetMemHandle(&a, h->harena));
+    memcpy(static_cast<char*>(out128) + 64, &a, sizeof(a));
+  }
+  return MRGAN_OK;
+}
+
+int mrgan_dp_ipc_open(mrgan_handle* h, const void* handles, int world) {
+  if (!h || !handles) return fail(h, MRGAN_ERR_ARG, "dp_ipc_open: null argument");
+  if (h->dp_world != world || world < 2 || world > DP_MAX_RANKS || h->dp_virtual)
+    return fail(h, MRGAN_ERR_STATE, "dp_ipc_open: call after mrgan_dp_init with the same world size (at most 8 ranks)");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = finish_pending(h); if (rc) return rc;
+  const char* hb = static_cast<const char*>(handles);
+  for (int p = 0; p < world; ++p) {
+    if (p == h->dp_rank) { h->peer_arena[p] = h->arena; h->peer_harena[p] = h->harena; continue; }
+    cudaIpcMemHandle_t a;
+    memcpy(&a, hb + (size_t)p * 128, sizeof(a));
+    void* ptr = nullptr;
+    CK(cudaIpcOpenMemHandle(&ptr, a, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_arena[p] = static_cast<char*>(ptr);
+    if (h->harena) {
+      memcpy(&a, hb + (size_t)p * 128 + 64, sizeof(a));
+      CK(cudaIpcOpenMemHandle(&ptr, a, cudaIpcMemLazyEnablePeerAccess));
+      h->peer_harena[p] = static_cast<__half*>(ptr);
+    }
+  }
+  h->dp_fused = !(getenv("MRGAN_DP_FUSED") && atoi(getenv("MRGAN_DP_FUSED")) == 0);
+  dp_build_peers(h);
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  h->graphs.clear(); h->graph_nodes.clear();
+  return MRGAN_OK;
+}
+
 int mrgan_dp_init_virtual(mrgan_handle* h, int world) {
   if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
   if (h->cfg.model != MRGAN_MODEL_GAN) return fail(h, MRGAN_ERR_STATE, "dp_init_virtual: data-parallel mode is implemented for the GAN model");
@@ -1865,8 +1978,11 @@ int mrgan_dp_init_virtual(mrgan_handle* h, int world) {
   CK(cudaSetDevice(h->cfg.device));
   int rc = finish_pending(h); if (rc) return rc;
   rc = alloc_split_bufs(h); if (rc) return rc;
+  if (world > DP_MAX_RANKS) return fail(h, MRGAN_ERR_ARG, "dp_init_virtual: at most 8 ranks");
   h->dp_world = world; h->dp_rank = 0; h->dp_virtual = true;
   h->hp.dp_bloc = h->cfg.batch; h->hp.dp_bg = h->cfg.batch * world; h->hp.dp_rank = -1;     // -1: rank = fold index (common.cuh)
+  h->dp_fused = !(getenv("MRGAN_DP_FUSED") && atoi(getenv("MRGAN_DP_FUSED")) == 0);
+  dp_build_peers(h);
 #ifdef MRGAN_WITH_TC
   if (h->cfg.precision != MRGAN_PREC_FP32) {   // gradients must be all-reduced before Adam: dW stores them, k_adam applies
     tc_teardown(h);

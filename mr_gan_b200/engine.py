@@ -75,11 +75,24 @@ class FoldGroup:
             raise MrganError("mrgan_nccl_unique_id: %s" % lib.mrgan_last_error(None).decode())
         return buf.raw
 
-    def dp_init(self, rank, world, unique_id):
-        """Join a data-parallel group: this handle's `batch` becomes the LOCAL batch (global = world * batch)."""
+    def dp_init(self, rank, world, unique_id, allgather=None):
+        """Join a data-parallel group: this handle's `batch` becomes the LOCAL batch (global = world * batch).
+
+        allgather: optional callable bytes -> list of `world` bytes objects (rank order), e.g. built on
+        ``torch.distributed.all_gather_object``.  When given, the ranks exchange the CUDA IPC handles of their arenas and the
+        per-step gradient exchange becomes the fused peer-memory kernel (reduce-scatter + sharded Adam + all-gather);
+        otherwise it is ncclAllReduce + a full Adam on every rank."""
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._chk(self.lib.mrgan_dp_init(self._h, int(rank), int(world), buf))
         self.dp_rank, self.dp_world = int(rank), int(world)
+        if allgather is not None and world > 1:
+            mine = C.create_string_buffer(128)
+            self._chk(self.lib.mrgan_dp_ipc_export(self._h, mine))
+            every = allgather(mine.raw)
+            if len(every) != world or any(len(b) != 128 for b in every):
+                raise ValueError("dp_init: allgather must return one 128-byte handle block per rank")
+            blob = C.create_string_buffer(b"".join(every), 128 * world)
+            self._chk(self.lib.mrgan_dp_ipc_open(self._h, blob, int(world)))
 
     def dp_init_virtual(self, world):
         """The data-parallel path with the handle's `world` folds playing the ranks on ONE GPU (collectives become

@@ -38,7 +38,11 @@ def run(batch, dp):
     out = []
     with FoldGroup([(D, max(2 * batch, 64), 16, 12345)], precision=a.precision, batch=batch, device=local) as fg:
         if dp:
-            fg.dp_init(rank, world, uid[0])
+            def allgather(b):
+                out = [None] * world
+                dist.all_gather_object(out, b)
+                return out
+            fg.dp_init(rank, world, uid[0], allgather=None if os.environ.get("MRGAN_DP_FUSED") == "0" else allgather)
         fg.set_params(0, 0, pD); fg.set_params(0, 1, pG)
         for s in steps:
             sel = sl if dp else slice(None)
