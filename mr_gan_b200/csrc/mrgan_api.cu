@@ -135,6 +135,7 @@ struct mrgan_handle {
   TcOp* d_tcops = nullptr;            // [NUM_OPS][nf] tensor maps + epilogue descriptors
   int tc_bn[NUM_OPS] = {0}, tc_maxME[NUM_OPS] = {0}, tc_maxNE[NUM_OPS] = {0};
   int tc_ksplit[NUM_OPS] = {0};       // large-batch dW: contraction slices per tile (deterministic split-K), 0/1 = off
+  bool tc_mt1[NUM_OPS] = {false};     // large-batch forward / dX whose 256 x 256 tiling would leave SMs idle: 128-feature CTAs (tc_pick_tile)
   float* d_tcws = nullptr;            // ... and their partial-product workspace
   bool tc_fused_adam = true;          // dW epilogue applies Adam in place (no gradient round trip)
   bool tc_mt2 = true;                 // forward / dX: 256 features per CTA where the layer is wide enough (MRGAN_MT2=0 disables)
@@ -1001,19 +1002,31 @@ void tc_set_smem_attr() { tc_set_smem_attr_fmt<false>(); tc_set_smem_attr_fmt<tr
 
 // fills the tcgen05 view of one GEMM (shapes in the fp32 path's convention); mode 0 fwd, 1 dX, 2 dW
 // esz = 2: g.A / g.B point at fp16 operand copies (pitches in elements); the epilogue side of g is unchanged.
-bool tc_fill_op(EncodeTiledFn fn, TcOp& t, const GemmDesc& g, int mode, int esz = 4) {
+// Large-batch forward / dX (more than 256 stacked rows): batch rows per tile and feature sub-tiles per CTA.  256 x 256
+// tiles are the efficient shape, but a narrow layer or a rank's slice of the batch leaves most of the 148 SMs without a
+// tile (D layer 1 at 3072 local rows: 4 x 12 = 48 CTAs; the generator's dX over K = 12032: 2 x 4 = 8 CTAs, each alone on
+// a 188-step contraction): fall back to 128-feature CTAs and then to narrower row tiles until the grid fills the chip.
+void tc_pick_tile(int rows, int feats, int nf, int* bn, bool* mt1) {
+  *bn = 256; *mt1 = false;
+  auto tiles = [&](int b, bool one) { return ((feats + (one ? 127 : 255)) / (one ? 128 : 256)) * ((rows + b - 1) / b) * nf; };
+  if (tiles(256, false) >= 120) return;
+  *mt1 = true;
+  for (int b : {256, 128, 64}) { *bn = b; if (tiles(b, true) >= 120) return; }
+}
+
+bool tc_fill_op(EncodeTiledFn fn, TcOp& t, const GemmDesc& g, int mode, int esz = 4, int bn_big = 256) {
   t.g = g;
   t.esz = esz;
   t.ME = g.N; t.NE = g.M; t.KE = g.K;
   const int kb = 128 / esz;   // contraction rows of an MN-major box = elements of one 128-byte row
   if (mode == 0) {            // forward: C[M rows, N feats] = act[M, K] @ W[K, N]
     t.epi = EPI_FWD;
-    t.bn = g.M <= 256 ? round_up(g.M, 16) : 256;
+    t.bn = g.M <= 256 ? round_up(g.M, 16) : bn_big;
     return make_map(fn, &t.mapA, g.B, g.N, g.K, g.ldb, kb, true, 0, esz) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false, 0, esz);
   }
   if (mode == 1) {            // dX: C[M rows, N in-feats] = dZ[M, K] @ W[N, K]^T
     t.epi = EPI_DX;
-    t.bn = g.M <= 256 ? round_up(g.M, 16) : 256;
+    t.bn = g.M <= 256 ? round_up(g.M, 16) : bn_big;
     return make_map(fn, &t.mapA, g.B, g.K, g.N, g.ldb, 128, false, 0, esz) && make_map(fn, &t.mapB, g.A, g.K, g.M, g.lda, t.bn, false, 0, esz);
   }
   t.epi = EPI_STORE;          // dW: C[M in-feats(+1), N out-feats] = act[K rows, M]^T @ dZ[K rows, N]
@@ -1062,13 +1075,15 @@ int tc_setup(mrgan_handle* h) {
       const GemmDesc& g = h->h_descs[(size_t)op * nf + f];
       TcOp& t = ops[(size_t)op * nf + f];
       const int mode = (!oi.at && !oi.bt) ? 0 : ((!oi.at && oi.bt) ? 1 : 2);
+      int bn_big = 256;
+      if (mode != 2 && oi.maxM > 256) { bool m1; tc_pick_tile(oi.maxM, oi.maxN, nf, &bn_big, &m1); h->tc_mt1[op] = m1; }
       if (h->om.mode == 2) {    // operands come from the fp16 copies (same element offsets and pitches as the fp32 buffers)
         GemmDesc gh = g;
         gh.A = reinterpret_cast<const float*>(h->harena + (g.A - h->om.fbase));
         gh.B = reinterpret_cast<const float*>(h->harena + (g.B - h->om.fbase));
-        if (!tc_fill_op(fn, t, gh, mode, 2)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled (fp16 operands) failed");
+        if (!tc_fill_op(fn, t, gh, mode, 2, bn_big)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled (fp16 operands) failed");
         t.g = g;                // the epilogue keeps addressing the fp32 buffers (and derives the copies' addresses itself)
-      } else if (!tc_fill_op(fn, t, g, mode)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+      } else if (!tc_fill_op(fn, t, g, mode, 4, bn_big)) return fail(nullptr, MRGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
       t.net = (op == OP_GW1 || op == OP_GW2 || op == OP_GW3) ? 1 : 0;
       if (h->tc_heads) {
         t.stats = h->d_step_stats + (size_t)f * 4;
@@ -1184,7 +1199,7 @@ void tc_teardown(mrgan_handle* h) {
   h->d_tcws = nullptr;
   for (int i = 0; i < NUM_OPS; ++i) h->tc_ksplit[i] = 0;
   for (int n = 0; n < 2; ++n) { if (h->d_ranges_tc[n]) cudaFree(h->d_ranges_tc[n]); h->d_ranges_tc[n] = nullptr; }
-  for (int i = 0; i < NUM_OPS; ++i) { h->tc_bn[i] = 0; h->tc_maxME[i] = 0; h->tc_maxNE[i] = 0; }
+  for (int i = 0; i < NUM_OPS; ++i) { h->tc_bn[i] = 0; h->tc_maxME[i] = 0; h->tc_maxNE[i] = 0; h->tc_mt1[i] = false; }
   h->d_tcadam = nullptr;
   h->d_tcops = nullptr;
 }
@@ -1199,7 +1214,7 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
   if (rows_override > 0 && !oi.at) NE = rows_override;
   dim3 grid((h->tc_maxME[op] + 127) / 128, (NE + bn - 1) / bn, nfl);
   const TcOp* d = h->d_tcops + (size_t)op * h->nf + f0;
-  if (bn == 256 && (oi.at || h->tc_maxME[op] >= 500)) {     // large-batch regime
+  if (bn == 256 && (oi.at || h->tc_maxME[op] >= 500) && !h->tc_mt1[op]) {     // large-batch regime
     grid.x = (h->tc_maxME[op] + 255) / 256;
     const size_t smem = tc_smem_bytes(256, TC_BIG_STAGES, 2);
     if (oi.at) {
@@ -1215,7 +1230,7 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
     return true;
   }
   const bool head_mt2 = (h->tc_heads & 2) && op == OP_D5G;      // feature matching: one CTA sums the loss over all 250 features
-  if (!oi.at && ((h->tc_mt2 && tc_use_mt2(h->tc_maxME[op], bn)) || head_mt2)) {
+  if (!oi.at && !h->tc_mt1[op] && ((h->tc_mt2 && tc_use_mt2(h->tc_maxME[op], bn)) || head_mt2)) {
     grid.x = (h->tc_maxME[op] + 255) / 256;
     const size_t smem = tc_smem_bytes(bn, TC_FWD_STAGES, 2);
     if (!oi.bt) TC_LAUNCH(h, f16, K_TC_FWD2, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);

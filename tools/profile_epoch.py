@@ -11,10 +11,11 @@ ap.add_argument("--precision", default="tf32")
 ap.add_argument("--D", type=int, default=1200)
 ap.add_argument("--n-train", type=int, default=300)
 ap.add_argument("--epochs", type=int, default=2)
+ap.add_argument("--batch", type=int, default=50)
 a = ap.parse_args()
 rng = np.random.default_rng(0)
 G, D, ntr, nte = a.folds, a.D, a.n_train, 100
-fg = FoldGroup([(D, ntr, nte, fold_key(0, i)) for i in range(G)], precision=a.precision)
+fg = FoldGroup([(D, ntr, nte, fold_key(0, i)) for i in range(G)], precision=a.precision, batch=a.batch, eval_each_epoch=a.batch <= 256)
 X = rng.standard_normal((ntr, D)).astype(np.float32); y = (np.arange(ntr) % 6).astype(np.int32)
 pD, pG = init_disc(D, rng), init_gen(D, rng)
 for i in range(G):
