@@ -162,6 +162,7 @@ k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ fo
 //   mode 1 (G step): rows [B,2B) unlabeled; rows [0,B) come from G
 //   mode 2 (mr_nn step): rows [0,n) labeled
 // from_stage: rows come from the step-API staging buffers instead of the resident fold.
+#define PREP_GROUPS 2       // 4-row noise groups per thread
 __global__ void __launch_bounds__(128)
 k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, int t, int B, int nrows,
        int noise_dim, float sigma_in, AdamHyper hp, OperandMode om) {
@@ -187,49 +188,70 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
   }
 
   const bool aligned = (hp.dp_bloc & 3) == 0 || hp.dp_bg == hp.dp_bloc;   // 4-row noise groups stay inside one section
-  // rows of this group that this step assembles from the data set: mode 0 -> [0, 2B), mode 1 -> [B, 2B), mode 2 -> [0, nrows)
+  const int fold = fold_base + (int)blockIdx.z;
+  // rows that this step assembles from the data set: mode 0 -> [0, 2B), mode 1 -> [B, 2B), mode 2 -> [0, nrows)
   const int r_lo = (mode == 1) ? B : 0, r_hi = (mode == 2) ? nrows : min(nrows, 2 * B);
-  if (c < D && rg * 4 + 3 >= r_lo && rg * 4 < r_hi) {
+  // A thread assembles PREP_GROUPS row groups of 4 rows of one column: the gathers of all of them are issued first, then
+  // their Philox chains run interleaved (one chain per thread left this kernel latency-bound: 24 % of the large-batch step)
+  if (c < D) {
     // descriptor fields in registers: through the FoldState reference every use is a generic load that the stores to a0
-    // force the compiler to repeat; the 4 gathers are issued before the Philox rounds so their latency overlaps the ALU work
+    // force the compiler to repeat
     const float* const x_train = fs.x_train; const float* const stage_x = fs.stage_x;
     float* const a0 = fs.a0;
     const int ldx = fs.ldx, lda0 = fs.lda0;
     const uint32_t key0 = fs.key0, key1 = fs.key1;
-    float xv[4];
+    float xv[PREP_GROUPS][4], nz[PREP_GROUPS][4];
+    bool live[PREP_GROUPS];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = rg * 4 + i;
-      xv[i] = 0.f;
-      if (r < r_lo || r >= r_hi) continue;
-      const int stream = (mode == 1) ? 2 : ((mode == 0 && r >= B) ? 1 : 0);
-      const int lr = (mode == 2) ? r : (r < B ? r : r - B);
-      const float* src = from_stage ? stage_x + (size_t)r * ldx : x_train + (size_t)__ldg(fs.idx[stream] + (size_t)t * B + lr) * ldx;
-      xv[i] = __ldg(src + c);
+    for (int u = 0; u < PREP_GROUPS; ++u) {
+      const int g4 = (rg * PREP_GROUPS + u) * 4;
+      live[u] = g4 + 3 >= r_lo && g4 < r_hi;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = g4 + i;
+        xv[u][i] = 0.f;
+        if (!live[u] || r < r_lo || r >= r_hi) continue;
+        const int stream = (mode == 1) ? 2 : ((mode == 0 && r >= B) ? 1 : 0);
+        const int lr = (mode == 2) ? r : (r < B ? r : r - B);
+        const float* src = from_stage ? stage_x + (size_t)r * ldx : x_train + (size_t)__ldg(fs.idx[stream] + (size_t)t * B + lr) * ldx;
+        xv[u][i] = __ldg(src + c);
+      }
     }
-    float nz[4];
-    if (aligned) normal4(key0, key1, (uint32_t)global_row(rg * 4, hp, fold_base + (int)blockIdx.z) >> 2, (uint32_t)c, step, 0u, nz);
-    else for (int i = 0; i < 4; ++i) nz[i] = normal1(key0, key1, (uint32_t)global_row(rg * 4 + i, hp, fold_base + (int)blockIdx.z), (uint32_t)c, step, 0u);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = rg * 4 + i;
-      if (r < r_lo || r >= r_hi) continue;
-      const float v = xv[i] + sigma_in * nz[i];
-      put_operand(a0 + (size_t)r * lda0 + c, v, om);
+    for (int u = 0; u < PREP_GROUPS; ++u) {
+      const int g4 = (rg * PREP_GROUPS + u) * 4;
+      if (!live[u]) continue;
+      if (aligned) normal4(key0, key1, (uint32_t)global_row(g4, hp, fold) >> 2, (uint32_t)c, step, 0u, nz[u]);
+      else for (int i = 0; i < 4; ++i) nz[u][i] = normal1(key0, key1, (uint32_t)global_row(g4 + i, hp, fold), (uint32_t)c, step, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < PREP_GROUPS; ++u) {
+      const int g4 = (rg * PREP_GROUPS + u) * 4;
+      if (!live[u]) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = g4 + i;
+        if (r < r_lo || r >= r_hi) continue;
+        put_operand(a0 + (size_t)r * lda0 + c, xv[u][i] + sigma_in * nz[u][i], om);
+      }
     }
   }
   if (mode != 2 && c < noise_dim) {       // generator input z (mr_gan.py:206,212)
-    float nz[4] = {0.f, 0.f, 0.f, 0.f};
-    if (!from_stage) {
-      if (aligned) normal4(fs.key0, fs.key1, (uint32_t)global_row(rg * 4, hp, fold_base + (int)blockIdx.z) >> 2, (uint32_t)c, step, MRGAN_TID_Z, nz);
-      else for (int i = 0; i < 4; ++i) nz[i] = normal1(fs.key0, fs.key1, (uint32_t)global_row(rg * 4 + i, hp, fold_base + (int)blockIdx.z), (uint32_t)c, step, MRGAN_TID_Z);
-    }
+    for (int u = 0; u < PREP_GROUPS; ++u) {
+      const int g4 = (rg * PREP_GROUPS + u) * 4;
+      if (g4 >= B) break;
+      float nz[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!from_stage) {
+        if (aligned) normal4(fs.key0, fs.key1, (uint32_t)global_row(g4, hp, fold) >> 2, (uint32_t)c, step, MRGAN_TID_Z, nz);
+        else for (int i = 0; i < 4; ++i) nz[i] = normal1(fs.key0, fs.key1, (uint32_t)global_row(g4 + i, hp, fold), (uint32_t)c, step, MRGAN_TID_Z);
+      }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = rg * 4 + i;
-      if (r >= B) break;
-      const float v = from_stage ? fs.stage_z[(size_t)r * noise_dim + c] : nz[i];
-      put_operand(fs.z + (size_t)r * fs.ldz + c, v, om);
+      for (int i = 0; i < 4; ++i) {
+        const int r = g4 + i;
+        if (r >= B) break;
+        const float v = from_stage ? fs.stage_z[(size_t)r * noise_dim + c] : nz[i];
+        put_operand(fs.z + (size_t)r * fs.ldz + c, v, om);
+      }
     }
   }
 }

@@ -641,7 +641,7 @@ void launch_prep(mrgan_handle* h, int f0, int nfl, int mode, int from_stage, int
   const mrgan_config& c = h->cfg;
   int cols = max_D(h, f0, nfl);
   if (c.noise_dim > cols) cols = c.noise_dim;
-  dim3 grid((cols + 127) / 128, (nrows + 3) / 4, nfl);
+  dim3 grid((cols + 127) / 128, (nrows + 4 * PREP_GROUPS - 1) / (4 * PREP_GROUPS), nfl);
   launch_k(h, k_prep, grid, dim3(128), 0, h->stream, h->d_folds, f0, mode, from_stage, t, c.batch, nrows, c.noise_dim, c.sigma_in, h->hp,
            h->om);
 }
@@ -1063,8 +1063,11 @@ int tc_setup(mrgan_handle* h) {
                  : (atoi(pr) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
   const int nf = h->nf;
   // reductions fused into GEMM epilogues: the reference batch regime (one batch tile, batch statistics local to the GPU)
-  h->tc_heads = (h->cfg.model == MRGAN_MODEL_GAN && h->tc_fused_adam && !h->d_dpbufs && h->R <= 256 && h->cfg.n_classes <= 32) ? 15 : 0;
-  if (const char* hv = getenv("MRGAN_HEADS")) h->tc_heads &= atoi(hv);      // A/B switch (bit mask)
+  h->tc_heads = (h->cfg.model == MRGAN_MODEL_GAN && h->tc_fused_adam && !h->d_dpbufs && h->R <= 256 && h->cfg.n_classes <= 32) ? 7 : 0;
+  // default: loss, feature-matching and BatchNorm-forward heads.  HEAD_BN_BWD (bit 8) is implemented and parity-tested but
+  // measured 1-2 % slower than the stand-alone k_bn_bwd (a thread per feature walks all 50 rows twice behind a GEMM whose
+  // own work is tiny), so it is opt-in: MRGAN_HEADS=15.  MRGAN_HEADS=0 runs every reduction as its own kernel (A/B).
+  if (const char* hv = getenv("MRGAN_HEADS")) h->tc_heads = h->tc_heads ? (atoi(hv) & 15) : 0;
   if (const char* kr = getenv("MRGAN_DW_SMALL")) h->tc_dw_small = atoi(kr) != 0;
   std::vector<TcOp> ops((size_t)NUM_OPS * nf);
   memset(ops.data(), 0, ops.size() * sizeof(TcOp));
