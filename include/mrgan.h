@@ -131,6 +131,15 @@ int  mrgan_test_batch(mrgan_handle* h, int fold, const float* x, const int32_t* 
 int  mrgan_train_epoch(mrgan_handle* h, const int32_t* idx_lab, const int32_t* idx_unl,
                        const int32_t* idx_unl2, mrgan_epoch_stats* stats);
 int  mrgan_epoch_result(mrgan_handle* h, mrgan_epoch_stats* stats);
+/* The same epoch with the permutations of mr_gan.py:189-202 drawn ON THE DEVICE: the host sends an
+ * epoch number instead of 3 x int32[n_train] per fold.  mrgan_set_epoch_rows uploads, once per fold, the labeled rows
+ * (mr_gan.py:102) and the optional unlabeled subset of table 6 (mr_gan.py:107; NULL / 0 = all training rows); every
+ * epoch then tiles fresh permutations of them exactly like the reference (floor(N/L) permutations of the L rows plus a
+ * permutation of the first N mod L), keyed by (fold seed, epoch, stream).  Subsets of at most 8192 rows. */
+int  mrgan_set_epoch_rows(mrgan_handle* h, int fold, const int32_t* lab_rows, int n_lab, const int32_t* unl_rows, int n_unl);
+int  mrgan_train_epoch_seeded(mrgan_handle* h, uint32_t epoch, mrgan_epoch_stats* stats);
+/* test hook: the three index streams of the last epoch, [3][n_train] */
+int  mrgan_debug_epoch_indices(mrgan_handle* h, int fold, int32_t* dst);
 /* testerror on the full resident test set in one call, mr_gan.py:230 */
 int  mrgan_eval(mrgan_handle* h, int fold, float* err);
 

@@ -54,6 +54,9 @@ SYMBOLS = {
     "mrgan_test_batch": (C.c_int, [_H, C.c_int, _fp, _ip, C.c_int, _fp]),
     "mrgan_train_epoch": (C.c_int, [_H, _ip, _ip, _ip, C.POINTER(EpochStats)]),
     "mrgan_epoch_result": (C.c_int, [_H, C.POINTER(EpochStats)]),
+    "mrgan_set_epoch_rows": (C.c_int, [_H, C.c_int, _ip, C.c_int, _ip, C.c_int]),
+    "mrgan_train_epoch_seeded": (C.c_int, [_H, C.c_uint32, C.POINTER(EpochStats)]),
+    "mrgan_debug_epoch_indices": (C.c_int, [_H, C.c_int, _ip]),
     "mrgan_eval": (C.c_int, [_H, C.c_int, _fp]),
     "mrgan_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "mrgan_dp_init": (C.c_int, [_H, C.c_int, C.c_int, C.c_void_p]),

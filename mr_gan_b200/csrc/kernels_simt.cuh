@@ -702,6 +702,56 @@ __global__ void k_fill_normal(float* __restrict__ dst, const FoldState* __restri
 }
 
 
+// ------------------------------------------------------------------ device-side epoch permutations (mr_gan.py:189-202)
+// The three index streams of an epoch, drawn on the device from a seed instead of being uploaded (3 x int32[n_train] per
+// fold and epoch).  Stream 0 = labeled rows: floor(N / L) independent permutations of the L labeled rows followed by a
+// permutation of the FIRST N mod L of them (mr_gan.py:189); streams 1 and 2 = permutations of all N training rows, or of
+// the unlabeled subset tiled the same way (mr_gan.py:193-194,197-200).  A permutation of n items = the order of the keys
+// (philox(i, tile, epoch, 0x50 + stream).x << 32) | i, sorted ascending (bitonic network in shared memory): unique keys,
+// so the result is defined exactly and the oracle restates it with a stable argsort (oracle/fold_loop.py:device_perm).
+struct PermDesc { const int* lab_rows; const int* unl_rows; int* idx; int n_lab, n_unl, n_train; uint32_t key0, key1; };
+
+#define PERM_MAX 8192       // largest tile (64 KB of 64-bit keys)
+__global__ void __launch_bounds__(1024)
+k_epoch_perm(const PermDesc* __restrict__ descs, uint32_t epoch) {
+  extern __shared__ unsigned long long pkeys[];
+  const PermDesc d = descs[blockIdx.y];
+  const int s = blockIdx.x;
+  const int* const src = (s == 0) ? d.lab_rows : d.unl_rows;           // null: the rows themselves
+  const int L = (s == 0) ? d.n_lab : (d.unl_rows ? d.n_unl : d.n_train);
+  int* const out = d.idx + (size_t)s * d.n_train;
+  const int N = d.n_train, ntiles = N / L, rem = N - ntiles * L;
+  for (int j = 0; j <= ntiles; ++j) {
+    const int n = (j < ntiles) ? L : rem;
+    if (n == 0) break;
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+      unsigned long long k = ~0ull;
+      if (i < n) k = ((unsigned long long)philox4x32_10(make_uint4((uint32_t)i, (uint32_t)j, epoch, 0x50u + (uint32_t)s), d.key0, d.key1).x << 32) | (uint32_t)i;
+      pkeys[i] = k;
+    }
+    __syncthreads();
+    for (int k2 = 2; k2 <= P; k2 <<= 1)
+      for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+        for (int i = threadIdx.x; i < P; i += blockDim.x) {
+          const int ixj = i ^ j2;
+          if (ixj > i) {
+            const unsigned long long a = pkeys[i], b = pkeys[ixj];
+            const bool up = (i & k2) == 0;
+            if ((a > b) == up) { pkeys[i] = b; pkeys[ixj] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int p = (int)(pkeys[i] & 0xffffffffull);
+      out[(size_t)j * L + i] = src ? src[p] : p;
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------ device-side fold preparation (mr_gan.py:96-101)
 // StandardScaler.fit over the training rows of a fold: per-column sum and sum of squares in float64.  Each of the
 // gridDim.y row slices writes its own partial sums ([slice][2 * D]); the consumer adds the slices in slice order, so the

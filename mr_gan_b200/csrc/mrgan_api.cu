@@ -62,6 +62,8 @@ struct FoldBuffers {
   float *a[6], *hb[6], *dz[6], *lg, *dlg, *dfake, *zb, *h1g, *xhat, *istd, *u, *h2g, *dz2g, *du, *dz1g;
   float *stage_x, *stage_z, *ex_stage, *xte, *eh[6], *elg, *xtr, *eval_out, *eval_out_s;
   int *stage_y, *labels_cur, *ey_stage, *ytr, *yte, *idx;
+  int *lab_rows, *unl_rows;      // device-side epoch permutations: labeled / unlabeled row subsets (mrgan_set_epoch_rows)
+  int n_lab = 0, n_unl = 0;
   int lda[6], ldz[6];   // pitches of a/h (with ones column) and dz
   bool loaded = false;
 };
@@ -74,6 +76,8 @@ namespace {
 int tc_setup(mrgan_handle* h);
 void tc_teardown(mrgan_handle* h);
 bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override, cudaStream_t st);
+void tc_launch_dw_adam(mrgan_handle* h, int op, int nlayers, int f0, int nfl, cudaStream_t st);
+bool tc_dw_merge(const mrgan_handle* h);
 void tc_params_changed(mrgan_handle* h, int fold, int net);
 int tc_debug_gemm(mrgan_handle* h, int mode, const GemmDesc& g, int esz);
 }
@@ -102,6 +106,7 @@ struct mrgan_handle {
   float *P = nullptr, *Mo = nullptr, *Vo = nullptr, *Gr = nullptr; long long n_flat = 0;
   FoldState* d_folds = nullptr; std::vector<FoldState> h_folds;
   GemmDesc* d_descs = nullptr; std::vector<GemmDesc> h_descs;
+  PermDesc* d_perm = nullptr;
   BnDesc* d_bn = nullptr; LossDesc* d_loss = nullptr; EvalDesc *d_eval = nullptr, *d_eval_s = nullptr;
   AdamRange* d_ranges[2] = {nullptr, nullptr};
   OpInfo ops[NUM_OPS];
@@ -140,6 +145,7 @@ struct mrgan_handle {
   bool tc_fused_adam = true;          // dW epilogue applies Adam in place (no gradient round trip)
   bool tc_mt2 = true;                 // forward / dX: 256 features per CTA where the layer is wide enough (MRGAN_MT2=0 disables)
   bool tc_adam_tma = true;            // ... with W/m/v staged through smem by TMA (k_dw_adam_tc) instead of the LSU
+  bool tc_dw_merge = true;            // dW+Adam of the narrow layers (D 3..6; G 1, 2) in one launch each; MRGAN_DW_MERGE=0: one launch per layer
   bool tc_dw_small = true;            // dW+Adam: 16 KB operand stages (32 fp16 / 16 fp32 batch rows) -> three CTAs per SM; MRGAN_DW_SMALL=0: two
   int tc_heads = 0;                   // losses / feature matching / BatchNorm fused into GEMM epilogues (set by tc_setup), bit mask:
                                       // 1 = HEAD_DISC (no k_loss_disc, no k_adam of D), 2 = HEAD_FM (no k_fm), 4 = HEAD_BN (no k_bn_fwd),
@@ -239,6 +245,7 @@ void layout_buffers(mrgan_handle* h, Arena& ar) {
   h->Gr = ar.take<float>(h->n_flat);
   h->d_folds = ar.take<FoldState>(nf);
   h->d_descs = ar.take<GemmDesc>((size_t)NUM_OPS * nf);
+  h->d_perm = ar.take<PermDesc>(nf);
   h->d_bn = ar.take<BnDesc>(nf);
   h->d_loss = ar.take<LossDesc>(nf);
   h->d_eval = ar.take<EvalDesc>(nf);
@@ -291,6 +298,8 @@ void layout_buffers(mrgan_handle* h, Arena& ar) {
     b.ytr = ar.take<int>(ntr);
     b.yte = ar.take<int>(nte);
     b.idx = ar.take<int>((size_t)3 * ntr);
+    b.lab_rows = ar.take<int>(ntr);
+    b.unl_rows = ar.take<int>(ntr);
   }
 }
 
@@ -712,9 +721,18 @@ void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) 
   if (!heads)        // otherwise the logit layer's epilogue computed the losses, their gradients and advanced the counters
     launch_k(h, k_loss_disc, dim3(1, 1, nfl), dim3(256), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, B,
              c.n_classes, c.unlabeled_weight, h->om, h->hp.dp_bg);
+#ifdef MRGAN_WITH_TC
+  const bool merge = tc_dw_merge(h);
+#else
+  const bool merge = false;
+#endif
   for (int l = 6; l >= 1; --l) {      // dX first: it reads W_l, which the fused-Adam dW epilogue overwrites
     if (l >= 2) launch_gemm(h, OP_DX2 + l - 2, f0, nfl, 0);
+    if (merge && l > 3) continue;     // the narrow layers 3..6 share ONE dW+Adam launch, after the last dX that reads their weights
     fork_side(h);                     // dW_l (+Adam) streams HBM on the side while main continues the dX chain
+#ifdef MRGAN_WITH_TC
+    if (merge && l == 3) { tc_launch_dw_adam(h, OP_DW3, 4, f0, nfl, h->side); continue; }
+#endif
     launch_gemm(h, OP_DW1 + l - 1, f0, nfl, 0, h->side);
   }
   if (!deferred_join(h) || from_stage) join_side(h);   // deferred: dW1+Adam overlaps the next G step's generator forward
@@ -750,8 +768,15 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   fork_side(h);
   launch_gemm(h, OP_GW3, f0, nfl, 0, h->side);
   launch_gemm(h, OP_GX2, f0, nfl, 0);
-  fork_side(h);
-  launch_gemm(h, OP_GW2, f0, nfl, 0, h->side);
+#ifdef MRGAN_WITH_TC
+  const bool merge = tc_dw_merge(h);
+#else
+  const bool merge = false;
+#endif
+  if (!merge) {
+    fork_side(h);
+    launch_gemm(h, OP_GW2, f0, nfl, 0, h->side);
+  }
   const dim3 bng((kGH + BN_COLS - 1) / BN_COLS, 1, nfl), bnt(B > 256 ? 1024 : 256);
   if (h->d_dpbufs) {
     k_bn_bwd_stats<<<bng, bnt, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, h->om);
@@ -762,6 +787,10 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
     launch_k(h, k_bn_bwd, bng, bnt, 0, h->stream, (const BnDesc*)(h->d_bn + f0), h->om);
   }
   fork_side(h);
+#ifdef MRGAN_WITH_TC
+  if (merge) tc_launch_dw_adam(h, OP_GW1, 2, f0, nfl, h->side);      // G layers 1 and 2 share one dW+Adam launch
+  else
+#endif
   launch_gemm(h, OP_GW1, f0, nfl, 0, h->side);
   if (!deferred_join(h) || from_stage) join_side(h);
   if (h->dp_world > 1) dp_update(h, f0, nfl, 1);
@@ -1069,6 +1098,7 @@ int tc_setup(mrgan_handle* h) {
   // own work is tiny), so it is opt-in: MRGAN_HEADS=15.  MRGAN_HEADS=0 runs every reduction as its own kernel (A/B).
   if (const char* hv = getenv("MRGAN_HEADS")) h->tc_heads = h->tc_heads ? (atoi(hv) & 15) : 0;
   if (const char* kr = getenv("MRGAN_DW_SMALL")) h->tc_dw_small = atoi(kr) != 0;
+  if (const char* kr = getenv("MRGAN_DW_MERGE")) h->tc_dw_merge = atoi(kr) != 0;
   std::vector<TcOp> ops((size_t)NUM_OPS * nf);
   memset(ops.data(), 0, ops.size() * sizeof(TcOp));
   for (int op = 0; op < NUM_OPS; ++op) {
@@ -1209,6 +1239,27 @@ void tc_teardown(mrgan_handle* h) {
 
 void tc_params_changed(mrgan_handle*, int, int) {}   // fp32 master weights are the MMA operands: nothing to refresh
 
+// dW + fused Adam of `nlayers` consecutive ops (op, op + 1, ...) of folds [f0, f0 + nfl) in ONE launch (grid.z = layer x fold;
+// CTAs beyond a layer's extents exit at once)
+void tc_launch_dw_adam(mrgan_handle* h, int op, int nlayers, int f0, int nfl, cudaStream_t st) {
+  const bool f16 = h->om.mode == 2;
+  int gx = 0, gy = 0;
+  for (int l = 0; l < nlayers; ++l) {
+    gx = std::max(gx, (h->tc_maxME[op + l] + 127) / 128);
+    gy = std::max(gy, (h->tc_maxNE[op + l] + 127) / 128);
+  }
+  const dim3 grid(gx, gy, nlayers * nfl);
+  const TcAdamOp* ad = h->d_tcadam + (size_t)op * h->nf + f0;
+  // small operand stages: three CTAs per SM (default); MRGAN_DW_SMALL=0: the two-CTA configuration (A/B)
+  if (f16 && h->tc_dw_small) launch_k(h, k_dw_adam_tc<true, 32>, grid, dim3(192), TcAdamCfg<true, 32>::SMEM, st, ad, h->d_folds, h->hp, nfl, h->nf);
+  else if (f16) launch_k(h, k_dw_adam_tc<true, 64>, grid, dim3(192), TcAdamCfg<true, 64>::SMEM, st, ad, h->d_folds, h->hp, nfl, h->nf);
+  else if (h->tc_dw_small) launch_k(h, k_dw_adam_tc<false, 16>, grid, dim3(192), TcAdamCfg<false, 16>::SMEM, st, ad, h->d_folds, h->hp, nfl, h->nf);
+  else launch_k(h, k_dw_adam_tc<false, 32>, grid, dim3(192), TcAdamCfg<false, 32>::SMEM, st, ad, h->d_folds, h->hp, nfl, h->nf);
+}
+
+// the fused-Adam dW path is active (tcgen05 precision, reference batch regime): narrow layers may share launches
+bool tc_dw_merge(const mrgan_handle* h) { return h->cfg.precision != MRGAN_PREC_FP32 && h->d_tcadam != nullptr && h->tc_dw_merge; }
+
 bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override, cudaStream_t st) {
   const OpInfo& oi = h->ops[op];
   const bool f16 = h->om.mode == 2;
@@ -1253,14 +1304,7 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
     else
       TC_LAUNCH(h, f16, K_TC_DX, grid, dim3(TC_FWD_THREADS), tc_smem_bytes(bn, TC_FWD_STAGES), st, d, h->d_folds, rows_override, h->hp, h->om);
   }
-  else if (h->d_tcadam) {
-    const TcAdamOp* ad = h->d_tcadam + (size_t)op * h->nf + f0;
-    // small operand stages: three CTAs per SM (default); MRGAN_DW_SMALL=0: the two-CTA configuration (A/B)
-    if (f16 && h->tc_dw_small) launch_k(h, k_dw_adam_tc<true, 32>, grid, dim3(192), TcAdamCfg<true, 32>::SMEM, st, ad, h->d_folds, h->hp);
-    else if (f16) launch_k(h, k_dw_adam_tc<true, 64>, grid, dim3(192), TcAdamCfg<true, 64>::SMEM, st, ad, h->d_folds, h->hp);
-    else if (h->tc_dw_small) launch_k(h, k_dw_adam_tc<false, 16>, grid, dim3(192), TcAdamCfg<false, 16>::SMEM, st, ad, h->d_folds, h->hp);
-    else launch_k(h, k_dw_adam_tc<false, 32>, grid, dim3(192), TcAdamCfg<false, 32>::SMEM, st, ad, h->d_folds, h->hp);
-  }
+  else if (h->d_tcadam) { tc_launch_dw_adam(h, op, 1, f0, nfl, st); return true; }
   else TC_LAUNCH(h, f16, K_TC_DW, grid, dim3(TC_DW_THREADS), tc_smem_bytes(bn, TC_DW_STAGES), st, d, h->d_folds, 0, h->hp, h->om);
   return true;
 }
@@ -1718,6 +1762,56 @@ int mrgan_epoch_result(mrgan_handle* h, mrgan_epoch_stats* stats) {
   return MRGAN_OK;
 }
 
+int mrgan_set_epoch_rows(mrgan_handle* h, int fold, const int32_t* lab_rows, int n_lab, const int32_t* unl_rows, int n_unl) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (h->cfg.model != MRGAN_MODEL_GAN) return fail(h, MRGAN_ERR_STATE, "set_epoch_rows needs a GAN handle");
+  const int N = h->n_train;
+  if (!lab_rows || n_lab < 1 || n_lab > N || n_lab > PERM_MAX) return fail(h, MRGAN_ERR_ARG, "set_epoch_rows: 1 <= n_lab <= min(n_train, 8192)");
+  if (unl_rows ? (n_unl < 1 || n_unl > N || n_unl > PERM_MAX) : (n_unl != 0 || N > PERM_MAX))
+    return fail(h, MRGAN_ERR_ARG, "set_epoch_rows: unlabeled subset must have 1..min(n_train, 8192) rows (none: n_train <= 8192)");
+  for (int i = 0; i < n_lab; ++i) if ((unsigned)lab_rows[i] >= (unsigned)N) return fail(h, MRGAN_ERR_ARG, "set_epoch_rows: labeled row out of range");
+  for (int i = 0; i < n_unl; ++i) if ((unsigned)unl_rows[i] >= (unsigned)N) return fail(h, MRGAN_ERR_ARG, "set_epoch_rows: unlabeled row out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  FoldBuffers& b = h->fb[fold];
+  CK(cudaMemcpyAsync(b.lab_rows, lab_rows, (size_t)n_lab * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  if (unl_rows) CK(cudaMemcpyAsync(b.unl_rows, unl_rows, (size_t)n_unl * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  b.n_lab = n_lab; b.n_unl = unl_rows ? n_unl : 0;
+  PermDesc pd{b.lab_rows, unl_rows ? b.unl_rows : nullptr, b.idx, n_lab, b.n_unl, N,
+              (uint32_t)(h->shapes[fold].seed & 0xFFFFFFFFull), (uint32_t)(h->shapes[fold].seed >> 32)};
+  CK(cudaMemcpyAsync(h->d_perm + fold, &pd, sizeof(pd), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));     // the pageable row arrays are borrowed only for the call
+  return MRGAN_OK;
+}
+
+static int launch_epoch(mrgan_handle* h, int nb, mrgan_epoch_stats* stats);
+
+int mrgan_train_epoch_seeded(mrgan_handle* h, uint32_t epoch, mrgan_epoch_stats* stats) {
+  if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
+  if (h->cfg.model != MRGAN_MODEL_GAN) return fail(h, MRGAN_ERR_STATE, "train_epoch_seeded needs a GAN handle");
+  for (int f = 0; f < h->nf; ++f) {
+    if (!h->fb[f].loaded) return fail(h, MRGAN_ERR_STATE, "train_epoch_seeded before mrgan_load_fold");
+    if (h->fb[f].n_lab < 1) return fail(h, MRGAN_ERR_STATE, "train_epoch_seeded before mrgan_set_epoch_rows");
+  }
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = finish_pending(h); if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_epoch_perm, cudaFuncAttributeMaxDynamicSharedMemorySize, PERM_MAX * 8); attr_set = true; }
+  k_epoch_perm<<<dim3(3, h->nf), 1024, PERM_MAX * 8, h->stream>>>(h->d_perm, epoch);
+  h->launches++;
+  return launch_epoch(h, h->n_train / h->cfg.batch, stats);
+}
+
+int mrgan_debug_epoch_indices(mrgan_handle* h, int fold, int32_t* dst) {
+  int rc = check_fold(h, fold); if (rc) return rc;
+  if (!dst) return fail(h, MRGAN_ERR_ARG, "debug_epoch_indices: null pointer");
+  CK(cudaSetDevice(h->cfg.device));
+  rc = finish_pending(h); if (rc) return rc;
+  CK(cudaMemcpyAsync(dst, h->fb[fold].idx, (size_t)3 * h->n_train * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return MRGAN_OK;
+}
+
 int mrgan_train_epoch(mrgan_handle* h, const int32_t* idx_lab, const int32_t* idx_unl, const int32_t* idx_unl2,
                       mrgan_epoch_stats* stats) {
   if (!h) return fail(nullptr, MRGAN_ERR_ARG, "null handle");
@@ -1733,13 +1827,19 @@ int mrgan_train_epoch(mrgan_handle* h, const int32_t* idx_lab, const int32_t* id
       return fail(h, MRGAN_ERR_ARG, "train_epoch: row index out of range");
   CK(cudaSetDevice(h->cfg.device));
   int rc = finish_pending(h); if (rc) return rc;
+  const int32_t* streams[3] = {idx_lab, idx_unl, idx_unl2};
+  rc = upload_indices(h, streams, 3, h->n_train); if (rc) return rc;
+  return launch_epoch(h, nb, stats);
+}
+
+// the epoch itself (index arrays already on their way on the handle's stream): one graph launch, or step by step
+static int launch_epoch(mrgan_handle* h, int nb, mrgan_epoch_stats* stats) {
   // data-parallel epochs are captured like the others (NCCL collectives and the fused exchange are stream-ordered graph
   // nodes; one chain, so every rank issues them in the same order); MRGAN_DP_GRAPH=0 enqueues them step by step instead
   static const bool dp_graph = !(getenv("MRGAN_DP_GRAPH") && atoi(getenv("MRGAN_DP_GRAPH")) == 0);
   const bool eager = h->dp_world > 1 && !dp_graph;
+  int rc = MRGAN_OK;
   if (!eager) { rc = build_graph(h, nb, nb, 0); if (rc) return rc; }
-  const int32_t* streams[3] = {idx_lab, idx_unl, idx_unl2};
-  rc = upload_indices(h, streams, 3, h->n_train); if (rc) return rc;
   CK(cudaEventRecord(h->ev0, h->stream));
   if (eager) {
     for (int t = 0; t < nb; ++t) { enqueue_disc_step(h, 0, h->nf, t, 0); enqueue_gen_step(h, 0, h->nf, t, 0); }

@@ -242,6 +242,24 @@ class FoldGroup:
         self._chk(self.lib.mrgan_train_epoch(self._h, _lib.iptr(a), _lib.iptr(b), _lib.iptr(c), None))
         return self.epoch_result() if wait else None
 
+    def set_epoch_rows(self, fold, lab_rows, unl_rows=None):
+        """Device-side epoch permutations: the labeled rows (mr_gan.py:102) and the optional unlabeled subset (mr_gan.py:107)."""
+        lab = _i32(lab_rows)
+        unl = _i32(unl_rows) if unl_rows is not None else None
+        self._chk(self.lib.mrgan_set_epoch_rows(self._h, int(fold), _lib.iptr(lab), lab.size,
+                                                _lib.iptr(unl) if unl is not None else None, unl.size if unl is not None else 0))
+
+    def train_epoch_seeded(self, epoch, wait=True):
+        """One epoch with the permutations of mr_gan.py:189-202 drawn on the device from (fold seed, epoch)."""
+        self._chk(self.lib.mrgan_train_epoch_seeded(self._h, int(epoch) & 0xFFFFFFFF, None))
+        return self.epoch_result() if wait else None
+
+    def epoch_indices(self, fold):
+        """Test hook: the three index streams the last epoch used, int32 [3, n_train]."""
+        out = np.empty((3, self.n_train), dtype=np.int32)
+        self._chk(self.lib.mrgan_debug_epoch_indices(self._h, int(fold), _lib.iptr(out)))
+        return out
+
     def epoch_result(self):
         st = (_lib.EpochStats * self.n_folds)()
         self._chk(self.lib.mrgan_epoch_result(self._h, st))

@@ -39,11 +39,13 @@ def dataset(modalities=0, forcetempTime=4, contactmicTime=0.2, leaveObjectOut=Fa
 
 
 def train_gan_folds(jobs, epochs=100, verbose=False, *, seed=0, precision='fp32', device=0, batch=50,
-                    eval_each_epoch=True, shared_t=True, return_group=False):
+                    eval_each_epoch=True, shared_t=True, return_group=False, device_perm=False):
     """Train a GROUP of independent folds side by side on one GPU.
 
     jobs: list of dicts with keys ``trainTestSets`` (or ``X``, ``y``), ``percentlabeled``,
     ``percentunlabeled`` (optional), ``job_id`` (optional, seeds the fold's streams).
+    device_perm: draw the epoch permutations of mr_gan.py:189-202 on the device (the host then sends one epoch number per
+    epoch instead of 3 x int32[n_train] per fold); same distribution, different draws than the host's numpy generator.
     Returns the list of test errors (mr_gan.py:230,234), one per job."""
     folds, rngs, slots = [], [], {}
     for i, job in enumerate(jobs):
@@ -92,12 +94,21 @@ def train_gan_folds(jobs, epochs=100, verbose=False, *, seed=0, precision='fp32'
         per = [foldprep.epoch_indices(rng, n_train, f.lab_rows, f.unl_rows) for f, rng in zip(folds, rngs)]
         return [np.stack([p[s] for p in per]) for s in range(3)]
 
-    nxt = draw()
+    if device_perm and max(len(f.lab_rows) for f in folds) <= 8192 and all(
+            (len(f.unl_rows) if f.unl_rows is not None else n_train) <= 8192 for f in folds):
+        for i, f in enumerate(folds):
+            fg.set_epoch_rows(i, f.lab_rows, f.unl_rows)
+    else:
+        device_perm = False
+    nxt = None if device_perm else draw()
     for epoch in range(1, epochs + 1):
         begin = time.time()
-        fg.train_epoch(*nxt, wait=False)          # one CUDA-graph launch: the whole epoch, all folds
-        if epoch < epochs:
-            nxt = draw()                          # host permutations of the next epoch overlap the GPU
+        if device_perm:
+            fg.train_epoch_seeded(epoch, wait=False)  # permutations drawn on the device from (fold key, epoch)
+        else:
+            fg.train_epoch(*nxt, wait=False)      # one CUDA-graph launch: the whole epoch, all folds
+            if epoch < epochs:
+                nxt = draw()                      # host permutations of the next epoch overlap the GPU
         st = fg.epoch_result()
         if verbose:
             for i in range(len(jobs)):
@@ -116,13 +127,13 @@ def train_gan_folds(jobs, epochs=100, verbose=False, *, seed=0, precision='fp32'
 
 
 def mr_gan(X, y, percentlabeled=50, percentunlabeled=None, epochs=100, trainTestSets=None, verbose=False, *,
-           seed=None, precision='fp32', device=0, batch=50):
+           seed=None, precision='fp32', device=0, batch=50, device_perm=False):
     """mr_gan.py:73-234, one fold.  ``seed=None`` reproduces the reference's 'Non Deterministic output'."""
     if seed is None:
         seed = int(np.random.SeedSequence().entropy % (2 ** 63))      # mr_gan.py:74-75
     job = dict(X=X, y=y, percentlabeled=percentlabeled, percentunlabeled=percentunlabeled, trainTestSets=trainTestSets)
     return train_gan_folds([job], epochs=epochs, verbose=verbose, seed=seed, precision=precision, device=device,
-                           batch=batch)[0]
+                           batch=batch, device_perm=device_perm)[0]
 
 
 # ------------------------------------------------------------------ CLI (mr_gan.py:236-341)
@@ -173,6 +184,7 @@ def main(argv=None):
     parser.add_argument('--group', type=int, default=42, help='folds trained side by side per GPU launch (42 = one modality of table 1)')
     parser.add_argument('--data-dir', default='data_processed')
     parser.add_argument('--synthetic', action='store_true', help='synthetic data of the MREO shape instead of the processed pickles')
+    parser.add_argument('--host-perm', action='store_true', help='draw the epoch permutations on the host (numpy) instead of on the device')
     args = parser.parse_args(argv)
     rank, world, local = sweep.dist_env()
     seed = sweep.shared_seed(args.seed)          # one seed for every rank: same dataset, same splits, same job streams
@@ -187,7 +199,7 @@ def main(argv=None):
             jid[0] += 1
         res = sweep.run_sharded(
             jobs, lambda js, dev: train_gan_folds(js, epochs=args.epochs, verbose=args.verbose, seed=seed,
-                                                  precision=args.precision, device=dev),
+                                                  precision=args.precision, device=dev, device_perm=not args.host_perm),
             group_size=args.group, key=job_rows, cost=job_width)
         return res
 

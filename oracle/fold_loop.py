@@ -61,6 +61,30 @@ def epoch_indices(rng, n_train, lab_rows, unl_rows=None):
     return idx_lab.astype(np.int32), np.asarray(u1, np.int32), np.asarray(u2, np.int32)
 
 
+def device_perm(key, epoch, stream, tile, n):
+    """A permutation of range(n) as the device draws it (csrc/kernels_simt.cuh:k_epoch_perm): the order of the 64-bit keys
+    (philox(i, tile, epoch, 0x50 + stream).x << 32) | i, ascending."""
+    x = philox.philox4x32_10(np.arange(n, dtype=np.int64), np.uint64(tile), np.uint64(epoch & 0xFFFFFFFF), np.uint64(0x50 + stream),
+                             key[0], key[1])[0]
+    keys = (np.broadcast_to(x, (n,)).astype(np.uint64) << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+    return np.argsort(keys, kind="stable")
+
+
+def device_epoch_indices(key, epoch, n_train, lab_rows, unl_rows=None):
+    """mr_gan.py:189-202 with the device's permutations: the three index streams of mrgan_train_epoch_seeded."""
+    def tiled(stream, rows, L):
+        parts = [device_perm(key, epoch, stream, j, L) for j in range(n_train // L)]
+        if n_train % L:
+            parts.append(device_perm(key, epoch, stream, n_train // L, n_train % L))
+        p = np.concatenate(parts)
+        return (rows[p] if rows is not None else p).astype(np.int32)
+    lab_rows = np.asarray(lab_rows)
+    out = [tiled(0, lab_rows, len(lab_rows))]
+    for s in (1, 2):
+        out.append(tiled(s, None if unl_rows is None else np.asarray(unl_rows), n_train if unl_rows is None else len(unl_rows)))
+    return out
+
+
 def train_epoch(model, X_train, y_train, idx_lab, idx_unl, idx_unl2, key, rng_step, B=O.BATCH_GAN):
     """mr_gan.py:204-217 with the device noise stream.  Returns per-step stats [nb,4] and the new rng_step.
 

@@ -492,6 +492,50 @@ def test_data_parallel_path_with_virtual_ranks(precision, D, Bg, nb):
     _param_close(pr[0], p1, pD + pG, ptol)
 
 
+def test_device_side_epoch_permutations_match_the_oracle_restatement():
+    """mrgan_train_epoch_seeded draws the index streams of mr_gan.py:189-202 on the device: (i) they equal the oracle's
+    restatement (oracle/fold_loop.py:device_epoch_indices) element for element, for plain permutations, for the tiled
+    labeled stream (60 labeled rows over 7100: 118 permutations + a permutation of the first 20) and for a table-6
+    unlabeled subset; (ii) every tile is a permutation; (iii) the epoch it runs is bit-identical to the epoch run from the
+    same indices uploaded by the host."""
+    rng = np.random.default_rng(5)
+    D, B = 12, 10
+    for ntr, n_lab, n_unl in ((7100, 60, None), (600, 240, 420), (330, 330, None)):
+        nte = 20
+        key = philox.fold_key(31, ntr)
+        X, y = rng.standard_normal((ntr + nte, D)).astype(np.float32), rng.integers(0, 6, ntr + nte).astype(np.int32)
+        lab = np.sort(rng.choice(ntr, n_lab, replace=False)).astype(np.int32)
+        unl = None if n_unl is None else np.sort(rng.choice(ntr, n_unl, replace=False)).astype(np.int32)
+        pD, pG = model.init_disc(D, rng), model.init_gen(D, rng)
+        res = []
+        for seeded in (True, False):
+            with FoldGroup([(D, ntr, nte, _key64(key))], precision="fp32", batch=B) as fg:
+                fg.set_params(0, 0, pD); fg.set_params(0, 1, pG)
+                fg.load_fold(0, X[:ntr], y[:ntr], X[ntr:], y[ntr:])
+                want = fold_loop.device_epoch_indices(key, 3, ntr, lab, unl)
+                if seeded:
+                    with pytest.raises(MrganError, match="set_epoch_rows"):
+                        fg.train_epoch_seeded(3)
+                    fg.set_epoch_rows(0, lab, unl)
+                    st = fg.train_epoch_seeded(3)
+                    got = fg.epoch_indices(0)
+                    for s in range(3):
+                        np.testing.assert_array_equal(got[s], want[s])
+                    src = [lab, np.arange(ntr) if unl is None else unl, np.arange(ntr) if unl is None else unl]
+                    for s in range(3):
+                        L = len(src[s])
+                        for j in range(ntr // L):
+                            assert sorted(got[s][j * L:(j + 1) * L]) == sorted(src[s])          # a permutation of the subset
+                        assert sorted(got[s][(ntr // L) * L:]) == sorted(src[s][:ntr % L])       # ... of its first N mod L rows
+                    assert not np.array_equal(got[1], got[2])                                    # independent streams
+                else:
+                    st = fg.train_epoch(*[a[None, :] for a in want])
+                res.append((st, fg.get_params(0, 0)))
+        np.testing.assert_array_equal(res[0][0], res[1][0])
+        for a, b in zip(res[0][1], res[1][1]):
+            np.testing.assert_array_equal(a, b)
+
+
 def test_device_side_fold_preparation_matches_host_path():
     """mrgan_load_dataset + mrgan_prepare_fold (scaler statistics, scaling, gather on the device) == the host's
     StandardScaler path (mr_gan.py:96-101) followed by mrgan_load_fold; a zero-variance column stays finite."""

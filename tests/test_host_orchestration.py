@@ -44,6 +44,14 @@ class FakeGroup:
         self.epochs.append((a.copy(), b.copy(), c.copy()))
         self.calls.append(("train_epoch",))
 
+    def set_epoch_rows(self, fold, lab_rows, unl_rows=None):      # device-side permutations (the CLI's default)
+        assert 0 < len(lab_rows) <= self.n_train and (unl_rows is None or len(unl_rows) <= self.n_train)
+        self.calls.append(("set_epoch_rows", fold, len(lab_rows), None if unl_rows is None else len(unl_rows)))
+
+    def train_epoch_seeded(self, epoch, wait=True):
+        assert sum(c[0] == "set_epoch_rows" for c in self.calls) == self.n_folds
+        self.calls.append(("train_epoch_seeded", epoch))
+
     def epoch_result(self):
         return np.tile(np.array([[1.5, 0.7, 0.25, 0.01, 0.3]], np.float32), (self.n_folds, 1))
 

@@ -178,3 +178,25 @@ def test_epoch_loop_restatement_shapes_and_counters():
     assert stats.shape == (N // B, 4) and step == 2 * (N // B) and m.iterations == step
     assert np.isfinite(stats).all()
     assert 0.0 <= fold_loop.eval_batches(m, Xte, yte, B=6) <= 1.0
+
+
+def test_device_permutation_restatement_is_a_permutation_and_tiles_like_the_reference():
+    """oracle/fold_loop.py:device_epoch_indices (what mrgan_train_epoch_seeded draws): every tile a permutation, the
+    labeled stream tiled as mr_gan.py:189 (floor(N/L) permutations + a permutation of the first N mod L rows),
+    deterministic in (key, epoch), different across epochs and streams."""
+    from oracle import fold_loop, philox
+    key = philox.fold_key(3, 4)
+    lab = np.array([5, 9, 11, 40, 41, 77, 300])
+    a = fold_loop.device_epoch_indices(key, 7, 31, lab)
+    b = fold_loop.device_epoch_indices(key, 7, 31, lab)
+    c = fold_loop.device_epoch_indices(key, 8, 31, lab)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+    assert any(not np.array_equal(x, y) for x, y in zip(a, c))
+    for j in range(4):
+        assert sorted(a[0][7 * j:7 * j + 7]) == sorted(lab)
+    assert sorted(a[0][28:]) == sorted(lab[:3])
+    assert sorted(a[1]) == list(range(31)) and sorted(a[2]) == list(range(31)) and not np.array_equal(a[1], a[2])
+    unl = np.arange(3, 15)
+    u = fold_loop.device_epoch_indices(key, 1, 31, lab, unl)
+    assert sorted(u[1][:12]) == list(unl) and sorted(u[2][24:]) == list(unl[:7])
