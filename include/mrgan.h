@@ -68,7 +68,13 @@ typedef struct {
   float bn_eps;          /* 2e-5 (mr_gan.py:112)                              */
   float unlabeled_weight;/* 1 (mr_gan.py:79)                                  */
   float sigma_in, sigma_hidden; /* .3, .5 (mr_gan.py:118-126)                 */
+  /* discriminator variants of others/wganlpctsemi.py:166-179 (defaults reproduce mr_gan.py / mr_nn.py): */
+  int hidden_act;        /* MRGAN_ACT_RELU (mr_gan.py:119-127) or MRGAN_ACT_LEAKY_RELU                 */
+  float leaky_alpha;     /* LeakyReLU slope, 0.3 = Keras default (wganlpctsemi.py:169)                 */
+  float dropout;         /* > 0: Dropout(rate) in front of hidden layers 2..5 in place of their
+                            GaussianNoise (wganlpctsemi.py:170); 0: GaussianNoise(sigma_hidden)        */
 } mrgan_config;
+enum { MRGAN_ACT_RELU = 0, MRGAN_ACT_LEAKY_RELU = 1 };
 
 typedef struct {
   int D;                 /* input width of this fold (X_train.shape[1])       */
@@ -203,7 +209,7 @@ double  mrgan_last_device_ms(const mrgan_handle* h);  /* CUDA-event time of the 
 const char* mrgan_version(void);
 /* ABI guard for hand-written bindings (ctypes / cgo / JNI lay the structs out by hand): fills
  * {MRGAN_ABI_VERSION, sizeof(mrgan_config), sizeof(mrgan_fold_shape), sizeof(mrgan_epoch_stats)}. */
-#define MRGAN_ABI_VERSION 2
+#define MRGAN_ABI_VERSION 3
 int  mrgan_abi_info(int out[4]);
 
 #ifdef __cplusplus

@@ -18,7 +18,8 @@ class Config(C.Structure):
                 ("eval_each_epoch", C.c_int), ("device", C.c_int),
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
                 ("bn_eps", C.c_float), ("unlabeled_weight", C.c_float),
-                ("sigma_in", C.c_float), ("sigma_hidden", C.c_float)]
+                ("sigma_in", C.c_float), ("sigma_hidden", C.c_float),
+                ("hidden_act", C.c_int), ("leaky_alpha", C.c_float), ("dropout", C.c_float)]
 
 
 class FoldShape(C.Structure):
@@ -78,7 +79,7 @@ SYMBOLS = {
     "mrgan_abi_info": (C.c_int, [C.POINTER(C.c_int)]),
 }
 
-ABI_VERSION = 2      # MRGAN_ABI_VERSION of include/mrgan.h this binding was written against
+ABI_VERSION = 3      # MRGAN_ABI_VERSION of include/mrgan.h this binding was written against
 
 
 def lib_path():

@@ -15,7 +15,7 @@
 
 #define MRGAN_TID_Z 5   // noise stream ids 0..4 = GaussianNoise layers of D, 5 = z
 
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SOFTPLUS = 2 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SOFTPLUS = 2, ACT_LEAKY = 3 };   // ACT_LEAKY: LeakyReLU(alpha), others/wganlpctsemi.py:169
 enum { EPI_FWD = 0, EPI_DX = 1, EPI_STORE = 2 };
 
 // Per-fold device state.  One per fold, resident in HBM for the handle's life.
@@ -57,6 +57,9 @@ struct AdamHyper {
   float lr, b1, b2, eps; int shared_t; int dp_bloc, dp_bg, dp_rank;
   // constants of the loss / BatchNorm heads fused into GEMM epilogues, and the batch index of the step being enqueued
   float w_unl, bn_eps; int n_classes, t;
+  // discriminator variants of others/wganlpctsemi.py:166-179: LeakyReLU slope, and Dropout(rate) in place of the
+  // GaussianNoise layers between hidden layers (drop == 0: the reference's GaussianNoise); drop_inv = 1 / (1 - drop)
+  float alpha, drop, drop_inv;
 };
 
 // Stacked-row index of this rank -> stacked-row index of the GLOBAL batch (identity unless data-parallel): sections
@@ -119,25 +122,45 @@ __device__ __forceinline__ void normal4(uint32_t k0, uint32_t k1, uint32_t rowgr
   out[0] = ra * ca; out[1] = ra * sa; out[2] = rb * cb; out[3] = rb * sb;
 }
 
+// Dropout(rate) keep factors of rows 4*rowgroup .. +3 at column `col`, from the same counter stream as the Gaussian noise it
+// replaces: u_i = ((x_i >> 9) + 0.5) 2^-23 of the four Philox words, kept (factor 1 / (1 - rate)) iff u_i >= rate
+// (definition: oracle/philox.py:dropout_factor).
+__device__ __forceinline__ void dropout4(uint32_t k0, uint32_t k1, uint32_t rowgroup, uint32_t col, uint32_t step, uint32_t tid,
+                                         float rate, float inv, float out[4]) {
+  const uint4 x = philox4x32_10(make_uint4(rowgroup, col, step, tid), k0, k1);
+  const float s = 1.1920928955078125e-07f;   // 2^-23
+  out[0] = (((float)(x.x >> 9) + 0.5f) * s >= rate) ? inv : 0.f;
+  out[1] = (((float)(x.y >> 9) + 0.5f) * s >= rate) ? inv : 0.f;
+  out[2] = (((float)(x.z >> 9) + 0.5f) * s >= rate) ? inv : 0.f;
+  out[3] = (((float)(x.w >> 9) + 0.5f) * s >= rate) ? inv : 0.f;
+}
+// what a forward epilogue combines with the activation of rows 4*rowgroup..+3: N(0,1) draws (y = x + sigma n) or, with
+// drop > 0, dropout keep factors (y = x f)
+__device__ __forceinline__ void noise_or_drop4(uint32_t k0, uint32_t k1, uint32_t rowgroup, uint32_t col, uint32_t step, uint32_t tid,
+                                               float drop, float inv, float out[4]) {
+  if (drop > 0.f) dropout4(k0, k1, rowgroup, col, step, tid, drop, inv, out);
+  else normal4(k0, k1, rowgroup, col, step, tid, out);
+}
+
 // Out-of-line noise draws for the GEMM epilogues: they draw up to 38 row groups per thread from several places, and an
 // inlined Philox (~150 instructions, plus the integer division of global_row) per call site grew the forward kernel to
 // 9 k instructions = 146 KB of SASS, far beyond the instruction cache -- the epilogue loop was fetching its own code
 // from L2 (ncu: no_inst stalls).  One call per row group; with 2 epilogue warps per scheduler a single Philox chain per
 // warp already keeps the issue slots busy.  `local_row` is this rank's stacked row index (see global_row).
 __device__ __noinline__ float4 noise4_call(uint32_t k0, uint32_t k1, int local_row, uint32_t col, uint32_t step, uint32_t tid,
-                                           int dp_bloc, int dp_bg, int dp_rank) {
+                                           int dp_bloc, int dp_bg, int dp_rank, float drop, float inv) {
   AdamHyper hp; hp.dp_bloc = dp_bloc; hp.dp_bg = dp_bg; hp.dp_rank = dp_rank;
   float n[4];
-  normal4(k0, k1, (uint32_t)global_row(local_row, hp) >> 2, col, step, tid, n);
+  noise_or_drop4(k0, k1, (uint32_t)global_row(local_row, hp) >> 2, col, step, tid, drop, inv, n);
   return make_float4(n[0], n[1], n[2], n[3]);
 }
 // one element (a 4-row group that straddles a section / rank boundary is drawn element by element)
 __device__ __noinline__ float noise1_call(uint32_t k0, uint32_t k1, int local_row, uint32_t col, uint32_t step, uint32_t tid,
-                                          int dp_bloc, int dp_bg, int dp_rank) {
+                                          int dp_bloc, int dp_bg, int dp_rank, float drop, float inv) {
   AdamHyper hp; hp.dp_bloc = dp_bloc; hp.dp_bg = dp_bg; hp.dp_rank = dp_rank;
   const uint32_t gr = (uint32_t)global_row(local_row, hp);
   float n[4];
-  normal4(k0, k1, gr >> 2, col, step, tid, n);
+  noise_or_drop4(k0, k1, gr >> 2, col, step, tid, drop, inv, n);
   const uint32_t e = gr & 3u;
   return e == 0 ? n[0] : (e == 1 ? n[1] : (e == 2 ? n[2] : n[3]));
 }

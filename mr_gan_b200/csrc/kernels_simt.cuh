@@ -118,15 +118,22 @@ k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ fo
         const int n = nb + j;
         if (n >= N) continue;
         float v = acc[i][j];
-        if (d.act == ACT_RELU) v = (d.aux[(size_t)m * d.ldaux + n] > 0.f) ? v : 0.f;
-        else if (d.act == ACT_SOFTPLUS) v *= 1.0f - expf(-d.aux[(size_t)m * d.ldaux + n]);
+        if (d.act == ACT_RELU || d.act == ACT_LEAKY) {       // aux = h, or with a Dropout layer behind the activation its dropped output
+          const float a = d.aux[(size_t)m * d.ldaux + n];
+          const bool drop = hp.drop > 0.f && d.tid >= 1;
+          float mlt = (a > 0.f ? 1.0f : (d.act == ACT_LEAKY ? hp.alpha : 0.f)) * (drop ? hp.drop_inv : 1.0f);
+          if (drop && a == 0.f) mlt = 0.f;
+          v *= mlt;
+        } else if (d.act == ACT_SOFTPLUS) v *= 1.0f - expf(-d.aux[(size_t)m * d.ldaux + n]);
         d.C[(size_t)m * d.ldc + n] = v;
       }
     }
     return;
   }
   // EPI_FWD: activation, optional clean copy (C), optional noisy copy for the next layer (C2)
-  const bool noisy = (d.C2 != nullptr) && (d.sigma != 0.f);
+  const bool mul = hp.drop > 0.f && d.C2 != nullptr && d.tid >= 1;      // Dropout in place of GaussianNoise (hidden layers)
+  const float ddrop = mul ? hp.drop : 0.f;
+  const bool noisy = (d.C2 != nullptr) && (d.sigma != 0.f || mul);
   uint32_t k0 = 0, k1 = 0, step = 0;
   if (noisy) { const FoldState& fs = folds[d.fold]; k0 = fs.key0; k1 = fs.key1; step = (uint32_t)fs.rng_step; }
 #pragma unroll
@@ -136,9 +143,14 @@ k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ fo
     float nz[4] = {0.f, 0.f, 0.f, 0.f};
     if (noisy) {
       if (((d.row0 + mb) & 3) == 0 && (hp.dp_bg == hp.dp_bloc || (hp.dp_bloc & 3) == 0)) {
-        normal4(k0, k1, (uint32_t)global_row(d.row0 + mb, hp, d.fold) >> 2, (uint32_t)n, step, (uint32_t)d.tid, nz);
+        noise_or_drop4(k0, k1, (uint32_t)global_row(d.row0 + mb, hp, d.fold) >> 2, (uint32_t)n, step, (uint32_t)d.tid, ddrop, hp.drop_inv, nz);
       } else {
-        for (int i = 0; i < 4; ++i) nz[i] = normal1(k0, k1, (uint32_t)global_row(d.row0 + mb + i, hp, d.fold), (uint32_t)n, step, (uint32_t)d.tid);
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t gr = (uint32_t)global_row(d.row0 + mb + i, hp, d.fold);
+          float q[4];
+          noise_or_drop4(k0, k1, gr >> 2, (uint32_t)n, step, (uint32_t)d.tid, ddrop, hp.drop_inv, q);
+          nz[i] = q[gr & 3];
+        }
       }
     }
 #pragma unroll
@@ -148,8 +160,9 @@ k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ fo
       float v = acc[i][j];
       if (d.act == ACT_RELU) v = fmaxf(v, 0.f);
       else if (d.act == ACT_SOFTPLUS) v = softplusf(v);
+      else if (d.act == ACT_LEAKY) v = v > 0.f ? v : hp.alpha * v;
       if (d.C) d.C[(size_t)m * d.ldc + n] = v;
-      if (d.C2) d.C2[(size_t)m * d.ldc2 + n] = v + d.sigma * nz[i];
+      if (d.C2) d.C2[(size_t)m * d.ldc2 + n] = mul ? v * nz[i] : v + d.sigma * nz[i];
     }
   }
 }
@@ -170,11 +183,10 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
   pdl_wait();
   FoldState& fs = folds[fold_base + blockIdx.z];
   const int c = blockIdx.x * 128 + threadIdx.x;
-  const int rg = blockIdx.y;
   const uint32_t step = (uint32_t)fs.rng_step;
   const int D = fs.D;
 
-  if (blockIdx.x == 0 && rg == 0) {
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
     if (threadIdx.x == 0) {
       const int net = (mode == 1) ? 1 : 0;
       const int tt = (hp.shared_t ? fs.iterations : fs.it_net[net]) + 1;
@@ -192,7 +204,10 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
   // rows that this step assembles from the data set: mode 0 -> [0, 2B), mode 1 -> [B, 2B), mode 2 -> [0, nrows)
   const int r_lo = (mode == 1) ? B : 0, r_hi = (mode == 2) ? nrows : min(nrows, 2 * B);
   // A thread assembles PREP_GROUPS row groups of 4 rows of one column: the gathers of all of them are issued first, then
-  // their Philox chains run interleaved (one chain per thread left this kernel latency-bound: 24 % of the large-batch step)
+  // their Philox chains run interleaved (one chain per thread left this kernel latency-bound: 24 % of the large-batch step);
+  // gridDim.y is capped, so at large batches a block walks several row slabs instead of 190 k tiny blocks being scheduled
+  const int nslab = (nrows + 4 * PREP_GROUPS - 1) / (4 * PREP_GROUPS);
+  for (int rg = blockIdx.y; rg < nslab; rg += gridDim.y) {
   if (c < D) {
     // descriptor fields in registers: through the FoldState reference every use is a generic load that the stores to a0
     // force the compiler to repeat
@@ -254,6 +269,7 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
       }
     }
   }
+  }      // row slabs
 }
 
 // ------------------------------------------------------------------ BatchNorm (batch statistics)
@@ -398,7 +414,7 @@ k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, 
 // Writes dZ5 (already multiplied by ReLU') for the fake rows.  1024 threads = 256 columns x 4 row slices.
 __global__ void __launch_bounds__(1024)
 k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total, int t, int B,
-     OperandMode om) {
+     OperandMode om, float alpha) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sh[32];
@@ -421,7 +437,7 @@ k_fm(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fol
     if (sl == 0) s = fmaf(diff, diff, s);
     const float g = 2.0f * diff / ((float)d.Wmid * B);
     for (int r = sl; r < B; r += 4)
-      put_grad_operand(d.dmid + (size_t)r * d.lddmid + j, (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : 0.f, om);
+      put_grad_operand(d.dmid + (size_t)r * d.lddmid + j, (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : alpha * g, om);
   }
   s = block_sum(s, sh);
   if (threadIdx.x == 0) step_stats[((size_t)t * nf_total + fold_base + blockIdx.z) * 4 + 3] = s / d.Wmid;
@@ -561,7 +577,7 @@ __global__ void __launch_bounds__(1024) k_fm_stats(const LossDesc* __restrict__ 
 
 __global__ void __launch_bounds__(1024)
 k_fm_apply(const LossDesc* __restrict__ descs, const DpBufs* __restrict__ bufs, float* __restrict__ step_stats, int fold_base,
-           int nf_total, int t, int B, OperandMode om, int Bg, int world) {
+           int nf_total, int t, int B, OperandMode om, int Bg, int world, float alpha) {
   __shared__ float sh[32];
   const LossDesc d = descs[blockIdx.z];
   const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
@@ -570,7 +586,7 @@ k_fm_apply(const LossDesc* __restrict__ descs, const DpBufs* __restrict__ bufs, 
     const float diff = (bufs[blockIdx.z].fm[j] - bufs[blockIdx.z].fm[d.Wmid + j]) / Bg;
     const float g = 2.0f * diff / ((float)d.Wmid * Bg);
     for (int r = sl; r < B; r += nsl)
-      put_grad_operand(d.dmid + (size_t)r * d.lddmid + j, (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : 0.f, om);
+      put_grad_operand(d.dmid + (size_t)r * d.lddmid + j, (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : alpha * g, om);
   }
   if (blockIdx.x == 0) {      // the loss itself: every rank holds the same global value; the statistics block is summed over ranks
     float s = 0.f;            // afterwards, so 1/world of it is stored

@@ -193,13 +193,14 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // of ~60 of branchy code; the chunk loops dispatch once per chunk.  Pointers walk down the rows by the pitch.
 template <bool F16, int ACT, bool HAS_C, bool HAS_C2>
 __device__ __forceinline__ void fwd_rows(const uint32_t (&va)[16], const float (&nz)[16], int nrows, float* pC, __half* hC, int ldc,
-                                         bool c_op, float* pC2, __half* hC2, int ldc2, bool c2_op, float sigma) {
+                                         bool c_op, float* pC2, __half* hC2, int ldc2, bool c2_op, float sigma, float alpha, bool mul) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     float x = __uint_as_float(va[j]);
     if (!F16) x *= TF32_TRUNC_DEBIAS;
     if (ACT == ACT_RELU) x = fmaxf(x, 0.f);
     else if (ACT == ACT_SOFTPLUS) x = softplus_fast(x);
+    else if (ACT == ACT_LEAKY) x = x > 0.f ? x : alpha * x;
     const bool ok = j < nrows;
     if (HAS_C) {                // clean activation: kept in fp32 (act' of the backward pass, feature matching, logits) ...
       if (F16) {
@@ -209,7 +210,7 @@ __device__ __forceinline__ void fwd_rows(const uint32_t (&va)[16], const float (
       pC += ldc;
     }
     if (HAS_C2) {               // noisy activation: only ever a GEMM operand
-      const float y = fmaf(sigma, nz[j], x);
+      const float y = mul ? x * nz[j] : fmaf(sigma, nz[j], x);      // Dropout keep factor / GaussianNoise
       if (F16) {
         if (ok) { if (c2_op) *hC2 = __float2half_rn(y); else *pC2 = y; }
         hC2 += ldc2;
@@ -219,14 +220,21 @@ __device__ __forceinline__ void fwd_rows(const uint32_t (&va)[16], const float (
   }
 }
 
+// ACT_RELU / ACT_LEAKY: av is the layer's clean output h (slope 1 where h > 0, else alpha; alpha = 0 for ReLU) -- or, when a
+// Dropout layer follows the activation (dinv = 1 / (1 - rate)), its DROPPED output a = f h: the element was dropped iff
+// a == 0, and a kept element has the sign of h, so one array carries both derivatives.
 template <bool F16, int ACT>
-__device__ __forceinline__ void dx_rows(const uint32_t (&va)[16], const float (&av)[16], int nrows, float* pC, __half* hC, int ldc, bool op_only) {
+__device__ __forceinline__ void dx_rows(const uint32_t (&va)[16], const float (&av)[16], int nrows, float* pC, __half* hC, int ldc, bool op_only,
+                                        float alpha, float dinv, bool drop) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     float x = __uint_as_float(va[j]);
     if (!F16) x *= TF32_TRUNC_DEBIAS;
-    if (ACT == ACT_RELU) x = (av[j] > 0.f) ? x : 0.f;
-    else if (ACT == ACT_SOFTPLUS) x *= 1.0f - __expf(-av[j]);
+    if (ACT == ACT_RELU || ACT == ACT_LEAKY) {
+      float m = (av[j] > 0.f ? 1.0f : (ACT == ACT_LEAKY ? alpha : 0.f)) * dinv;
+      if (drop && av[j] == 0.f) m = 0.f;
+      x *= m;
+    } else if (ACT == ACT_SOFTPLUS) x *= 1.0f - __expf(-av[j]);
     if (j < nrows) {
       if (F16 && op_only) *hC = grad_to_half(x);             // operand only: 16-bit copy, loss-scaled like the accumulator
       else *pC = (!F16 && op_only) ? rna_tf32(x) : x;
@@ -240,13 +248,14 @@ __device__ __forceinline__ void dx_rows(const uint32_t (&va)[16], const float (&
 // ---- fused heads: a second pass over the finished accumulator (TMEM reads are cheap) by the epilogue warps -----------
 // One 16-row chunk of this thread's feature from TMEM, as the activation the forward epilogue stored.
 template <bool F16, int ACT>
-__device__ __forceinline__ void head_chunk(uint32_t taddr, float (&x)[16]) {
+__device__ __forceinline__ void head_chunk(uint32_t taddr, float (&x)[16], float alpha = 0.f) {
   tc::tmem_ld16(taddr, x);
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     if (!F16) x[j] *= TF32_TRUNC_DEBIAS;
     if (ACT == ACT_RELU) x[j] = fmaxf(x[j], 0.f);
     else if (ACT == ACT_SOFTPLUS) x[j] = softplus_fast(x[j]);
+    else if (ACT == ACT_LEAKY) x[j] = x[j] > 0.f ? x[j] : alpha * x[j];
   }
 }
 
@@ -307,7 +316,7 @@ __device__ __forceinline__ void head_fm(uint32_t trow, int ncols, int f, bool f_
   float mg = 0.f, mr = 0.f;
   for (int c0 = 0; c0 < ncols; c0 += 16) {
     float x[16];
-    head_chunk<F16, ACT_RELU>(trow + (uint32_t)c0, x);
+    head_chunk<F16, ACT_LEAKY>(trow + (uint32_t)c0, x, hp.alpha);      // alpha = 0: ReLU
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int r = c0 + j;
@@ -321,12 +330,12 @@ __device__ __forceinline__ void head_fm(uint32_t trow, int ncols, int f, bool f_
   if (!F16) g = rna_tf32(g);
   for (int c0 = 0; c0 < B; c0 += 16) {
     float x[16];
-    head_chunk<F16, ACT_RELU>(trow + (uint32_t)c0, x);
+    head_chunk<F16, ACT_LEAKY>(trow + (uint32_t)c0, x, hp.alpha);
     if (!f_ok) continue;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int r = c0 + j;
-      if (r < B) put_grad_operand(L.dmid + (size_t)r * L.lddmid + f, x[j] > 0.f ? g : 0.f, om);
+      if (r < B) put_grad_operand(L.dmid + (size_t)r * L.lddmid + f, x[j] > 0.f ? g : hp.alpha * g, om);
     }
   }
 }
@@ -642,10 +651,15 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
       // parked in the free TMEM columns; chunks that do not fit are register-prefetched one chunk ahead.  Per chunk the
       // accumulator and the parked values are fetched with two TMEM loads behind ONE wait.
       const bool has_act = g.act != ACT_NONE;
+      // Dropout variant: aux is the layer's DROPPED output a (see dx_rows), which in f16 mode exists only as the fp16 copy
+      const bool drop = hp.drop > 0.f && (g.act == ACT_RELU || g.act == ACT_LEAKY) && g.tid >= 1;
+      const __half* const haux = (F16 && drop) ? om.hbase + (g.aux - om.fbase) : nullptr;
       auto fetch = [&](int c0, float (&av)[16]) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          av[j] = (f_ok && has_act && c0 + j < ncols) ? __ldg(g.aux + (size_t)(n0 + c0 + j) * g.ldaux + f) : 1.0f;
+        for (int j = 0; j < 16; ++j) {
+          const size_t o = (size_t)(n0 + c0 + j) * g.ldaux + f;
+          av[j] = (f_ok && has_act && c0 + j < ncols) ? (haux ? __half2float(haux[o]) : __ldg(g.aux + o)) : 1.0f;
+        }
       };
       float avA[16], avB[16];
       const int npk = has_act ? npark : 0;
@@ -692,9 +706,11 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         const int nrows = ncols - c0;
         float* const pC = g.C + o0;
         __half* const phC = F16 ? hC + o0 : nullptr;
-        if (g.act == ACT_RELU) dx_rows<F16, ACT_RELU>(va, av, nrows, pC, phC, g.ldc, op_only);
-        else if (g.act == ACT_SOFTPLUS) dx_rows<F16, ACT_SOFTPLUS>(va, av, nrows, pC, phC, g.ldc, op_only);
-        else dx_rows<F16, ACT_NONE>(va, av, nrows, pC, phC, g.ldc, op_only);
+        const float dinv = drop ? hp.drop_inv : 1.0f;
+        if (g.act == ACT_RELU) dx_rows<F16, ACT_RELU>(va, av, nrows, pC, phC, g.ldc, op_only, 0.f, dinv, drop);
+        else if (g.act == ACT_LEAKY) dx_rows<F16, ACT_LEAKY>(va, av, nrows, pC, phC, g.ldc, op_only, hp.alpha, dinv, drop);
+        else if (g.act == ACT_SOFTPLUS) dx_rows<F16, ACT_SOFTPLUS>(va, av, nrows, pC, phC, g.ldc, op_only, 0.f, 1.0f, false);
+        else dx_rows<F16, ACT_NONE>(va, av, nrows, pC, phC, g.ldc, op_only, 0.f, 1.0f, false);
       }
       if (op.head == HEAD_BN_BWD)
         head_bn_bwd<F16>(trow, cbeg, ncols, min(bn, NE - n0), f, f_ok, *static_cast<const BnDesc*>(op.hd), hp, om, folds[g.fold].lr_t[1],
@@ -705,7 +721,11 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
       // idle while the TMA / MMA warps run the mainloop -- so they draw now and park whole 16-row chunks in the free TMEM
       // columns.  Chunks that do not fit are drawn in the epilogue BETWEEN issuing the accumulator's TMEM load and waiting
       // for it, so the Philox rounds hide the load latency; per chunk there is one wait for both TMEM loads.
-      const bool noisy = g.C2 != nullptr && g.sigma != 0.f;
+      // Dropout variant (hp.drop > 0): the transforms in front of D's hidden layers 2..5 (stream ids 1..4) are Dropout(rate)
+      // instead of GaussianNoise: the parked / drawn values are keep factors and combine by multiplication
+      const bool mul = hp.drop > 0.f && g.C2 != nullptr && g.tid >= 1;
+      const float ddrop = mul ? hp.drop : 0.f;
+      const bool noisy = g.C2 != nullptr && (g.sigma != 0.f || mul);
       uint32_t key0 = 0, key1 = 0, step = 0;
       if (noisy) { const FoldState& fs = folds[g.fold]; key0 = fs.key0; key1 = fs.key1; step = (uint32_t)fs.rng_step; }
       // 4-row noise groups must not straddle row-section or rank boundaries (oracle/philox.py): otherwise per-element draws
@@ -718,17 +738,18 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
           // the common case: four independent Philox chains, inlined so the compiler interleaves them (the epilogue warps
           // are latency-bound here: 2 warps per scheduler)
 #pragma unroll
-          for (int q = 0; q < 4; ++q) normal4(key0, key1, (uint32_t)(r0 + 4 * q) >> 2, (uint32_t)f, step, (uint32_t)g.tid, &nz[4 * q]);
+          for (int q = 0; q < 4; ++q)
+            noise_or_drop4(key0, key1, (uint32_t)(r0 + 4 * q) >> 2, (uint32_t)f, step, (uint32_t)g.tid, ddrop, hp.drop_inv, &nz[4 * q]);
         } else if (grp) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const float4 n4 = noise4_call(key0, key1, r0 + 4 * q, (uint32_t)f, step, (uint32_t)g.tid, hp.dp_bloc, hp.dp_bg, dprank);
+            const float4 n4 = noise4_call(key0, key1, r0 + 4 * q, (uint32_t)f, step, (uint32_t)g.tid, hp.dp_bloc, hp.dp_bg, dprank, ddrop, hp.drop_inv);
             nz[4 * q] = n4.x; nz[4 * q + 1] = n4.y; nz[4 * q + 2] = n4.z; nz[4 * q + 3] = n4.w;
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            nz[j] = noise1_call(key0, key1, r0 + j, (uint32_t)f, step, (uint32_t)g.tid, hp.dp_bloc, hp.dp_bg, dprank);
+            nz[j] = noise1_call(key0, key1, r0 + j, (uint32_t)f, step, (uint32_t)g.tid, hp.dp_bloc, hp.dp_bg, dprank, ddrop, hp.drop_inv);
         }
       };
       const int npk = (noisy && grp) ? npark : 0;
@@ -774,11 +795,12 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
 #pragma unroll
           for (int j = 0; j < 16; ++j) nz[j] = 0.f;
         }
-#define FWD_ROWS(ACT, HC, HC2) fwd_rows<F16, ACT, HC, HC2>(va, nz, nrows, pC, phC, g.ldc, c_op, pC2, phC2, g.ldc2, c2_op, g.sigma)
+#define FWD_ROWS(ACT, HC, HC2) fwd_rows<F16, ACT, HC, HC2>(va, nz, nrows, pC, phC, g.ldc, c_op, pC2, phC2, g.ldc2, c2_op, g.sigma, hp.alpha, mul)
 #define FWD_ACT(HC, HC2)                                                     \
         do {                                                                 \
           if (g.act == ACT_RELU) FWD_ROWS(ACT_RELU, HC, HC2);                \
           else if (g.act == ACT_SOFTPLUS) FWD_ROWS(ACT_SOFTPLUS, HC, HC2);   \
+          else if (g.act == ACT_LEAKY) FWD_ROWS(ACT_LEAKY, HC, HC2);         \
           else FWD_ROWS(ACT_NONE, HC, HC2);                                  \
         } while (0)
         if (g.C && g.C2) FWD_ACT(true, true);

@@ -337,13 +337,15 @@ int build_descs(mrgan_handle* h) {
     int win[6] = {D, kDW[0], kDW[1], kDW[2], kDW[3], kDW[4]};
     int wout[6] = {kDW[0], kDW[1], kDW[2], kDW[3], kDW[4], K};
     const float sig[5] = {c.sigma_in, c.sigma_hidden, c.sigma_hidden, c.sigma_hidden, c.sigma_hidden};
+    const int hact = c.hidden_act == MRGAN_ACT_LEAKY_RELU ? ACT_LEAKY : ACT_RELU;      // mr_gan.py:119-127 / wganlpctsemi.py:169
+    const bool dropout = c.dropout > 0.0f;
     // ---- discriminator forward (train): layer l (1-based) reads a[l-1], writes h[l] (+ noisy a[l])
     for (int l = 1; l <= 6; ++l) {
       const TensorLayout& W = LD.t[l - 1];
       float* C = (l <= 5) ? b.hb[l] : b.lg;
       const int ldc = (l <= 5) ? b.lda[l] : pitch8(K);
       GemmDesc d = make_desc(b.a[l - 1], b.lda[l - 1], PD + W.off, W.pitch, C, ldc, R, wout[l - 1], win[l - 1] + 1,
-                             EPI_FWD, l <= 5 ? ACT_RELU : ACT_NONE, f);
+                             EPI_FWD, l <= 5 ? hact : ACT_NONE, f);
       if (l <= 4) { d.C2 = b.a[l]; d.ldc2 = b.lda[l]; d.sigma = sig[l]; d.tid = l; d.row0 = 0; }
       setop(OP_D1 + l - 1, f, d, false, false, (l == 5 ? 1 : 0) | 2);
       if (gan && l <= 5) { GemmDesc dg = d; dg.M = 2 * B; setop(OP_D1G + l - 1, f, dg, false, false, (l == 5 ? 1 : 0) | 2); }
@@ -351,7 +353,7 @@ int build_descs(mrgan_handle* h) {
       const float* EA = (l == 1) ? b.xte : b.eh[l - 1];
       float* EC = (l <= 5) ? b.eh[l] : b.elg;
       GemmDesc e = make_desc(EA, b.lda[l - 1], PD + W.off, W.pitch, EC, ldc, h->shapes[f].n_test, wout[l - 1],
-                             win[l - 1] + 1, EPI_FWD, l <= 5 ? ACT_RELU : ACT_NONE, f);
+                             win[l - 1] + 1, EPI_FWD, l <= 5 ? hact : ACT_NONE, f);
       setop(l == 1 ? OP_E1 : OP_E2 + l - 2, f, e, false, false, l <= 5 ? 1 : 0);
       if (l == 1) { e.A = b.ex_stage; setop(OP_E1S, f, e, false, false, 1); }
       // dW (+db): grad(Waug_l) = a[l-1]^T @ dZ[l]
@@ -363,8 +365,10 @@ int build_descs(mrgan_handle* h) {
       // dX: dZ[l-1] = (dZ[l] @ W_l^T) * relu'(h[l-1])
       if (l >= 2) {
         GemmDesc x = make_desc(dZ, lddz, PD + W.off, W.pitch, b.dz[l - 1], b.ldz[l - 1], R, win[l - 1], wout[l - 1],
-                               EPI_DX, ACT_RELU, f);
-        x.aux = b.hb[l - 1]; x.ldaux = b.lda[l - 1];
+                               EPI_DX, hact, f);
+        // act'(h[l-1]) needs the layer's clean output -- or, when Dropout follows the activation, the dropped output a[l-1],
+        // which carries the keep mask and the sign of h at once (dx_rows); tid >= 1 marks "behind a hidden-layer transform"
+        x.aux = (dropout && l - 1 <= 4) ? b.a[l - 1] : b.hb[l - 1]; x.ldaux = b.lda[l - 1]; x.tid = (l - 1 <= 4) ? l - 1 : 0;
         setop(OP_DX2 + l - 2, f, x, false, true, 1);
         if (gan && l <= 5) { GemmDesc xg = x; xg.M = B; setop(OP_DX2G + l - 2, f, xg, false, true, 1); }
       }
@@ -650,7 +654,8 @@ void launch_prep(mrgan_handle* h, int f0, int nfl, int mode, int from_stage, int
   const mrgan_config& c = h->cfg;
   int cols = max_D(h, f0, nfl);
   if (c.noise_dim > cols) cols = c.noise_dim;
-  dim3 grid((cols + 127) / 128, (nrows + 4 * PREP_GROUPS - 1) / (4 * PREP_GROUPS), nfl);
+  const int nslab = (nrows + 4 * PREP_GROUPS - 1) / (4 * PREP_GROUPS);
+  dim3 grid((cols + 127) / 128, std::min(nslab, 64), nfl);
   launch_k(h, k_prep, grid, dim3(128), 0, h->stream, h->d_folds, f0, mode, from_stage, t, c.batch, nrows, c.noise_dim, c.sigma_in, h->hp,
            h->om);
 }
@@ -756,11 +761,11 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
     k_fm_stats<<<fmg, fmt, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, B);
     dp_allreduce(h, h->dp_fm + (size_t)f0 * 2 * kDW[4], (size_t)nfl * 2 * kDW[4]);
     k_fm_apply<<<fmg, fmt, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, h->d_step_stats, f0, h->nf, t, B,
-                                           h->om, h->hp.dp_bg, h->dp_world);
+                                           h->om, h->hp.dp_bg, h->dp_world, h->hp.alpha);
     h->launches += 2;
   } else if (!(hm & 2)) {   // otherwise D layer 5's epilogue computed the feature-matching loss, its gradient, and advanced the counters
     launch_k(h, k_fm, dim3(1, 1, nfl), dim3(1024), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, B,
-             h->om);
+             h->om, h->hp.alpha);
   }
   for (int l = 5; l >= 2; --l) launch_gemm(h, OP_DX2G + l - 2, f0, nfl, 0);
   launch_gemm(h, OP_DX1G, f0, nfl, 0);
@@ -1336,6 +1341,7 @@ int mrgan_default_config(int model, mrgan_config* cfg) {
   cfg->device = 0;
   cfg->beta2 = 0.999f; cfg->adam_eps = 1e-8f; cfg->bn_eps = 2e-5f;
   cfg->unlabeled_weight = 1.0f; cfg->sigma_in = 0.3f; cfg->sigma_hidden = 0.5f;
+  cfg->hidden_act = MRGAN_ACT_RELU; cfg->leaky_alpha = 0.3f; cfg->dropout = 0.0f;
   if (model == MRGAN_MODEL_NN) { cfg->batch = 20; cfg->lr = 1e-3f; cfg->beta1 = 0.9f; }
   else { cfg->batch = 50; cfg->lr = 6e-4f; cfg->beta1 = 0.5f; }
   return MRGAN_OK;
@@ -1351,6 +1357,8 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
     return fail(nullptr, MRGAN_ERR_ARG, "bad config (n_folds/batch/n_classes/noise_dim)");
   if (cfg->model != MRGAN_MODEL_GAN && cfg->model != MRGAN_MODEL_NN) return fail(nullptr, MRGAN_ERR_ARG, "bad model");
   if (cfg->batch > (1 << 16)) return fail(nullptr, MRGAN_ERR_ARG, "batch too large");
+  if ((cfg->hidden_act != MRGAN_ACT_RELU && cfg->hidden_act != MRGAN_ACT_LEAKY_RELU) || !(cfg->dropout >= 0.0f && cfg->dropout < 1.0f))
+    return fail(nullptr, MRGAN_ERR_ARG, "bad config (hidden_act / dropout)");
   for (int f = 0; f < cfg->n_folds; ++f) {
     if (folds[f].D < 1 || folds[f].n_train < cfg->batch || folds[f].n_test < 1)
       return fail(nullptr, MRGAN_ERR_ARG, "bad fold shape");
@@ -1375,7 +1383,8 @@ int mrgan_create(const mrgan_config* cfg, const mrgan_fold_shape* folds, mrgan_h
   h->shapes.assign(folds, folds + h->nf);
   h->fb.resize(h->nf);
   h->hp = AdamHyper{cfg->lr, cfg->beta1, cfg->beta2, cfg->adam_eps, cfg->shared_t, cfg->batch, cfg->batch, 0,
-                    cfg->unlabeled_weight, cfg->bn_eps, cfg->n_classes, 0};
+                    cfg->unlabeled_weight, cfg->bn_eps, cfg->n_classes, 0,
+                    cfg->hidden_act == MRGAN_ACT_LEAKY_RELU ? cfg->leaky_alpha : 0.0f, cfg->dropout, 1.0f / (1.0f - cfg->dropout)};
   int ne = h->R;
   for (int f = 0; f < h->nf; ++f) ne = folds[f].n_test > ne ? folds[f].n_test : ne;
   h->NE = ne;

@@ -19,6 +19,14 @@ def d_noise(key, step, rows, D, row0, tids=philox.TID_D_LAYER):
     return [philox.normal(key, step, tids[l], rows, widths[l], row0=row0) for l in range(5)]
 
 
+def d_transforms(key, step, rows, D, row0, dropout_rate, tids=philox.TID_D_LAYER):
+    """Dropout variant (others/wganlpctsemi.py:170) of ``d_noise``: N(0,1) for the input layer, Dropout keep factors for
+    the four transforms in front of hidden layers 2..5 -- the ``noise`` list of gan_oracle.disc_forward(dropout=True)."""
+    widths = (D,) + O.D_WIDTHS[:4]
+    return [philox.normal(key, step, tids[0], rows, widths[0], row0=row0)] + \
+           [philox.dropout_factor(key, step, tids[l], rows, widths[l], dropout_rate, row0=row0) for l in range(1, 5)]
+
+
 def prep_fold(X_train, X_test, y_train, y_test, percentlabeled, percentunlabeled, rng, K=O.K_CLASSES):
     """mr_gan.py:96-107: StandardScaler, shuffle, first 10*percent rows per class as labeled.
 

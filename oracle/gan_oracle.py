@@ -144,16 +144,26 @@ def gen_backward(pG, c, dout):
 
 
 # -------------------------------------------------------------- discriminator
-def disc_forward(pD, x, noise=None, upto_mid=False):
+# Variant of others/wganlpctsemi.py:166-179 (LeakyReLU + Dropout stacks), off by default:
+#   alpha > 0 : the hidden activation is LeakyReLU(alpha) (Keras default alpha = 0.3) instead of ReLU;
+#   dropout   : ``noise[l]`` for l >= 1 then holds Dropout KEEP FACTORS (0 or 1 / (1 - rate), Keras inverted dropout) that
+#               MULTIPLY the layer input in place of the additive GaussianNoise; noise[0] stays the N(0,1) input noise.
+def disc_forward(pD, x, noise=None, upto_mid=False, alpha=0.0, dropout=False):
     """mr_gan.py:117-128.  ``noise`` = list of 5 N(0,1) arrays (train phase) or None (test phase)."""
     a, a_in, hs = x, [], []
     for l in range(5):
-        ai = a + D_SIGMAS[l] * noise[l] if noise is not None else a
-        h = np.maximum(ai @ pD[2 * l] + pD[2 * l + 1], 0.0)
+        if noise is None:
+            ai = a
+        elif dropout and l >= 1:
+            ai = a * noise[l]
+        else:
+            ai = a + D_SIGMAS[l] * noise[l]
+        z = ai @ pD[2 * l] + pD[2 * l + 1]
+        h = np.where(z > 0, z, alpha * z)
         a_in.append(ai)
         hs.append(h)
         a = h
-    cache = dict(a_in=a_in, h=hs)
+    cache = dict(a_in=a_in, h=hs, alpha=alpha, drop=noise if (dropout and noise is not None) else None)
     if upto_mid:                       # mid_output model, mr_gan.py:127,133
         return a, cache
     return a @ pD[10] + pD[11], cache
@@ -168,12 +178,15 @@ def disc_backward(pD, c, dtop, from_mid=False, need_dx=False):
         g[10] = c['h'][4].T @ dtop
         g[11] = dtop.sum(axis=0)
         dh = dtop @ pD[10].T
+    alpha, drop = c.get('alpha', 0.0), c.get('drop')
     for l in range(4, -1, -1):
-        dz = dh * (c['h'][l] > 0)
+        dz = dh * np.where(c['h'][l] > 0, 1.0, alpha)
         g[2 * l] = c['a_in'][l].T @ dz
         g[2 * l + 1] = dz.sum(axis=0)
         if l > 0 or need_dx:
-            dh = dz @ pD[2 * l].T
+            dh = dz @ pD[2 * l].T                  # gradient w.r.t. the layer INPUT a_in[l] ...
+            if drop is not None and l >= 1:
+                dh = dh * drop[l]                  # ... and through the Dropout in front of it, w.r.t. h[l-1]
     return g, (dh if need_dx else None)
 
 
@@ -216,7 +229,8 @@ def adam_update(params, grads, ms, vs, t, lr, b1, b2, eps):
 class GanOracle:
     """One fold's G + D + the shared Adam (mr_gan.py:109-171)."""
 
-    def __init__(self, pD, pG, shared_t=True, lr=GAN_LR, b1=GAN_B1, b2=GAN_B2, eps=GAN_EPS):
+    def __init__(self, pD, pG, shared_t=True, lr=GAN_LR, b1=GAN_B1, b2=GAN_B2, eps=GAN_EPS, alpha=0.0, dropout=False):
+        self.var = dict(alpha=alpha, dropout=dropout)      # discriminator variant (see disc_forward)
         self.pD = [np.array(p, dtype=np.float64) for p in pD]
         self.pG = [np.array(p, dtype=np.float64) for p in pG]
         self.mD = [np.zeros_like(p) for p in self.pD]
@@ -242,9 +256,9 @@ class GanOracle:
     # train_batch_disc, mr_gan.py:169 (graph at :141-149,161,166)
     def disc_grads(self, x_lab, labels, x_unl, z, n_lab, n_unl, n_fake):
         fake, _ = gen_forward(self.pG, z)
-        l_lab, c_lab = disc_forward(self.pD, x_lab, n_lab)
-        l_unl, c_unl = disc_forward(self.pD, x_unl, n_unl)
-        l_fake, c_fake = disc_forward(self.pD, fake, n_fake)
+        l_lab, c_lab = disc_forward(self.pD, x_lab, n_lab, **self.var)
+        l_unl, c_unl = disc_forward(self.pD, x_unl, n_unl, **self.var)
+        l_fake, c_fake = disc_forward(self.pD, fake, n_fake, **self.var)
         ll, lu, te, d_lab, d_unl, d_fake = disc_losses(l_lab, labels, l_unl, l_fake)
         g = [np.zeros_like(p) for p in self.pD]
         for c, d in ((c_lab, d_lab), (c_unl, d_unl), (c_fake, d_fake)):
@@ -261,8 +275,8 @@ class GanOracle:
     # train_batch_gen, mr_gan.py:170 (graph at :152-154,167)
     def gen_grads(self, x_unl, z, n_fake, n_real):
         fake, cg = gen_forward(self.pG, z)
-        f_fake, c_fake = disc_forward(self.pD, fake, n_fake, upto_mid=True)
-        f_real, _ = disc_forward(self.pD, x_unl, n_real, upto_mid=True)
+        f_fake, c_fake = disc_forward(self.pD, fake, n_fake, upto_mid=True, **self.var)
+        f_real, _ = disc_forward(self.pD, x_unl, n_real, upto_mid=True, **self.var)
         loss, dmid = fm_loss(f_fake, f_real)
         _, dfake = disc_backward(self.pD, c_fake, dmid, from_mid=True, need_dx=True)
         return loss, gen_backward(self.pG, cg, dfake)
@@ -274,7 +288,7 @@ class GanOracle:
 
     # test_batch, mr_gan.py:171 (phase 0: GaussianNoise is identity)
     def test_batch(self, x, y):
-        logits, _ = disc_forward(self.pD, x, None)
+        logits, _ = disc_forward(self.pD, x, None, alpha=self.var['alpha'])
         return float((logits.argmax(axis=1) != y).mean())
 
 
@@ -282,7 +296,8 @@ class GanOracle:
 class NnOracle:
     """mr_nn.py:101-118: D architecture as a classifier, MSE vs one-hot, default Adam."""
 
-    def __init__(self, pD, lr=NN_LR, b1=NN_B1, b2=NN_B2, eps=NN_EPS):
+    def __init__(self, pD, lr=NN_LR, b1=NN_B1, b2=NN_B2, eps=NN_EPS, alpha=0.0, dropout=False):
+        self.var = dict(alpha=alpha, dropout=dropout)
         self.pD = [np.array(p, dtype=np.float64) for p in pD]
         self.m = [np.zeros_like(p) for p in self.pD]
         self.v = [np.zeros_like(p) for p in self.pD]
@@ -290,7 +305,7 @@ class NnOracle:
         self.hp = (lr, b1, b2, eps)
 
     def grads(self, x, labels, noise):
-        logits, c = disc_forward(self.pD, x, noise)
+        logits, c = disc_forward(self.pD, x, noise, **self.var)
         onehot = np.zeros_like(logits)
         onehot[np.arange(len(labels)), labels] = 1.0
         diff = logits - onehot
@@ -306,7 +321,7 @@ class NnOracle:
         return out
 
     def evaluate(self, x, y):
-        logits, _ = disc_forward(self.pD, x, None)
+        logits, _ = disc_forward(self.pD, x, None, alpha=self.var['alpha'])
         onehot = np.zeros_like(logits)
         onehot[np.arange(len(y)), y] = 1.0
         return float(((logits - onehot) ** 2).mean()), float((logits.argmax(axis=1) == y).mean())

@@ -87,3 +87,17 @@ def normal(key, step, tensor_id, rows, cols, row0=0, dtype=np.float64):
     ang = np.pi * (2.0 * u2 - 1.0)
     odd = np.broadcast_to((r & 1).astype(bool), (rows, cols))
     return np.where(odd, rad * np.sin(ang), rad * np.cos(ang)).astype(dtype)
+
+
+def dropout_factor(key, step, tensor_id, rows, cols, rate, row0=0, dtype=np.float64):
+    """Dropout(rate) keep factors [rows, cols] of the device stream (csrc/common.cuh:dropout4): the same counters as
+    ``normal``; element (row, col) uses word ``row & 3`` of philox(row >> 2, col, step, tensor_id):
+    u = ((x >> 9) + 0.5) * 2**-23 (computed in float32 like the device), kept iff u >= rate, factor 1 / (1 - rate)."""
+    r = (np.arange(rows, dtype=np.int64) + row0)[:, None]
+    c = np.arange(cols, dtype=np.int64)[None, :]
+    x = philox4x32_10(r >> 2, c, np.uint64(step & 0xFFFFFFFF), np.uint64(tensor_id), key[0], key[1])
+    x = np.stack([np.broadcast_to(v, (rows, cols)) for v in x])
+    w = np.take_along_axis(x, np.broadcast_to((r & 3)[None], (1, rows, cols)), axis=0)[0]
+    u = ((w >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(2.0 ** -23)
+    inv = np.float32(1.0) / (np.float32(1.0) - np.float32(rate))
+    return np.where(u >= np.float32(rate), inv, np.float32(0.0)).astype(dtype)

@@ -492,6 +492,51 @@ def test_data_parallel_path_with_virtual_ranks(precision, D, Bg, nb):
     _param_close(pr[0], p1, pD + pG, ptol)
 
 
+@pytest.mark.parametrize("precision", PRECISIONS)
+@pytest.mark.parametrize("act,rate", [("leaky", 0.2), ("relu", 0.4), ("leaky", 0.0)])
+def test_leaky_relu_and_dropout_epilogue_variants_against_oracle(precision, act, rate):
+    """The discriminator variants of others/wganlpctsemi.py:166-179 as epilogue options of the same kernels: LeakyReLU(0.3)
+    hidden activations and Dropout(rate) in place of the GaussianNoise in front of hidden layers 2..5 (the keep mask is a
+    Philox stream the oracle replays; backward recovers it from the dropped activation).  One D step, one G step (each from
+    identical state), test_batch (inference: no dropout) and one mr_nn step, against the float64 oracle."""
+    D, B = 52, 48
+    alpha = 0.3 if act == "leaky" else 0.0
+    hyper = dict(hidden_act=1 if act == "leaky" else 0, leaky_alpha=0.3, dropout=rate)
+    key = philox.fold_key(14, 3)
+    pD, pG, steps = make_golden.case_inputs(D, B, 61, 1)
+    s = steps[0]
+
+    def tr(step, row0):
+        return fold_loop.d_transforms(key, step, B, D, row0, rate) if rate > 0 else fold_loop.d_noise(key, step, B, D, row0)
+
+    mo = O.GanOracle(pD, pG, alpha=alpha, dropout=rate > 0)
+    want_d = mo.disc_step(s['x_lab'], s['labels'], s['x_unl'], s['z_d'], tr(0, 0), tr(0, B), tr(0, 2 * B))
+    mg_ = O.GanOracle(pD, pG, alpha=alpha, dropout=rate > 0)
+    want_g = mg_.gen_step(s['x_unl2'], s['z_g'], tr(0, 0), tr(0, B))
+    with FoldGroup([(D, 100, 40, _key64(key))], precision=precision, batch=B, **hyper) as fg:
+        fg.set_params(0, 0, pD); fg.set_params(0, 1, pG)
+        got_d = fg.train_batch_disc(0, s['x_lab'], s['labels'], s['x_unl'], s['z_d'])
+        _param_close(fg.get_params(0, 0), mo.pD, pD, PARAM_TOL[precision])
+        xt, yt = s['x_unl'][:37], s['labels'][:37]
+        assert abs(fg.test_batch(0, xt, yt) - mo.test_batch(xt, yt)) <= FLIPS[precision] / 37 + 1e-6
+    with FoldGroup([(D, 100, 40, _key64(key))], precision=precision, batch=B, **hyper) as fg:
+        fg.set_params(0, 0, pD); fg.set_params(0, 1, pG)
+        got_g = fg.train_batch_gen(0, s['x_unl2'], s['z_g'])
+        _param_close(fg.get_params(0, 1), mg_.pG, pG, PARAM_TOL[precision])
+    np.testing.assert_allclose(got_d[:2], want_d[:2], rtol=LOSS_RTOL[precision])
+    assert abs(got_d[2] - want_d[2]) <= FLIPS[precision] / B + 1e-6
+    np.testing.assert_allclose(got_g, want_g, rtol=GEN_RTOL_SMALL_BATCH[precision])
+    # mr_nn twin (wganlpctsemi.py:160-181 is the supervised classifier with the same stack)
+    mn_ = O.NnOracle(pD, alpha=alpha, dropout=rate > 0)
+    x, y = s['x_lab'][:20], s['labels'][:20]
+    nz = fold_loop.d_transforms(key, 0, 20, D, 0, rate) if rate > 0 else fold_loop.d_noise(key, 0, 20, D, 0)
+    want = mn_.step(x.astype(np.float64), y, nz)
+    with FoldGroup([(D, 100, 40, _key64(key))], model="nn", precision=precision, **hyper) as fg:
+        fg.set_params(0, 0, pD)
+        got = fg.nn_step(0, x, y)
+    np.testing.assert_allclose(got, want, rtol=LOSS_RTOL[precision], atol=1e-6)
+
+
 def test_device_side_epoch_permutations_match_the_oracle_restatement():
     """mrgan_train_epoch_seeded draws the index streams of mr_gan.py:189-202 on the device: (i) they equal the oracle's
     restatement (oracle/fold_loop.py:device_epoch_indices) element for element, for plain permutations, for the tiled

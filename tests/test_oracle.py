@@ -200,3 +200,43 @@ def test_device_permutation_restatement_is_a_permutation_and_tiles_like_the_refe
     unl = np.arange(3, 15)
     u = fold_loop.device_epoch_indices(key, 1, 31, lab, unl)
     assert sorted(u[1][:12]) == list(unl) and sorted(u[2][24:]) == list(unl[:7])
+
+
+def test_leaky_relu_dropout_variant_gradients_by_finite_differences():
+    """The oracle's restatement of the LeakyReLU + Dropout discriminator stack (others/wganlpctsemi.py:166-179): analytic
+    gradients of both steps against central differences; the replayed keep factors are 0 or 1 / (1 - rate) at about `rate`."""
+    from oracle import fold_loop, gan_oracle as O, philox
+    rng = np.random.default_rng(0)
+    D, B, rate = 12, 8, 0.25
+    pD, pG = O.init_disc_params(D, rng), O.init_gen_params(D, rng)
+    for p in pD + pG:
+        if p.ndim == 1:
+            p += 0.1 * rng.standard_normal(p.shape)
+    key = philox.fold_key(1, 2)
+    m = O.GanOracle(pD, pG, alpha=0.3, dropout=True)
+    x1, x2 = rng.standard_normal((B, D)), rng.standard_normal((B, D))
+    y, z = rng.integers(0, 6, B), rng.standard_normal((B, 100))
+    n = [fold_loop.d_transforms(key, 0, B, D, r0, rate) for r0 in (0, B, 2 * B)]
+    f = np.concatenate([a.ravel() for a in n[0][1:]])
+    assert set(np.unique(f)) <= {0.0, np.float64(np.float32(1) / (np.float32(1) - np.float32(rate)))} and 0.1 < (f == 0).mean() < 0.4
+    (_, _, _), g = m.disc_grads(x1, y, x2, z, *n)
+    for t in (0, 1, 4, 8, 10):
+        idx = tuple(int(rng.integers(0, s)) for s in m.pD[t].shape)
+        old, e = m.pD[t][idx], 1e-6
+        vals = []
+        for d in (e, -e):
+            m.pD[t][idx] = old + d
+            (a, b, _), _ = m.disc_grads(x1, y, x2, z, *n)
+            vals.append(a + b)
+        m.pD[t][idx] = old
+        assert abs(g[t][idx] - (vals[0] - vals[1]) / (2 * e)) <= 1e-6 * max(1.0, abs(g[t][idx]) * 1e3)
+    _, gg = m.gen_grads(x2, z, n[0], n[1])
+    for t in (0, 2, 4, 6):
+        idx = tuple(int(rng.integers(0, s)) for s in m.pG[t].shape)
+        old, e = m.pG[t][idx], 1e-6
+        vals = []
+        for d in (e, -e):
+            m.pG[t][idx] = old + d
+            vals.append(m.gen_grads(x2, z, n[0], n[1])[0])
+        m.pG[t][idx] = old
+        assert abs(gg[t][idx] - (vals[0] - vals[1]) / (2 * e)) <= 1e-9 + 1e-4 * abs(gg[t][idx])
