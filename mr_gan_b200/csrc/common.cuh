@@ -105,16 +105,13 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   return y;
 }
 
-// The 4 normals of rows 4*rowgroup .. 4*rowgroup+3 at column `col`
-// (definition: oracle/philox.py module docstring).
-__device__ __forceinline__ void normal4(uint32_t k0, uint32_t k1, uint32_t rowgroup, uint32_t col,
-                                        uint32_t step, uint32_t tid, float out[4]) {
-  const uint4 x = philox4x32_10(make_uint4(rowgroup, col, step, tid), k0, k1);
+// Box-Muller on the four words of one Philox output: the 4 normals of rows 4*rowgroup .. 4*rowgroup+3
+__device__ __forceinline__ void box_muller4(const uint4 x, float out[4]) {
   const float s = 1.1920928955078125e-07f;   // 2^-23
   const float u1a = ((float)(x.x >> 9) + 0.5f) * s, u2a = ((float)(x.y >> 9) + 0.5f) * s;
   const float u1b = ((float)(x.z >> 9) + 0.5f) * s, u2b = ((float)(x.w >> 9) + 0.5f) * s;
-  // fast-math intrinsics: |error| of a normal <= ~3e-6 (lg2.approx / sin.approx / cos.approx on [-pi, pi]), far below
-  // the 1e-3 loss tolerance; the epilogue warps generate ~800k normals per fold and step pair
+  // fast-math intrinsics: |error| of a normal <= ~3e-6 (lg2.approx / sin.approx / cos.approx on [-pi, pi], sqrt.approx), far
+  // below the 1e-3 loss tolerance; the epilogue warps generate ~800k normals per fold and step pair
   const float ra = sqrt_approx(-2.0f * __logf(u1a)), rb = sqrt_approx(-2.0f * __logf(u1b));
   const float pi = 3.14159265358979323846f;
   const float ta = pi * (2.0f * u2a - 1.0f), tb = pi * (2.0f * u2b - 1.0f);
@@ -122,12 +119,16 @@ __device__ __forceinline__ void normal4(uint32_t k0, uint32_t k1, uint32_t rowgr
   out[0] = ra * ca; out[1] = ra * sa; out[2] = rb * cb; out[3] = rb * sb;
 }
 
-// Dropout(rate) keep factors of rows 4*rowgroup .. +3 at column `col`, from the same counter stream as the Gaussian noise it
-// replaces: u_i = ((x_i >> 9) + 0.5) 2^-23 of the four Philox words, kept (factor 1 / (1 - rate)) iff u_i >= rate
-// (definition: oracle/philox.py:dropout_factor).
-__device__ __forceinline__ void dropout4(uint32_t k0, uint32_t k1, uint32_t rowgroup, uint32_t col, uint32_t step, uint32_t tid,
-                                         float rate, float inv, float out[4]) {
-  const uint4 x = philox4x32_10(make_uint4(rowgroup, col, step, tid), k0, k1);
+// The 4 normals of rows 4*rowgroup .. 4*rowgroup+3 at column `col`
+// (definition: oracle/philox.py module docstring).
+__device__ __forceinline__ void normal4(uint32_t k0, uint32_t k1, uint32_t rowgroup, uint32_t col,
+                                        uint32_t step, uint32_t tid, float out[4]) {
+  box_muller4(philox4x32_10(make_uint4(rowgroup, col, step, tid), k0, k1), out);
+}
+
+// Dropout(rate) keep factors of the same four rows from the same four words: u_i = ((x_i >> 9) + 0.5) 2^-23, kept (factor
+// 1 / (1 - rate)) iff u_i >= rate (definition: oracle/philox.py:dropout_factor).
+__device__ __forceinline__ void keep4(const uint4 x, float rate, float inv, float out[4]) {
   const float s = 1.1920928955078125e-07f;   // 2^-23
   out[0] = (((float)(x.x >> 9) + 0.5f) * s >= rate) ? inv : 0.f;
   out[1] = (((float)(x.y >> 9) + 0.5f) * s >= rate) ? inv : 0.f;
@@ -135,11 +136,12 @@ __device__ __forceinline__ void dropout4(uint32_t k0, uint32_t k1, uint32_t rowg
   out[3] = (((float)(x.w >> 9) + 0.5f) * s >= rate) ? inv : 0.f;
 }
 // what a forward epilogue combines with the activation of rows 4*rowgroup..+3: N(0,1) draws (y = x + sigma n) or, with
-// drop > 0, dropout keep factors (y = x f)
+// drop > 0, dropout keep factors (y = x f).  ONE Philox evaluation either way (the counter stream is shared).
 __device__ __forceinline__ void noise_or_drop4(uint32_t k0, uint32_t k1, uint32_t rowgroup, uint32_t col, uint32_t step, uint32_t tid,
                                                float drop, float inv, float out[4]) {
-  if (drop > 0.f) dropout4(k0, k1, rowgroup, col, step, tid, drop, inv, out);
-  else normal4(k0, k1, rowgroup, col, step, tid, out);
+  const uint4 x = philox4x32_10(make_uint4(rowgroup, col, step, tid), k0, k1);
+  if (drop > 0.f) keep4(x, drop, inv, out);
+  else box_muller4(x, out);
 }
 
 // Out-of-line noise draws for the GEMM epilogues: they draw up to 38 row groups per thread from several places, and an

@@ -204,10 +204,8 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
   // rows that this step assembles from the data set: mode 0 -> [0, 2B), mode 1 -> [B, 2B), mode 2 -> [0, nrows)
   const int r_lo = (mode == 1) ? B : 0, r_hi = (mode == 2) ? nrows : min(nrows, 2 * B);
   // A thread assembles PREP_GROUPS row groups of 4 rows of one column: the gathers of all of them are issued first, then
-  // their Philox chains run interleaved (one chain per thread left this kernel latency-bound: 24 % of the large-batch step);
-  // gridDim.y is capped, so at large batches a block walks several row slabs instead of 190 k tiny blocks being scheduled
-  const int nslab = (nrows + 4 * PREP_GROUPS - 1) / (4 * PREP_GROUPS);
-  for (int rg = blockIdx.y; rg < nslab; rg += gridDim.y) {
+  // their Philox chains run interleaved (one chain per thread left this kernel latency-bound: 24 % of the large-batch step)
+  const int rg = blockIdx.y;
   if (c < D) {
     // descriptor fields in registers: through the FoldState reference every use is a generic load that the stores to a0
     // force the compiler to repeat
@@ -269,7 +267,6 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
       }
     }
   }
-  }      // row slabs
 }
 
 // ------------------------------------------------------------------ BatchNorm (batch statistics)

@@ -309,14 +309,15 @@ __device__ __forceinline__ void head_disc(uint32_t trow, int cbeg, int ncols, in
 // HEAD_FM: rows [0,B) = fake, [B,2B) = real post-ReLU activations of D layer 5; this thread's feature f (MT = 2: the warp
 // group owns all rows of its sub-tile).  Writes the warp's partial of sum_f diff_f^2 to *red and dZ5 (already multiplied by
 // ReLU') for the fake rows (mr_gan.py:152-154).
-template <bool F16>
+template <bool F16, bool VAR>
 __device__ __forceinline__ void head_fm(uint32_t trow, int ncols, int f, bool f_ok, int lane, const LossDesc& L, const AdamHyper& hp,
                                         const OperandMode& om, float* red) {
+  constexpr int HACT = VAR ? ACT_LEAKY : ACT_RELU;      // alpha = 0 in the VAR kernels reproduces ReLU
   const int B = hp.dp_bloc;
   float mg = 0.f, mr = 0.f;
   for (int c0 = 0; c0 < ncols; c0 += 16) {
     float x[16];
-    head_chunk<F16, ACT_LEAKY>(trow + (uint32_t)c0, x, hp.alpha);      // alpha = 0: ReLU
+    head_chunk<F16, HACT>(trow + (uint32_t)c0, x, hp.alpha);
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int r = c0 + j;
@@ -330,7 +331,7 @@ __device__ __forceinline__ void head_fm(uint32_t trow, int ncols, int f, bool f_
   if (!F16) g = rna_tf32(g);
   for (int c0 = 0; c0 < B; c0 += 16) {
     float x[16];
-    head_chunk<F16, ACT_LEAKY>(trow + (uint32_t)c0, x, hp.alpha);
+    head_chunk<F16, HACT>(trow + (uint32_t)c0, x, hp.alpha);
     if (!f_ok) continue;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -437,7 +438,9 @@ __device__ __forceinline__ void head_bn_bwd(uint32_t trow, int cbeg, int ncols, 
 // swizzle, UMMA layout 2, SBO 1024 B, LBO 8192 B); otherwise fp32 operands read as tf32 (32 elements per row, K = 8 per
 // MMA, MN-major boxes of 32 x 32 with the 32-byte-atom swizzle, UMMA layout 1, SBO 512 B, LBO 4096 B).  Compile-time,
 // so every descriptor constant folds and the single-thread producer / issuer loops unroll.
-template <bool A_MN, bool B_MN, int STAGES, int TMEM_COLS, int MINB, int EPW, int MT, bool F16>
+// VAR: the LeakyReLU / Dropout variants of the discriminator (others/wganlpctsemi.py:166-179) are compiled in.  A separate
+// instantiation, because carrying them in the reference configuration's epilogues measured 2.3 % of the whole step.
+template <bool A_MN, bool B_MN, int STAGES, int TMEM_COLS, int MINB, int EPW, int MT, bool F16, bool VAR>
 __global__ void __launch_bounds__(64 + 32 * EPW, MINB)
 k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_override, AdamHyper hp, OperandMode om) {
   using namespace tc;
@@ -652,7 +655,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
       // accumulator and the parked values are fetched with two TMEM loads behind ONE wait.
       const bool has_act = g.act != ACT_NONE;
       // Dropout variant: aux is the layer's DROPPED output a (see dx_rows), which in f16 mode exists only as the fp16 copy
-      const bool drop = hp.drop > 0.f && (g.act == ACT_RELU || g.act == ACT_LEAKY) && g.tid >= 1;
+      const bool drop = VAR && hp.drop > 0.f && (g.act == ACT_RELU || g.act == ACT_LEAKY) && g.tid >= 1;
       const __half* const haux = (F16 && drop) ? om.hbase + (g.aux - om.fbase) : nullptr;
       auto fetch = [&](int c0, float (&av)[16]) {
 #pragma unroll
@@ -708,7 +711,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         __half* const phC = F16 ? hC + o0 : nullptr;
         const float dinv = drop ? hp.drop_inv : 1.0f;
         if (g.act == ACT_RELU) dx_rows<F16, ACT_RELU>(va, av, nrows, pC, phC, g.ldc, op_only, 0.f, dinv, drop);
-        else if (g.act == ACT_LEAKY) dx_rows<F16, ACT_LEAKY>(va, av, nrows, pC, phC, g.ldc, op_only, hp.alpha, dinv, drop);
+        else if (VAR && g.act == ACT_LEAKY) dx_rows<F16, ACT_LEAKY>(va, av, nrows, pC, phC, g.ldc, op_only, hp.alpha, dinv, drop);
         else if (g.act == ACT_SOFTPLUS) dx_rows<F16, ACT_SOFTPLUS>(va, av, nrows, pC, phC, g.ldc, op_only, 0.f, 1.0f, false);
         else dx_rows<F16, ACT_NONE>(va, av, nrows, pC, phC, g.ldc, op_only, 0.f, 1.0f, false);
       }
@@ -723,7 +726,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
       // for it, so the Philox rounds hide the load latency; per chunk there is one wait for both TMEM loads.
       // Dropout variant (hp.drop > 0): the transforms in front of D's hidden layers 2..5 (stream ids 1..4) are Dropout(rate)
       // instead of GaussianNoise: the parked / drawn values are keep factors and combine by multiplication
-      const bool mul = hp.drop > 0.f && g.C2 != nullptr && g.tid >= 1;
+      const bool mul = VAR && hp.drop > 0.f && g.C2 != nullptr && g.tid >= 1;
       const float ddrop = mul ? hp.drop : 0.f;
       const bool noisy = g.C2 != nullptr && (g.sigma != 0.f || mul);
       uint32_t key0 = 0, key1 = 0, step = 0;
@@ -738,8 +741,10 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
           // the common case: four independent Philox chains, inlined so the compiler interleaves them (the epilogue warps
           // are latency-bound here: 2 warps per scheduler)
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            noise_or_drop4(key0, key1, (uint32_t)(r0 + 4 * q) >> 2, (uint32_t)f, step, (uint32_t)g.tid, ddrop, hp.drop_inv, &nz[4 * q]);
+          for (int q = 0; q < 4; ++q) {
+            if (VAR) noise_or_drop4(key0, key1, (uint32_t)(r0 + 4 * q) >> 2, (uint32_t)f, step, (uint32_t)g.tid, ddrop, hp.drop_inv, &nz[4 * q]);
+            else normal4(key0, key1, (uint32_t)(r0 + 4 * q) >> 2, (uint32_t)f, step, (uint32_t)g.tid, &nz[4 * q]);
+          }
         } else if (grp) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -795,12 +800,12 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
 #pragma unroll
           for (int j = 0; j < 16; ++j) nz[j] = 0.f;
         }
-#define FWD_ROWS(ACT, HC, HC2) fwd_rows<F16, ACT, HC, HC2>(va, nz, nrows, pC, phC, g.ldc, c_op, pC2, phC2, g.ldc2, c2_op, g.sigma, hp.alpha, mul)
+#define FWD_ROWS(ACT, HC, HC2) fwd_rows<F16, ACT, HC, HC2>(va, nz, nrows, pC, phC, g.ldc, c_op, pC2, phC2, g.ldc2, c2_op, g.sigma, hp.alpha, VAR && mul)
 #define FWD_ACT(HC, HC2)                                                     \
         do {                                                                 \
           if (g.act == ACT_RELU) FWD_ROWS(ACT_RELU, HC, HC2);                \
           else if (g.act == ACT_SOFTPLUS) FWD_ROWS(ACT_SOFTPLUS, HC, HC2);   \
-          else if (g.act == ACT_LEAKY) FWD_ROWS(ACT_LEAKY, HC, HC2);         \
+          else if (VAR && g.act == ACT_LEAKY) FWD_ROWS(ACT_LEAKY, HC, HC2);  \
           else FWD_ROWS(ACT_NONE, HC, HC2);                                  \
         } while (0)
         if (g.C && g.C2) FWD_ACT(true, true);
@@ -815,7 +820,7 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         head_disc<F16, EPW>(trow, cbeg, ncols, min(bn, NE - n0), lane_base, lane, warp - 2, *static_cast<const LossDesc*>(op.hd), hp, om,
                             sl, sl + 8192);
       } else if (op.head == HEAD_FM) {  // MT == 2 (host): this warp group owns its sub-tile's features and all rows
-        head_fm<F16>(trow, ncols, f, f_ok, lane, *static_cast<const LossDesc*>(op.hd), hp, om, red + (warp - 2));
+        head_fm<F16, VAR>(trow, ncols, f, f_ok, lane, *static_cast<const LossDesc*>(op.hd), hp, om, red + (warp - 2));
       } else if (op.head == HEAD_BN) {
         head_bn<F16>(trow, cbeg, ncols, min(bn, NE - n0), f, f_ok, *static_cast<const BnDesc*>(op.hd), hp, om);
       }

@@ -654,8 +654,7 @@ void launch_prep(mrgan_handle* h, int f0, int nfl, int mode, int from_stage, int
   const mrgan_config& c = h->cfg;
   int cols = max_D(h, f0, nfl);
   if (c.noise_dim > cols) cols = c.noise_dim;
-  const int nslab = (nrows + 4 * PREP_GROUPS - 1) / (4 * PREP_GROUPS);
-  dim3 grid((cols + 127) / 128, std::min(nslab, 64), nfl);
+  dim3 grid((cols + 127) / 128, (nrows + 4 * PREP_GROUPS - 1) / (4 * PREP_GROUPS), nfl);
   launch_k(h, k_prep, grid, dim3(128), 0, h->stream, h->d_folds, f0, mode, from_stage, t, c.batch, nrows, c.noise_dim, c.sigma_in, h->hp,
            h->om);
 }
@@ -986,23 +985,27 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 #define TC_FWD_THREADS (64 + 32 * 8)
 #define TC_DW_THREADS (64 + 32 * 4)
 // kernel instantiations, indexed by the operand format F (false: fp32 operands as tf32, true: fp16 operand copies)
-#define K_TC_FWD(F) k_gemm_tc<true, false, TC_FWD_STAGES, 256, 1, 8, 1, F>
-#define K_TC_FWD_N(F) k_gemm_tc<true, false, TC_FWD_STAGES, 512, 1, 8, 1, F>   // all 512 TMEM columns: room to park the epilogue's noise
-#define K_TC_DX(F) k_gemm_tc<false, false, TC_FWD_STAGES, 256, 1, 8, 1, F>
-#define K_TC_FWD2(F) k_gemm_tc<true, false, TC_FWD_STAGES, 512, 1, 8, 2, F>     // 256 features per CTA (layers >= 500 wide)
-#define K_TC_DX_N(F) k_gemm_tc<false, false, TC_FWD_STAGES, 512, 1, 8, 1, F>
-#define K_TC_DX2(F) k_gemm_tc<false, false, TC_FWD_STAGES, 512, 1, 8, 2, F>
-#define K_TC_DW(F) k_gemm_tc<true, true, TC_DW_STAGES, 128, 2, 4, 1, F>
+#define K_TC_FWD(F, V) k_gemm_tc<true, false, TC_FWD_STAGES, 256, 1, 8, 1, F, V>
+#define K_TC_FWD_N(F, V) k_gemm_tc<true, false, TC_FWD_STAGES, 512, 1, 8, 1, F, V>   // all 512 TMEM columns: room to park the epilogue's noise
+#define K_TC_DX(F, V) k_gemm_tc<false, false, TC_FWD_STAGES, 256, 1, 8, 1, F, V>
+#define K_TC_FWD2(F, V) k_gemm_tc<true, false, TC_FWD_STAGES, 512, 1, 8, 2, F, V>     // 256 features per CTA (layers >= 500 wide)
+#define K_TC_DX_N(F, V) k_gemm_tc<false, false, TC_FWD_STAGES, 512, 1, 8, 1, F, V>
+#define K_TC_DX2(F, V) k_gemm_tc<false, false, TC_FWD_STAGES, 512, 1, 8, 2, F, V>
+#define K_TC_DW(F, V) k_gemm_tc<true, true, TC_DW_STAGES, 128, 2, 4, 1, F, V>
 // large-batch regime (more than 256 batch rows: data-parallel config 5): 256 x 256 tiles, 3-stage ring of 64 KB stages
 #define TC_BIG_STAGES 3
-#define K_TC_FWD_BIG(F) k_gemm_tc<true, false, TC_BIG_STAGES, 512, 1, 8, 2, F>
-#define K_TC_DX_BIG(F) k_gemm_tc<false, false, TC_BIG_STAGES, 512, 1, 8, 2, F>
-#define K_TC_DW_BIG(F) k_gemm_tc<true, true, TC_BIG_STAGES, 512, 1, 8, 2, F>
-// launches K(false) or K(true) with identical arguments
+#define K_TC_FWD_BIG(F, V) k_gemm_tc<true, false, TC_BIG_STAGES, 512, 1, 8, 2, F, V>
+#define K_TC_DX_BIG(F, V) k_gemm_tc<false, false, TC_BIG_STAGES, 512, 1, 8, 2, F, V>
+#define K_TC_DW_BIG(F, V) k_gemm_tc<true, true, TC_BIG_STAGES, 512, 1, 8, 2, F, V>
+// launches K(operand format, variant) with identical arguments: f16 = fp16 operand copies, var = the handle uses the
+// LeakyReLU / Dropout discriminator variants (their epilogue code lives in separate instantiations)
 #define TC_LAUNCH(h, f16, K, grid, block, smem, st, ...)                          \
   do {                                                                            \
-    if (f16) launch_k(h, K(true), grid, block, smem, st, __VA_ARGS__);            \
-    else launch_k(h, K(false), grid, block, smem, st, __VA_ARGS__);               \
+    const bool var_ = (h)->cfg.hidden_act != MRGAN_ACT_RELU || (h)->cfg.dropout > 0.0f;                \
+    if (f16 && var_) launch_k(h, K(true, true), grid, block, smem, st, __VA_ARGS__);                   \
+    else if (f16) launch_k(h, K(true, false), grid, block, smem, st, __VA_ARGS__);                     \
+    else if (var_) launch_k(h, K(false, true), grid, block, smem, st, __VA_ARGS__);                    \
+    else launch_k(h, K(false, false), grid, block, smem, st, __VA_ARGS__);                             \
   } while (0)
 size_t tc_smem_bytes(int bn, int stages, int mt = 1) { return 1024 + (size_t)stages * ((size_t)mt * 128 * 128 + (size_t)bn * 128) + 256; }
 // two feature sub-tiles per CTA when the layer is wide enough and the 4-stage ring still fits in 227 KB
@@ -1018,21 +1021,26 @@ EncodeTiledFn tc_encoder() {
   return fn;
 }
 
-template <bool F> void tc_set_smem_attr_fmt() {
-  cudaFuncSetAttribute(K_TC_FWD(F), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
-  cudaFuncSetAttribute(K_TC_FWD_N(F), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
-  cudaFuncSetAttribute(K_TC_DX(F), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
-  cudaFuncSetAttribute(K_TC_DX_N(F), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
-  cudaFuncSetAttribute(K_TC_FWD_BIG(F), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(K_TC_DX_BIG(F), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(K_TC_DW_BIG(F), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(K_TC_FWD2(F), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(K_TC_DX2(F), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  cudaFuncSetAttribute(K_TC_DW(F), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(128, TC_DW_STAGES));
-  cudaFuncSetAttribute(k_dw_adam_tc<F, (F ? 64 : 32)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcAdamCfg<F, (F ? 64 : 32)>::SMEM);
-  cudaFuncSetAttribute(k_dw_adam_tc<F, (F ? 32 : 16)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcAdamCfg<F, (F ? 32 : 16)>::SMEM);
+template <bool F, bool V> void tc_set_smem_attr_fmt() {
+  cudaFuncSetAttribute(K_TC_FWD(F, V), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
+  cudaFuncSetAttribute(K_TC_FWD_N(F, V), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
+  cudaFuncSetAttribute(K_TC_DX(F, V), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
+  cudaFuncSetAttribute(K_TC_DX_N(F, V), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(256, TC_FWD_STAGES));
+  cudaFuncSetAttribute(K_TC_FWD_BIG(F, V), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(K_TC_DX_BIG(F, V), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(K_TC_DW_BIG(F, V), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(K_TC_FWD2(F, V), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(K_TC_DX2(F, V), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaFuncSetAttribute(K_TC_DW(F, V), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem_bytes(128, TC_DW_STAGES));
+  if (!V) {
+    cudaFuncSetAttribute(k_dw_adam_tc<F, (F ? 64 : 32)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcAdamCfg<F, (F ? 64 : 32)>::SMEM);
+    cudaFuncSetAttribute(k_dw_adam_tc<F, (F ? 32 : 16)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcAdamCfg<F, (F ? 32 : 16)>::SMEM);
+  }
 }
-void tc_set_smem_attr() { tc_set_smem_attr_fmt<false>(); tc_set_smem_attr_fmt<true>(); }
+void tc_set_smem_attr() {
+  tc_set_smem_attr_fmt<false, false>(); tc_set_smem_attr_fmt<true, false>();
+  tc_set_smem_attr_fmt<false, true>(); tc_set_smem_attr_fmt<true, true>();
+}
 
 // fills the tcgen05 view of one GEMM (shapes in the fp32 path's convention); mode 0 fwd, 1 dX, 2 dW
 // esz = 2: g.A / g.B point at fp16 operand copies (pitches in elements); the epilogue side of g is unchanged.
@@ -2261,9 +2269,9 @@ int mrgan_debug_gemm_time(mrgan_handle* h, int mode, int M, int N, int K, int gr
   dim3 grid((t.ME + 127) / 128, (t.NE + t.bn - 1) / t.bn, groups);
   auto once = [&]() {
     const OperandMode om0{0, 1.0f, nullptr, nullptr};
-    if (mode == 0) K_TC_FWD(false)<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, om0);
-    else if (mode == 1) K_TC_DX(false)<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, om0);
-    else K_TC_DW(false)<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, om0);
+    if (mode == 0) K_TC_FWD(false, false)<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, om0);
+    else if (mode == 1) K_TC_DX(false, false)<<<grid, TC_FWD_THREADS, tc_smem_bytes(t.bn, TC_FWD_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, om0);
+    else K_TC_DW(false, false)<<<grid, TC_DW_THREADS, tc_smem_bytes(t.bn, TC_DW_STAGES), h->stream>>>(dops, h->d_folds, 0, h->hp, om0);
   };
   once();
   CK(cudaEventRecord(h->ev0, h->stream));
