@@ -191,31 +191,52 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // ---- epilogue row processors: one 16-row chunk of one feature (= thread).  Everything that is uniform over the launch
 // (activation, which outputs exist, operand formats) is a template parameter, so a row costs ~10 instructions instead
 // of ~60 of branchy code; the chunk loops dispatch once per chunk.  Pointers walk down the rows by the pitch.
-template <bool F16, int ACT, bool HAS_C, bool HAS_C2>
+// Global stores of the epilogues: plain st.global (the output pointers are never in another state space; a generic ST would
+// carry the state-space check) of one element per row, addressed as base + j * pitch so that no pointer chain links the rows.
+__device__ __forceinline__ void stg_f32(float* p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void stg_h16(__half* p, __half v) { asm volatile("st.global.b16 [%0], %1;" ::"l"(p), "h"(__half_as_ushort(v)) : "memory"); }
+
+// FULL: all 16 rows of the chunk exist (every chunk but the last of a tile) -- no per-row predicate at all.  The branches
+// on c_op / c2_op are uniform over the launch and sit outside the row loops, so a row is ~8 straight-line instructions.
+template <bool F16, int ACT, bool HAS_C, bool HAS_C2, bool FULL>
 __device__ __forceinline__ void fwd_rows(const uint32_t (&va)[16], const float (&nz)[16], int nrows, float* pC, __half* hC, int ldc,
                                          bool c_op, float* pC2, __half* hC2, int ldc2, bool c2_op, float sigma, float alpha, bool mul) {
+  float x[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    float x = __uint_as_float(va[j]);
-    if (!F16) x *= TF32_TRUNC_DEBIAS;
-    if (ACT == ACT_RELU) x = fmaxf(x, 0.f);
-    else if (ACT == ACT_SOFTPLUS) x = softplus_fast(x);
-    else if (ACT == ACT_LEAKY) x = x > 0.f ? x : alpha * x;
-    const bool ok = j < nrows;
-    if (HAS_C) {                // clean activation: kept in fp32 (act' of the backward pass, feature matching, logits) ...
-      if (F16) {
-        if (ok) { *pC = x; if (c_op) *hC = __float2half_rn(x); }      // ... plus its 16-bit operand copy where a GEMM reads it
-        hC += ldc;
-      } else if (ok) *pC = c_op ? rna_tf32(x) : x;
-      pC += ldc;
+    float v = __uint_as_float(va[j]);
+    if (!F16) v *= TF32_TRUNC_DEBIAS;
+    if (ACT == ACT_RELU) v = fmaxf(v, 0.f);
+    else if (ACT == ACT_SOFTPLUS) v = softplus_fast(v);
+    else if (ACT == ACT_LEAKY) v = v > 0.f ? v : alpha * v;
+    x[j] = v;
+  }
+  if (HAS_C) {                  // clean activation: kept in fp32 (act' of the backward pass, feature matching, logits) ...
+    if (!F16 && c_op) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) if (FULL || j < nrows) stg_f32(pC + (uint32_t)(j * ldc), rna_tf32(x[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) if (FULL || j < nrows) stg_f32(pC + (uint32_t)(j * ldc), x[j]);
     }
-    if (HAS_C2) {               // noisy activation: only ever a GEMM operand
-      const float y = mul ? x * nz[j] : fmaf(sigma, nz[j], x);      // Dropout keep factor / GaussianNoise
-      if (F16) {
-        if (ok) { if (c2_op) *hC2 = __float2half_rn(y); else *pC2 = y; }
-        hC2 += ldc2;
-      } else if (ok) *pC2 = c2_op ? rna_tf32(y) : y;
-      pC2 += ldc2;
+    if (F16 && c_op) {          // ... plus its 16-bit operand copy where a GEMM reads it
+#pragma unroll
+      for (int j = 0; j < 16; ++j) if (FULL || j < nrows) stg_h16(hC + (uint32_t)(j * ldc), __float2half_rn(x[j]));
+    }
+  }
+  if (HAS_C2) {                 // noisy activation: only ever a GEMM operand
+    float y[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = mul ? x[j] * nz[j] : fmaf(sigma, nz[j], x[j]);      // Dropout keep factor / GaussianNoise
+    if (F16 && c2_op) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) if (FULL || j < nrows) stg_h16(hC2 + (uint32_t)(j * ldc2), __float2half_rn(y[j]));
+    } else if (!F16 && c2_op) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) if (FULL || j < nrows) stg_f32(pC2 + (uint32_t)(j * ldc2), rna_tf32(y[j]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) if (FULL || j < nrows) stg_f32(pC2 + (uint32_t)(j * ldc2), y[j]);
     }
   }
 }
@@ -223,24 +244,30 @@ __device__ __forceinline__ void fwd_rows(const uint32_t (&va)[16], const float (
 // ACT_RELU / ACT_LEAKY: av is the layer's clean output h (slope 1 where h > 0, else alpha; alpha = 0 for ReLU) -- or, when a
 // Dropout layer follows the activation (dinv = 1 / (1 - rate)), its DROPPED output a = f h: the element was dropped iff
 // a == 0, and a kept element has the sign of h, so one array carries both derivatives.
-template <bool F16, int ACT>
+template <bool F16, int ACT, bool FULL>
 __device__ __forceinline__ void dx_rows(const uint32_t (&va)[16], const float (&av)[16], int nrows, float* pC, __half* hC, int ldc, bool op_only,
                                         float alpha, float dinv, bool drop) {
+  float x[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    float x = __uint_as_float(va[j]);
-    if (!F16) x *= TF32_TRUNC_DEBIAS;
+    float v = __uint_as_float(va[j]);
+    if (!F16) v *= TF32_TRUNC_DEBIAS;
     if (ACT == ACT_RELU || ACT == ACT_LEAKY) {
       float m = (av[j] > 0.f ? 1.0f : (ACT == ACT_LEAKY ? alpha : 0.f)) * dinv;
       if (drop && av[j] == 0.f) m = 0.f;
-      x *= m;
-    } else if (ACT == ACT_SOFTPLUS) x *= 1.0f - __expf(-av[j]);
-    if (j < nrows) {
-      if (F16 && op_only) *hC = grad_to_half(x);             // operand only: 16-bit copy, loss-scaled like the accumulator
-      else *pC = (!F16 && op_only) ? rna_tf32(x) : x;
-    }
-    pC += ldc;
-    if (F16) hC += ldc;
+      v *= m;
+    } else if (ACT == ACT_SOFTPLUS) v *= 1.0f - __expf(-av[j]);
+    x[j] = v;
+  }
+  if (F16 && op_only) {         // operand only: 16-bit copy, loss-scaled like the accumulator
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (FULL || j < nrows) stg_h16(hC + (uint32_t)(j * ldc), grad_to_half(x[j]));
+  } else if (!F16 && op_only) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (FULL || j < nrows) stg_f32(pC + (uint32_t)(j * ldc), rna_tf32(x[j]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) if (FULL || j < nrows) stg_f32(pC + (uint32_t)(j * ldc), x[j]);
   }
 }
 
@@ -710,10 +737,15 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         float* const pC = g.C + o0;
         __half* const phC = F16 ? hC + o0 : nullptr;
         const float dinv = drop ? hp.drop_inv : 1.0f;
-        if (g.act == ACT_RELU) dx_rows<F16, ACT_RELU>(va, av, nrows, pC, phC, g.ldc, op_only, 0.f, dinv, drop);
-        else if (VAR && g.act == ACT_LEAKY) dx_rows<F16, ACT_LEAKY>(va, av, nrows, pC, phC, g.ldc, op_only, hp.alpha, dinv, drop);
-        else if (g.act == ACT_SOFTPLUS) dx_rows<F16, ACT_SOFTPLUS>(va, av, nrows, pC, phC, g.ldc, op_only, 0.f, 1.0f, false);
-        else dx_rows<F16, ACT_NONE>(va, av, nrows, pC, phC, g.ldc, op_only, 0.f, 1.0f, false);
+#define DX_ACT(FULL)                                                                                                        \
+        do {                                                                                                                    \
+          if (g.act == ACT_RELU) dx_rows<F16, ACT_RELU, FULL>(va, av, nrows, pC, phC, g.ldc, op_only, 0.f, dinv, drop);         \
+          else if (VAR && g.act == ACT_LEAKY) dx_rows<F16, ACT_LEAKY, FULL>(va, av, nrows, pC, phC, g.ldc, op_only, hp.alpha, dinv, drop); \
+          else if (g.act == ACT_SOFTPLUS) dx_rows<F16, ACT_SOFTPLUS, FULL>(va, av, nrows, pC, phC, g.ldc, op_only, 0.f, 1.0f, false);      \
+          else dx_rows<F16, ACT_NONE, FULL>(va, av, nrows, pC, phC, g.ldc, op_only, 0.f, 1.0f, false);                          \
+        } while (0)
+        if (nrows >= 16) DX_ACT(true); else DX_ACT(false);
+#undef DX_ACT
       }
       if (op.head == HEAD_BN_BWD)
         head_bn_bwd<F16>(trow, cbeg, ncols, min(bn, NE - n0), f, f_ok, *static_cast<const BnDesc*>(op.hd), hp, om, folds[g.fold].lr_t[1],
@@ -771,10 +803,19 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
       __half* const hC = (F16 && g.C) ? om.hbase + (g.C - om.fbase) : nullptr;
       __half* const hC2 = (F16 && g.C2) ? om.hbase + (g.C2 - om.fbase) : nullptr;
       const bool c_op = (g.rnd & 1) != 0, c2_op = (g.rnd & 2) != 0;   // C / C2 feed a tensor-core GEMM as operands
-      for (int ch = 0; ch < nchunks; ++ch) {
+#ifdef MRGAN_PHASE_TIMING
+      unsigned long long tch[24];
+#endif
+      // The second warp group walks its chunks backwards: the two warps that share a scheduler (one of each group) then work on
+      // a parked chunk (store-bound) and a drawn chunk (ALU-bound) at the same time instead of both on the same kind.
+      for (int it = 0; it < nchunks; ++it) {
+        const int ch = (wg & 1) ? nchunks - 1 - it : it;
         const int c0 = cbeg + 16 * ch;
         uint32_t va[16], vn[16];
         float nz[16];
+#ifdef MRGAN_PHASE_TIMING
+        if (ch < 12) tch[2 * ch] = gtimer();
+#endif
         tmem_ld16_issue(trow + (uint32_t)c0, va);
         if (ch < npk) tmem_ld16_issue(tfree + 16u * (uint32_t)ch, vn);
 #ifdef MRGAN_EXP_NODRAW
@@ -783,6 +824,9 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
         else if (noisy) draw16(c0, nz);                        // overlaps the accumulator load
 #endif
         tmem_wait_ld();
+#ifdef MRGAN_PHASE_TIMING
+        if (ch < 12) tch[2 * ch + 1] = gtimer();
+#endif
         tmem_fence16(va);
         if (ch < npk) {
           tmem_fence16(vn);
@@ -800,20 +844,36 @@ k_gemm_tc(const TcOp* __restrict__ ops, FoldState* __restrict__ folds, int rows_
 #pragma unroll
           for (int j = 0; j < 16; ++j) nz[j] = 0.f;
         }
-#define FWD_ROWS(ACT, HC, HC2) fwd_rows<F16, ACT, HC, HC2>(va, nz, nrows, pC, phC, g.ldc, c_op, pC2, phC2, g.ldc2, c2_op, g.sigma, hp.alpha, VAR && mul)
-#define FWD_ACT(HC, HC2)                                                     \
-        do {                                                                 \
-          if (g.act == ACT_RELU) FWD_ROWS(ACT_RELU, HC, HC2);                \
-          else if (g.act == ACT_SOFTPLUS) FWD_ROWS(ACT_SOFTPLUS, HC, HC2);   \
-          else if (VAR && g.act == ACT_LEAKY) FWD_ROWS(ACT_LEAKY, HC, HC2);  \
-          else FWD_ROWS(ACT_NONE, HC, HC2);                                  \
+#define FWD_ROWS(ACT, HC, HC2, FULL) \
+        fwd_rows<F16, ACT, HC, HC2, FULL>(va, nz, nrows, pC, phC, g.ldc, c_op, pC2, phC2, g.ldc2, c2_op, g.sigma, hp.alpha, VAR && mul)
+#define FWD_ACT(HC, HC2, FULL)                                                     \
+        do {                                                                       \
+          if (g.act == ACT_RELU) FWD_ROWS(ACT_RELU, HC, HC2, FULL);                \
+          else if (g.act == ACT_SOFTPLUS) FWD_ROWS(ACT_SOFTPLUS, HC, HC2, FULL);   \
+          else if (VAR && g.act == ACT_LEAKY) FWD_ROWS(ACT_LEAKY, HC, HC2, FULL);  \
+          else FWD_ROWS(ACT_NONE, HC, HC2, FULL);                                  \
         } while (0)
-        if (g.C && g.C2) FWD_ACT(true, true);
-        else if (g.C) FWD_ACT(true, false);
-        else if (g.C2) FWD_ACT(false, true);
+#define FWD_OUT(FULL)                                                              \
+        do {                                                                       \
+          if (g.C && g.C2) FWD_ACT(true, true, FULL);                              \
+          else if (g.C) FWD_ACT(true, false, FULL);                                \
+          else if (g.C2) FWD_ACT(false, true, FULL);                               \
+        } while (0)
+        if (nrows >= 16) FWD_OUT(true); else FWD_OUT(false);
+#undef FWD_OUT
 #undef FWD_ACT
 #undef FWD_ROWS
       }
+#ifdef MRGAN_PHASE_TIMING
+      if (warp == 2 && lane == 0 && blockIdx.x == 0 && blockIdx.z == 0 && nchunks >= 10) {
+        const unsigned long long te2 = gtimer();
+        const unsigned long long b = pt[0];
+        printf("PTCH npk=%d: %llu+%llu %llu+%llu %llu+%llu %llu+%llu %llu+%llu %llu+%llu %llu+%llu %llu+%llu %llu+%llu %llu+%llu end=%llu\n", npk,
+               tch[0] - b, tch[1] - tch[0], tch[2] - b, tch[3] - tch[2], tch[4] - b, tch[5] - tch[4], tch[6] - b, tch[7] - tch[6], tch[8] - b, tch[9] - tch[8],
+               tch[10] - b, tch[11] - tch[10], tch[12] - b, tch[13] - tch[12], tch[14] - b, tch[15] - tch[14], tch[16] - b, tch[17] - tch[16],
+               tch[18] - b, tch[19] - tch[18], te2 - b);
+      }
+#endif
       // ---- reductions fused into this GEMM (the host selects them only for single-tile batches outside the DP mode) ----
       if (op.head == HEAD_DISC) {       // scratch: operand stage 0 (every MMA has retired); partial sums behind the logits
         float* const sl = reinterpret_cast<float*>(smem);
