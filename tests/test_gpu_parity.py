@@ -621,7 +621,7 @@ def test_data_parallel_mode_matches_single_gpu_large_batch():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for prec in ("fp32", "tf32"):
+    for prec in ("fp32", "tf32", "f16"):
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
                             "127.0.0.1", "--master-port", "29577", os.path.join(root, "tools", "dp_check.py"), "--precision", prec],
                            capture_output=True, text=True, timeout=600)
