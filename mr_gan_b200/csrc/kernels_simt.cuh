@@ -175,7 +175,9 @@ k_gemm_simt(const GemmDesc* __restrict__ descs, const FoldState* __restrict__ fo
 //   mode 1 (G step): rows [B,2B) unlabeled; rows [0,B) come from G
 //   mode 2 (mr_nn step): rows [0,n) labeled
 // from_stage: rows come from the step-API staging buffers instead of the resident fold.
-#define PREP_GROUPS 2       // 4-row noise groups per thread
+// PG: 4-row noise groups per thread: 2 at the reference batch (a fold's batch is ~100 rows, and 13 x 10 blocks per fold keep
+// the grid large enough), 4 in the large-batch regime.
+template <int PG>
 __global__ void __launch_bounds__(128)
 k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, int t, int B, int nrows,
        int noise_dim, float sigma_in, AdamHyper hp, OperandMode om) {
@@ -203,55 +205,81 @@ k_prep(FoldState* __restrict__ folds, int fold_base, int mode, int from_stage, i
   const int fold = fold_base + (int)blockIdx.z;
   // rows that this step assembles from the data set: mode 0 -> [0, 2B), mode 1 -> [B, 2B), mode 2 -> [0, nrows)
   const int r_lo = (mode == 1) ? B : 0, r_hi = (mode == 2) ? nrows : min(nrows, 2 * B);
-  // A thread assembles PREP_GROUPS row groups of 4 rows of one column: the gathers of all of them are issued first, then
-  // their Philox chains run interleaved (one chain per thread left this kernel latency-bound: 24 % of the large-batch step)
+  // A thread assembles PG row groups of 4 rows of one column: the gathers of all of them are issued first, then their
+  // Philox chains run interleaved in pairs (one chain per thread left this kernel latency-bound)
   const int rg = blockIdx.y;
   if (c < D) {
     // descriptor fields in registers: through the FoldState reference every use is a generic load that the stores to a0
     // force the compiler to repeat
     const float* const x_train = fs.x_train; const float* const stage_x = fs.stage_x;
+    const int* const idx0 = fs.idx[0]; const int* const idx1 = fs.idx[1]; const int* const idx2 = fs.idx[2];
     float* const a0 = fs.a0;
     const int ldx = fs.ldx, lda0 = fs.lda0;
     const uint32_t key0 = fs.key0, key1 = fs.key1;
-    float xv[PREP_GROUPS][4], nz[PREP_GROUPS][4];
-    bool live[PREP_GROUPS];
+    float xv[PG][4];
+    bool live[PG];
+    // Gathers: row numbers first, then the rows, for ALL rows of the thread at once and without a branch in front of any
+    // load (out-of-range rows are clamped onto a row this step does assemble and discarded at the store).  Behind per-row
+    // predicates the compiler issued "index load -> wait -> row load" pairs one after the other, so a thread paid the memory
+    // latency 8 times in a row: 51 % of this kernel's stall samples (profiles/r02_prep_ncu_before.txt).
+    const int blk_lo = rg * PG * 4;
+    const bool blk_live = blk_lo + PG * 4 > r_lo && blk_lo < r_hi;      // uniform per block
+    if (blk_live) {
+      int rix[PG][4];
+      if (from_stage) {
 #pragma unroll
-    for (int u = 0; u < PREP_GROUPS; ++u) {
-      const int g4 = (rg * PREP_GROUPS + u) * 4;
-      live[u] = g4 + 3 >= r_lo && g4 < r_hi;
+        for (int u = 0; u < PG; ++u)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = g4 + i;
-        xv[u][i] = 0.f;
-        if (!live[u] || r < r_lo || r >= r_hi) continue;
-        const int stream = (mode == 1) ? 2 : ((mode == 0 && r >= B) ? 1 : 0);
-        const int lr = (mode == 2) ? r : (r < B ? r : r - B);
-        const float* src = from_stage ? stage_x + (size_t)r * ldx : x_train + (size_t)__ldg(fs.idx[stream] + (size_t)t * B + lr) * ldx;
-        xv[u][i] = __ldg(src + c);
+          for (int i = 0; i < 4; ++i) rix[u][i] = min(max(blk_lo + 4 * u + i, r_lo), r_hi - 1);
+      } else {
+        const size_t tb = (size_t)t * B;
+#pragma unroll
+        for (int u = 0; u < PG; ++u)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = min(max(blk_lo + 4 * u + i, r_lo), r_hi - 1);
+            const int* const idx = (mode == 1) ? idx2 : ((mode == 0 && r >= B) ? idx1 : idx0);
+            const int lr = (mode == 2) ? r : (r < B ? r : r - B);
+            rix[u][i] = __ldg(idx + tb + lr);
+          }
       }
+      const float* const xsrc = (from_stage ? stage_x : x_train) + c;
+#pragma unroll
+      for (int u = 0; u < PG; ++u)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[u][i] = __ldg(xsrc + (size_t)rix[u][i] * ldx);
     }
 #pragma unroll
-    for (int u = 0; u < PREP_GROUPS; ++u) {
-      const int g4 = (rg * PREP_GROUPS + u) * 4;
-      if (!live[u]) continue;
-      if (aligned) normal4(key0, key1, (uint32_t)global_row(g4, hp, fold) >> 2, (uint32_t)c, step, 0u, nz[u]);
-      else for (int i = 0; i < 4; ++i) nz[u][i] = normal1(key0, key1, (uint32_t)global_row(g4 + i, hp, fold), (uint32_t)c, step, 0u);
+    for (int u = 0; u < PG; ++u) {
+      const int g4 = blk_lo + 4 * u;
+      live[u] = blk_live && g4 + 3 >= r_lo && g4 < r_hi;
     }
 #pragma unroll
-    for (int u = 0; u < PREP_GROUPS; ++u) {
-      const int g4 = (rg * PREP_GROUPS + u) * 4;
-      if (!live[u]) continue;
+    for (int u0 = 0; u0 < PG; u0 += 2) {
+      float nz[2][4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = g4 + i;
-        if (r < r_lo || r >= r_hi) continue;
-        put_operand(a0 + (size_t)r * lda0 + c, xv[u][i] + sigma_in * nz[u][i], om);
+      for (int v = 0; v < 2; ++v) {
+        const int g4 = (rg * PG + u0 + v) * 4;
+        if (!live[u0 + v]) continue;
+        if (aligned) normal4(key0, key1, (uint32_t)global_row(g4, hp, fold) >> 2, (uint32_t)c, step, 0u, nz[v]);
+        else for (int i = 0; i < 4; ++i) nz[v][i] = normal1(key0, key1, (uint32_t)global_row(g4 + i, hp, fold), (uint32_t)c, step, 0u);
+      }
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        const int g4 = (rg * PG + u0 + v) * 4;
+        if (!live[u0 + v]) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = g4 + i;
+          if (r < r_lo || r >= r_hi) continue;
+          put_operand(a0 + (size_t)r * lda0 + c, xv[u0 + v][i] + sigma_in * nz[v][i], om);
+        }
       }
     }
   }
   if (mode != 2 && c < noise_dim) {       // generator input z (mr_gan.py:206,212)
-    for (int u = 0; u < PREP_GROUPS; ++u) {
-      const int g4 = (rg * PREP_GROUPS + u) * 4;
+    for (int u = 0; u < PG; ++u) {
+      const int g4 = (rg * PG + u) * 4;
       if (g4 >= B) break;
       float nz[4] = {0.f, 0.f, 0.f, 0.f};
       if (!from_stage) {
@@ -354,6 +382,7 @@ __global__ void __launch_bounds__(1024) k_bn_bwd(const BnDesc* __restrict__ desc
 }
 
 // ------------------------------------------------------------------ loss heads
+#define LOSS_MAX_BLOCKS 64
 struct LossDesc {
   const float* logits; float* dlogits; int ld;   // [rows, ld]
   const int* labels;
@@ -362,15 +391,18 @@ struct LossDesc {
 
 // Salimans-style supervised + unsupervised losses on the stacked logits
 // (mr_gan.py:146-149,161) and their gradients.
+// gridDim.x == 1 at the reference batch.  In the large-batch regime the 3B rows are spread over gridDim.x blocks (one block
+// walked 24 576 rows in 184 us); each block leaves its three partial sums in `part` ([fold][block][4]) and the last one to
+// arrive (`ctr[fold]`) adds them in block order, so the statistics stay reproducible.
 __global__ void __launch_bounds__(256)
 k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, int fold_base, int nf_total,
-            int t, int B, int K, float w_unl, OperandMode om, int Bg) {
+            int t, int B, int K, float w_unl, OperandMode om, int Bg, float* __restrict__ part, unsigned* __restrict__ ctr) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sh[32];
   const LossDesc d = descs[blockIdx.z];   // B rows per section on this rank, Bg in the global batch (means are over Bg)
   float s_lab = 0.f, s_unl = 0.f, s_err = 0.f;
-  for (int r = threadIdx.x; r < 3 * B; r += blockDim.x) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < 3 * B; r += blockDim.x * gridDim.x) {
     const float* l = d.logits + (size_t)r * d.ld;
     float mx = l[0]; int am = 0;
     for (int k = 1; k < K; ++k) if (l[k] > mx) { mx = l[k]; am = k; }
@@ -401,9 +433,23 @@ k_loss_disc(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, 
   s_lab = block_sum(s_lab, sh);
   s_unl = block_sum(s_unl, sh);
   s_err = block_sum(s_err, sh);
+  float* const st = step_stats + ((size_t)t * nf_total + fold_base + blockIdx.z) * 4;
+  if (gridDim.x == 1) {
+    if (threadIdx.x == 0) { st[0] = s_lab / Bg; st[1] = s_unl / Bg; st[2] = s_err / Bg; }
+    return;
+  }
+  float* const pf = part + (size_t)(fold_base + blockIdx.z) * 4 * LOSS_MAX_BLOCKS;
   if (threadIdx.x == 0) {
-    float* st = step_stats + ((size_t)t * nf_total + fold_base + blockIdx.z) * 4;
-    st[0] = s_lab / Bg; st[1] = s_unl / Bg; st[2] = s_err / Bg;
+    pf[4 * blockIdx.x] = s_lab; pf[4 * blockIdx.x + 1] = s_unl; pf[4 * blockIdx.x + 2] = s_err;
+    __threadfence();
+    const unsigned n = atomicAdd(ctr + fold_base + blockIdx.z, 1u);
+    if (n == gridDim.x - 1) {
+      ctr[fold_base + blockIdx.z] = 0u;
+      __threadfence();
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      for (unsigned b = 0; b < gridDim.x; ++b) { a0 += __ldcg(pf + 4 * b); a1 += __ldcg(pf + 4 * b + 1); a2 += __ldcg(pf + 4 * b + 2); }
+      st[0] = a0 / Bg; st[1] = a1 / Bg; st[2] = a2 / Bg;
+    }
   }
 }
 
@@ -480,22 +526,71 @@ k_loss_mse(const LossDesc* __restrict__ descs, float* __restrict__ step_stats, i
 // In the data-parallel mode the batch statistics that the reference takes over the whole batch (BatchNorm mean /
 // variance mr_gan.py:112, feature-matching means mr_gan.py:152-153) are summed locally, all-reduced over NVLink,
 // and applied by a second kernel, so that W ranks compute exactly the single-GPU large-batch step.
-struct DpBufs { float* bnf; float* bnb; float* fm; };   // per fold: [2*W] sums each (W = 500 / 500 / 250)
+// part / ctr: scratch of the row-parallel statistics kernels -- SPLIT_MAX_Y row chunks x 2 x 512 partial sums per fold, and
+// one arrival counter per column block (the last block to arrive adds the chunks IN CHUNK ORDER and resets the counter,
+// so the sums are reproducible and the kernels replay inside a CUDA graph).
+struct DpBufs { float* bnf; float* bnb; float* fm; float* part; unsigned* ctr; };   // per fold: [2*W] sums each (W = 500 / 500 / 250)
+#define SPLIT_MAX_Y 32
+#define SPLIT_PART_W 512
 
+// Publishes this block's partial sums (already written by its slice-0 threads) and tells whether it is the last of the
+// gridDim.y row-chunk blocks of its column block to do so.  Block-uniform result.
+__device__ __forceinline__ bool split_last_block(unsigned* ctr) {
+  __shared__ int last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned n = atomicAdd(ctr, 1u);
+    last = (n == gridDim.y - 1);
+    if (last) *ctr = 0u;
+  }
+  __syncthreads();
+  if (last) __threadfence();
+  return last != 0;
+}
+
+// Column sums of two quantities over this block's row chunk -> out[j], out[W + j] (gridDim.y == 1) or, with several row
+// chunks, the chunk's partial; the last block adds the partials in chunk order.  `red` = [2][slices][32] shared floats.
+__device__ __forceinline__ void split_reduce(float a, float b, float (*red)[BN_MAX_SLICES][BN_COLS], int W, const DpBufs& bf, float* out,
+                                             float* out2a, float* out2b, float scale2) {
+  const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
+  const int j = blockIdx.x * BN_COLS + cx;
+  red[0][sl][cx] = a; red[1][sl][cx] = b;
+  __syncthreads();
+  if (sl == 0 && j < W) {
+    a = 0.f; b = 0.f;
+    for (int i = 0; i < nsl; ++i) { a += red[0][i][cx]; b += red[1][i][cx]; }
+    if (gridDim.y == 1) {
+      out[j] = a; out[W + j] = b;
+      if (out2a) { out2a[j] = a * scale2; out2b[j] = b * scale2; }
+    } else {
+      float* p = bf.part + (size_t)blockIdx.y * 2 * SPLIT_PART_W;
+      p[j] = a; p[SPLIT_PART_W + j] = b;
+    }
+  }
+  if (gridDim.y == 1) return;
+  if (!split_last_block(bf.ctr + blockIdx.x)) return;
+  if (sl == 0 && j < W) {
+    a = 0.f; b = 0.f;
+    for (unsigned y = 0; y < gridDim.y; ++y) {
+      const float* p = bf.part + (size_t)y * 2 * SPLIT_PART_W;
+      a += __ldcg(p + j); b += __ldcg(p + SPLIT_PART_W + j);
+    }
+    out[j] = a; out[W + j] = b;
+    if (out2a) { out2a[j] = a * scale2; out2b[j] = b * scale2; }
+  }
+}
+
+// grid = (column blocks of 32, row chunks, folds); block = 32 columns x (blockDim.x / 32) row slices.  Rows of a block:
+// r = blockIdx.y * slices + slice, stepping by slices * gridDim.y.
 __global__ void __launch_bounds__(1024) k_bn_stats(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs) {
   __shared__ float red[2][BN_MAX_SLICES][BN_COLS];
   const BnDesc d = descs[blockIdx.z];
   const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
   const int j = blockIdx.x * BN_COLS + cx;
   float s = 0.f, q = 0.f;
-  if (j < d.W) for (int r = sl; r < d.B; r += nsl) { const float x = d.h1[(size_t)r * d.ld + j]; s += x; q = fmaf(x, x, q); }
-  red[0][sl][cx] = s; red[1][sl][cx] = q;
-  __syncthreads();
-  if (sl == 0 && j < d.W) {
-    s = 0.f; q = 0.f;
-    for (int i = 0; i < nsl; ++i) { s += red[0][i][cx]; q += red[1][i][cx]; }
-    bufs[blockIdx.z].bnf[j] = s; bufs[blockIdx.z].bnf[d.W + j] = q;
-  }
+  if (j < d.W) for (int r = blockIdx.y * nsl + sl; r < d.B; r += nsl * gridDim.y) { const float x = d.h1[(size_t)r * d.ld + j]; s += x; q = fmaf(x, x, q); }
+  split_reduce(s, q, red, d.W, bufs[blockIdx.z], bufs[blockIdx.z].bnf, nullptr, nullptr, 0.f);
 }
 
 __global__ void __launch_bounds__(1024) k_bn_apply(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs,
@@ -507,9 +602,9 @@ __global__ void __launch_bounds__(1024) k_bn_apply(const BnDesc* __restrict__ de
   const float mu = bufs[blockIdx.z].bnf[j] / Bg;
   const float var = fmaxf(bufs[blockIdx.z].bnf[d.W + j] / Bg - mu * mu, 0.f);
   const float istd = rsqrtf(var + eps);
-  if (sl == 0) d.istd[j] = istd;
+  if (sl == 0 && blockIdx.y == 0) d.istd[j] = istd;
   const float g = d.gamma[j], b = d.beta[j];
-  for (int r = sl; r < d.B; r += nsl) {
+  for (int r = blockIdx.y * nsl + sl; r < d.B; r += nsl * gridDim.y) {
     const float xh = (d.h1[(size_t)r * d.ld + j] - mu) * istd;
     d.xhat[(size_t)r * d.ld + j] = xh;
     const float u = fmaf(g, xh, b);
@@ -525,16 +620,10 @@ __global__ void __launch_bounds__(1024) k_bn_bwd_stats(const BnDesc* __restrict_
   const int j = blockIdx.x * BN_COLS + cx;
   const float ginv = (om.mode == 2) ? 1.0f / om.gscale : 1.0f;
   float s1 = 0.f, s2 = 0.f;
-  if (j < d.W) for (int r = sl; r < d.B; r += nsl) { const float du = d.du[(size_t)r * d.ld + j] * ginv; s1 += du; s2 = fmaf(du, d.xhat[(size_t)r * d.ld + j], s2); }
-  red[0][sl][cx] = s1; red[1][sl][cx] = s2;
-  __syncthreads();
-  if (sl == 0 && j < d.W) {
-    s1 = 0.f; s2 = 0.f;
-    for (int i = 0; i < nsl; ++i) { s1 += red[0][i][cx]; s2 += red[1][i][cx]; }
-    const float gs = (om.mode == 2) ? om.gscale : 1.0f;
-    d.g_gamma[j] = s2 * gs; d.g_beta[j] = s1 * gs;        // LOCAL partial gradients: the flat gradient all-reduce completes them
-    bufs[blockIdx.z].bnb[j] = s1; bufs[blockIdx.z].bnb[d.W + j] = s2;
-  }
+  if (j < d.W) for (int r = blockIdx.y * nsl + sl; r < d.B; r += nsl * gridDim.y) { const float du = d.du[(size_t)r * d.ld + j] * ginv; s1 += du; s2 = fmaf(du, d.xhat[(size_t)r * d.ld + j], s2); }
+  // bnb = [s1 | s2]; the LOCAL partial gradients g_beta = s1, g_gamma = s2 (times the loss scale of the gradient buffer):
+  // the flat gradient all-reduce completes them
+  split_reduce(s1, s2, red, d.W, bufs[blockIdx.z], bufs[blockIdx.z].bnb, d.g_beta, d.g_gamma, (om.mode == 2) ? om.gscale : 1.0f);
 }
 
 __global__ void __launch_bounds__(1024) k_bn_bwd_apply(const BnDesc* __restrict__ descs, const DpBufs* __restrict__ bufs,
@@ -546,7 +635,7 @@ __global__ void __launch_bounds__(1024) k_bn_bwd_apply(const BnDesc* __restrict_
   const float s1 = bufs[blockIdx.z].bnb[j], s2 = bufs[blockIdx.z].bnb[d.W + j];
   const float g = d.gamma[j], istd = d.istd[j], invB = 1.0f / Bg;
   const float ginv = (om.mode == 2) ? 1.0f / om.gscale : 1.0f;
-  for (int r = sl; r < d.B; r += nsl) {
+  for (int r = blockIdx.y * nsl + sl; r < d.B; r += nsl * gridDim.y) {
     const float xh = d.xhat[(size_t)r * d.ld + j];
     const float dxh = d.du[(size_t)r * d.ld + j] * ginv * g;
     const float dh1 = istd * (dxh - invB * g * s1 - xh * invB * g * s2);
@@ -555,21 +644,14 @@ __global__ void __launch_bounds__(1024) k_bn_bwd_apply(const BnDesc* __restrict_
   }
 }
 
-// grid.x = column blocks of 32; block = 32 columns x (blockDim.x / 32) row slices
 __global__ void __launch_bounds__(1024) k_fm_stats(const LossDesc* __restrict__ descs, const DpBufs* __restrict__ bufs, int B) {
   __shared__ float red[2][BN_MAX_SLICES][BN_COLS];
   const LossDesc d = descs[blockIdx.z];
   const int nsl = blockDim.x / BN_COLS, cx = threadIdx.x & (BN_COLS - 1), sl = threadIdx.x / BN_COLS;
   const int j = blockIdx.x * BN_COLS + cx;
   float mg = 0.f, mr = 0.f;
-  if (j < d.Wmid) for (int r = sl; r < B; r += nsl) { mg += d.mid[(size_t)r * d.ldmid + j]; mr += d.mid[(size_t)(r + B) * d.ldmid + j]; }
-  red[0][sl][cx] = mg; red[1][sl][cx] = mr;
-  __syncthreads();
-  if (sl == 0 && j < d.Wmid) {
-    mg = 0.f; mr = 0.f;
-    for (int i = 0; i < nsl; ++i) { mg += red[0][i][cx]; mr += red[1][i][cx]; }
-    bufs[blockIdx.z].fm[j] = mg; bufs[blockIdx.z].fm[d.Wmid + j] = mr;
-  }
+  if (j < d.Wmid) for (int r = blockIdx.y * nsl + sl; r < B; r += nsl * gridDim.y) { mg += d.mid[(size_t)r * d.ldmid + j]; mr += d.mid[(size_t)(r + B) * d.ldmid + j]; }
+  split_reduce(mg, mr, red, d.Wmid, bufs[blockIdx.z], bufs[blockIdx.z].fm, nullptr, nullptr, 0.f);
 }
 
 __global__ void __launch_bounds__(1024)
@@ -582,11 +664,11 @@ k_fm_apply(const LossDesc* __restrict__ descs, const DpBufs* __restrict__ bufs, 
   if (j < d.Wmid) {
     const float diff = (bufs[blockIdx.z].fm[j] - bufs[blockIdx.z].fm[d.Wmid + j]) / Bg;
     const float g = 2.0f * diff / ((float)d.Wmid * Bg);
-    for (int r = sl; r < B; r += nsl)
+    for (int r = blockIdx.y * nsl + sl; r < B; r += nsl * gridDim.y)
       put_grad_operand(d.dmid + (size_t)r * d.lddmid + j, (d.mid[(size_t)r * d.ldmid + j] > 0.f) ? g : alpha * g, om);
   }
-  if (blockIdx.x == 0) {      // the loss itself: every rank holds the same global value; the statistics block is summed over ranks
-    float s = 0.f;            // afterwards, so 1/world of it is stored
+  if (blockIdx.x == 0 && blockIdx.y == 0) {   // the loss itself: every rank holds the same global value; the statistics block is
+    float s = 0.f;                            // summed over ranks afterwards, so 1/world of it is stored
     for (int c = threadIdx.x; c < d.Wmid; c += blockDim.x) {
       const float diff = (bufs[blockIdx.z].fm[c] - bufs[blockIdx.z].fm[d.Wmid + c]) / Bg;
       s = fmaf(diff, diff, s);

@@ -136,6 +136,7 @@ struct mrgan_handle {
   void* nccl_comm = nullptr;
   float* d_dpmem = nullptr; DpBufs* d_dpbufs = nullptr;
   float *dp_bnf = nullptr, *dp_bnb = nullptr, *dp_fm = nullptr;   // [nf][2*500], [nf][2*500], [nf][2*250]
+  float* dp_losspart = nullptr; unsigned* dp_lossctr = nullptr;    // k_loss_disc block partials [nf][4*64] and arrival counters [nf]
 #ifdef MRGAN_WITH_TC
   TcOp* d_tcops = nullptr;            // [NUM_OPS][nf] tensor maps + epilogue descriptors
   int tc_bn[NUM_OPS] = {0}, tc_maxME[NUM_OPS] = {0}, tc_maxNE[NUM_OPS] = {0};
@@ -601,15 +602,31 @@ void dp_update(mrgan_handle* h, int f0, int nfl, int net) {
 int alloc_split_bufs(mrgan_handle* h) {
   if (h->d_dpbufs) return MRGAN_OK;
   const int nf = h->nf;
-  const size_t per = 2 * kGH + 2 * kGH + 2 * kDW[4];
+  // per fold: the three statistics blocks, the row-chunk partials of the statistics kernels, the block partials of
+  // k_loss_disc, and the arrival counters (16 column blocks + 1 for the loss kernel, as 32 words)
+  const size_t stats = 2 * kGH + 2 * kGH + 2 * kDW[4];
+  const size_t per = stats + (size_t)SPLIT_MAX_Y * 2 * SPLIT_PART_W + 4 * LOSS_MAX_BLOCKS + 32;
   CK(cudaMalloc(&h->d_dpmem, per * nf * sizeof(float)));
   CK(cudaMemset(h->d_dpmem, 0, per * nf * sizeof(float)));
   h->dp_bnf = h->d_dpmem; h->dp_bnb = h->dp_bnf + (size_t)nf * 2 * kGH; h->dp_fm = h->dp_bnb + (size_t)nf * 2 * kGH;
+  float* const part = h->dp_fm + (size_t)nf * 2 * kDW[4];
+  h->dp_losspart = part + (size_t)nf * SPLIT_MAX_Y * 2 * SPLIT_PART_W;
+  unsigned* const ctr = reinterpret_cast<unsigned*>(h->dp_losspart + (size_t)nf * 4 * LOSS_MAX_BLOCKS);
+  h->dp_lossctr = ctr + (size_t)nf * 16;
   std::vector<DpBufs> bufs(nf);
-  for (int f = 0; f < nf; ++f) bufs[f] = DpBufs{h->dp_bnf + (size_t)f * 2 * kGH, h->dp_bnb + (size_t)f * 2 * kGH, h->dp_fm + (size_t)f * 2 * kDW[4]};
+  for (int f = 0; f < nf; ++f)
+    bufs[f] = DpBufs{h->dp_bnf + (size_t)f * 2 * kGH, h->dp_bnb + (size_t)f * 2 * kGH, h->dp_fm + (size_t)f * 2 * kDW[4],
+                     part + (size_t)f * SPLIT_MAX_Y * 2 * SPLIT_PART_W, ctr + (size_t)f * 16};
   CK(cudaMalloc(&h->d_dpbufs, nf * sizeof(DpBufs)));
   CK(cudaMemcpy(h->d_dpbufs, bufs.data(), nf * sizeof(DpBufs), cudaMemcpyHostToDevice));
   return MRGAN_OK;
+}
+
+// Row chunks (grid.y) of the split statistics / apply kernels: one chunk per 256 rows (8 rows per thread of a 1024-thread
+// block), so that a large batch spreads over the chip instead of 8 - 16 CTAs.
+int split_chunks(int rows) {
+  const int y = (rows + 255) / 256;
+  return y < 1 ? 1 : (y > SPLIT_MAX_Y ? SPLIT_MAX_Y : y);
 }
 
 // ------------------------------------------------------------------ launch sequences
@@ -654,9 +671,14 @@ void launch_prep(mrgan_handle* h, int f0, int nfl, int mode, int from_stage, int
   const mrgan_config& c = h->cfg;
   int cols = max_D(h, f0, nfl);
   if (c.noise_dim > cols) cols = c.noise_dim;
-  dim3 grid((cols + 127) / 128, (nrows + 4 * PREP_GROUPS - 1) / (4 * PREP_GROUPS), nfl);
-  launch_k(h, k_prep, grid, dim3(128), 0, h->stream, h->d_folds, f0, mode, from_stage, t, c.batch, nrows, c.noise_dim, c.sigma_in, h->hp,
-           h->om);
+  // rows per thread: 8 at the reference batch, 16 in the large-batch regime (kernels_simt.cuh: k_prep; 8 / 16 / 32 rows per
+  // thread measured the same once the gathers were batched: 224 / 227 / 227 step pairs/s at D = 12032, B = 8192)
+  const int pg = nrows > 512 ? 4 : 2;
+  dim3 grid((cols + 127) / 128, (nrows + 4 * pg - 1) / (4 * pg), nfl);
+#define LAUNCH_PREP(PG) launch_k(h, k_prep<PG>, grid, dim3(128), 0, h->stream, h->d_folds, f0, mode, from_stage, t, c.batch, nrows, c.noise_dim, \
+                                 c.sigma_in, h->hp, h->om)
+  if (pg == 4) LAUNCH_PREP(4); else LAUNCH_PREP(2);
+#undef LAUNCH_PREP
 }
 
 void launch_adam(mrgan_handle* h, int f0, int nfl, int net, bool counters_only) {
@@ -698,7 +720,7 @@ void enqueue_gen_fwd(mrgan_handle* h, int f0, int nfl, int op_g3) {
     launch_gemm(h, op_g3, f0, nfl, 0);
     return;
   }
-  const dim3 bnf((kGH + BN_COLS - 1) / BN_COLS, 1, nfl);
+  const dim3 bnf((kGH + BN_COLS - 1) / BN_COLS, h->d_dpbufs ? split_chunks(h->cfg.batch) : 1, nfl);
   const dim3 bnt(h->cfg.batch > 256 ? 1024 : 256);     // 32 columns x 8 (reference batch) or 32 (large batch) row slices
   const OperandMode tf32 = h->om;
   if (h->d_dpbufs) {          // batch statistics over the GLOBAL batch: local sums -> NVLink all-reduce -> apply
@@ -722,9 +744,13 @@ void enqueue_disc_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) 
   launch_prep(h, f0, nfl, 0, from_stage, t, 2 * B);
   enqueue_gen_fwd(h, f0, nfl, OP_G3D);
   for (int l = 0; l < 6; ++l) launch_gemm(h, OP_D1 + l, f0, nfl, 0);
-  if (!heads)        // otherwise the logit layer's epilogue computed the losses, their gradients and advanced the counters
-    launch_k(h, k_loss_disc, dim3(1, 1, nfl), dim3(256), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, B,
-             c.n_classes, c.unlabeled_weight, h->om, h->hp.dp_bg);
+  if (!heads) {      // otherwise the logit layer's epilogue computed the losses, their gradients and advanced the counters
+    // large batch: the 3B rows spread over up to 64 blocks (needs the split scratch for the ordered partial sums)
+    int lb = h->dp_losspart ? (3 * B + 511) / 512 : 1;
+    lb = lb < 1 ? 1 : (lb > LOSS_MAX_BLOCKS ? LOSS_MAX_BLOCKS : lb);
+    launch_k(h, k_loss_disc, dim3(lb, 1, nfl), dim3(256), 0, h->stream, (const LossDesc*)(h->d_loss + f0), h->d_step_stats, f0, h->nf, t, B,
+             c.n_classes, c.unlabeled_weight, h->om, h->hp.dp_bg, h->dp_losspart, h->dp_lossctr);
+  }
 #ifdef MRGAN_WITH_TC
   const bool merge = tc_dw_merge(h);
 #else
@@ -756,7 +782,7 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
   if (deferred_join(h)) join_side(h);          // discriminator weights updated by the D step's dW+Adam kernels
   for (int l = 0; l < 5; ++l) launch_gemm(h, OP_D1G + l, f0, nfl, 0);
   if (h->d_dpbufs) {
-    const dim3 fmg((kDW[4] + BN_COLS - 1) / BN_COLS, 1, nfl), fmt(B > 256 ? 1024 : 256);
+    const dim3 fmg((kDW[4] + BN_COLS - 1) / BN_COLS, split_chunks(B), nfl), fmt(B > 256 ? 1024 : 256);
     k_fm_stats<<<fmg, fmt, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, B);
     dp_allreduce(h, h->dp_fm + (size_t)f0 * 2 * kDW[4], (size_t)nfl * 2 * kDW[4]);
     k_fm_apply<<<fmg, fmt, 0, h->stream>>>(h->d_loss + f0, h->d_dpbufs + f0, h->d_step_stats, f0, h->nf, t, B,
@@ -781,7 +807,7 @@ void enqueue_gen_step(mrgan_handle* h, int f0, int nfl, int t, int from_stage) {
     fork_side(h);
     launch_gemm(h, OP_GW2, f0, nfl, 0, h->side);
   }
-  const dim3 bng((kGH + BN_COLS - 1) / BN_COLS, 1, nfl), bnt(B > 256 ? 1024 : 256);
+  const dim3 bng((kGH + BN_COLS - 1) / BN_COLS, h->d_dpbufs ? split_chunks(B) : 1, nfl), bnt(B > 256 ? 1024 : 256);
   if (h->d_dpbufs) {
     k_bn_bwd_stats<<<bng, bnt, 0, h->stream>>>(h->d_bn + f0, h->d_dpbufs + f0, h->om);
     dp_allreduce(h, h->dp_bnb + (size_t)f0 * 2 * kGH, (size_t)nfl * 2 * kGH);
