@@ -105,6 +105,12 @@ __device__ __forceinline__ float sqrt_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Box-Muller on the four words of one Philox output: the 4 normals of rows 4*rowgroup .. 4*rowgroup+3
 __device__ __forceinline__ void box_muller4(const uint4 x, float out[4]) {
   const float s = 1.1920928955078125e-07f;   // 2^-23
@@ -112,7 +118,8 @@ __device__ __forceinline__ void box_muller4(const uint4 x, float out[4]) {
   const float u1b = ((float)(x.z >> 9) + 0.5f) * s, u2b = ((float)(x.w >> 9) + 0.5f) * s;
   // fast-math intrinsics: |error| of a normal <= ~3e-6 (lg2.approx / sin.approx / cos.approx on [-pi, pi], sqrt.approx), far
   // below the 1e-3 loss tolerance; the epilogue warps generate ~800k normals per fold and step pair
-  const float ra = sqrt_approx(-2.0f * __logf(u1a)), rb = sqrt_approx(-2.0f * __logf(u1b));
+  // ln u = lg2.approx(u) * ln 2: what __logf computes, minus its subnormal-input handling (u >= 2^-24 here) -- same bits
+  const float ra = sqrt_approx(-2.0f * (lg2_approx(u1a) * 0.693147182464599609375f)), rb = sqrt_approx(-2.0f * (lg2_approx(u1b) * 0.693147182464599609375f));
   const float pi = 3.14159265358979323846f;
   const float ta = pi * (2.0f * u2a - 1.0f), tb = pi * (2.0f * u2b - 1.0f);
   const float sa = __sinf(ta), ca = __cosf(ta), sb = __sinf(tb), cb = __cosf(tb);

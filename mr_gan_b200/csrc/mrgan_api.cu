@@ -1316,7 +1316,7 @@ bool tc_launch_gemm(mrgan_handle* h, int op, int f0, int nfl, int rows_override,
       TC_LAUNCH(h, f16, K_TC_DW_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, ks, h->hp, h->om);
       if (ks > 1) {
         const int n4 = h->tc_maxNE[op] * pitch8(h->tc_maxME[op]) / 4;
-        launch_k(h, k_splitk_reduce, dim3(std::min((n4 + 255) / 256, 64), nfl, 1), dim3(256), 0, st, d, ks);
+        launch_k(h, k_splitk_reduce, dim3(std::min((n4 + 255) / 256, 1184), nfl, 1), dim3(256), 0, st, d, ks);
       }
     } else if (!oi.bt) TC_LAUNCH(h, f16, K_TC_FWD_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
     else TC_LAUNCH(h, f16, K_TC_DX_BIG, grid, dim3(TC_FWD_THREADS), smem, st, d, h->d_folds, rows_override, h->hp, h->om);
