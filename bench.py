@@ -331,7 +331,7 @@ def run_table1(args, rank, world, local, barrier):
         j['job_id'] = i
     t_data = time.perf_counter() - t0
     errors = sweep.run_sharded(jobs, lambda js, dev: mg.train_gan_folds(js, epochs=args.epochs, seed=seed, precision=args.precision, device=dev),
-                               group_size=args.group, key=mg.job_rows, cost=mg.job_width, init_dist=False)
+                               group_size=args.group, key=mg.job_rows, cost=mg.job_cost, init_dist=False)
     barrier()
     wall = time.perf_counter() - t0
     pairs = sum((mg.job_rows(j)[0] // 50) * args.epochs for j in jobs)

@@ -173,6 +173,12 @@ def job_width(j):
     return j['X'].shape[1] if 'train_idx' in j else j['trainTestSets'][0].shape[1]
 
 
+def job_cost(j):
+    """Relative cost of a fold-training for the scheduler: the step is HBM-bound on the optimizer traffic, 28 bytes per
+    parameter of N_D + N_G = 1501 D + 1 055 756, i.e. ~ (D + 703) per step pair, times the pairs per epoch."""
+    return (job_width(j) + 703.0) * max(job_rows(j)[0] // 50, 1)
+
+
 def main(argv=None):
     parser = argparse.ArgumentParser(description='Semi-supervised learning with GANs for material recognition on haptic data.')
     parser.add_argument('-t', '--tables', nargs='+', help='[Required] Tables to recompute', required=True)
@@ -200,7 +206,7 @@ def main(argv=None):
         res = sweep.run_sharded(
             jobs, lambda js, dev: train_gan_folds(js, epochs=args.epochs, verbose=args.verbose, seed=seed,
                                                   precision=args.precision, device=dev, device_perm=not args.host_perm),
-            group_size=args.group, key=job_rows, cost=job_width)
+            group_size=args.group, key=job_rows, cost=job_cost)
         return res
 
     def report(errors, label='Average error:'):

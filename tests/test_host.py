@@ -90,6 +90,30 @@ def test_sweep_grouping_and_assignment():
     assert res == [2 * j['D'] for j in jobs]
 
 
+def test_sweep_plan_deals_folds_by_cost_over_ranks():
+    """Table 1 on 8 GPUs: 7 modalities x 42 folds of widths 400..3632 (mr_gan.py:49-62,248-258).  Every fold is trained
+    exactly once, groups share (n_train, n_test), and no rank carries more than 1 % above the mean cost -- dealing whole
+    one-modality groups left one GPU idle and the widest modality alone on another."""
+    widths = [800, 400, 1200, 2432, 2832, 3632, 3232]
+    jobs = [dict(D=widths[m], n=6000 if m != 3 else 7100) for m in range(7) for _ in range(42)]
+    cost = lambda j: (j['D'] + 703.0) * (j['n'] // 50)
+    for world in (1, 2, 4, 8):
+        pl = sweep.plan(jobs, world, 42, key=lambda j: j['n'], cost=cost)
+        seen = sorted(i for r in pl for g in pl[r] for i in g)
+        assert seen == list(range(len(jobs)))
+        assert all(len(g) <= 42 and len({jobs[i]['n'] for i in g}) == 1 for r in pl for g in pl[r])
+        if world > 1:
+            loads = [sum(cost(jobs[i]) for g in pl[r] for i in g) for r in range(world)]
+            assert max(loads) <= 1.01 * sum(loads) / world, loads
+    one = sweep.plan(jobs, 1, 42, key=lambda j: j['n'], cost=cost)[0]
+    assert one == sweep.make_groups(jobs, 42, key=lambda j: j['n'])        # one GPU: the reference's loop order, cut into groups
+    # inside a mixed group the concurrent fold chains (contiguous quarters of the group) carry equal cost
+    g = sweep.plan(jobs, 8, 42, key=lambda j: j['n'], cost=cost)[0][0]
+    nch = sweep.chain_count(len(g))
+    q = [sum(cost(jobs[i]) for i in g[len(g) * ch // nch:len(g) * (ch + 1) // nch]) for ch in range(nch)]
+    assert nch == 4 and max(q) <= 1.15 * min(q), q
+
+
 def test_dataset_raises_without_the_pickles_unless_synthetic_is_requested(tmp_path):
     """The reference's dataset() raises IOError on a missing pickle (mr_gan.py:33 open()); so does the drop-in.  Synthetic
     data is opt-in: a wrong --data-dir must not print plausible tables from made-up data."""
