@@ -14,12 +14,21 @@ python tools/update_traffic.py /tmp/dw.ncu-rep f16 74 1200 profiles/r02_f16_dw1_
 cp profiles/ncu_traffic.json gpurun_out/ncu_traffic.json
 L=$(python -c "import json; print(json.load(open('profiles/ncu_traffic.json'))['dw1/f16']['launch_in_report'])")
 python profiles/extract_ncu.py /tmp/dw.ncu-rep $L > gpurun_out/r02_f16_dw1_ncu_full.txt 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc -c 12 -o /tmp/g $CMD > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc -c 16 -o /tmp/g $CMD > /dev/null 2>&1
 ncu -i /tmp/g.ncu-rep --page raw --csv 2>/dev/null | python -c "
 import csv,sys
 rows=list(csv.reader(sys.stdin)); h=rows[0]; ix={k:i for i,k in enumerate(h)}
-for n,r in enumerate(rows[2:]): print(n, r[ix['Kernel Name']][:60], r[ix['Grid Size']], r[ix['gpu__time_duration.sum']])
-" > gpurun_out/r02_gemm_launch_index.txt
+fwd=dx=None
+for n,r in enumerate(rows[2:]):
+    name, grid = r[ix['Kernel Name']], r[ix['Grid Size']].replace(' ','')
+    print('#', n, name[:48], grid, r[ix['gpu__time_duration.sum']], file=sys.stderr)
+    if grid == '(4,1,74)' and 'k_gemm_tc<1, 0' in name and fwd is None: fwd = n
+    if grid == '(4,1,74)' and 'k_gemm_tc<0, 0' in name and dx is None: dx = n
+print(fwd if fwd is not None else -1, dx if dx is not None else -1)
+" > gpurun_out/r02_gemm_idx.txt 2> gpurun_out/r02_gemm_launch_index.txt
+read FWD DX < gpurun_out/r02_gemm_idx.txt
+[ "$FWD" -ge 0 ] && python profiles/extract_ncu.py /tmp/g.ncu-rep $FWD > gpurun_out/r02_f16_fwd1_ncu_full.txt 2>&1
+[ "$DX" -ge 0 ] && python profiles/extract_ncu.py /tmp/g.ncu-rep $DX > gpurun_out/r02_f16_dx2_ncu_full.txt 2>&1
 unset MRGAN_CHAINS
 cat gpurun_out/r02_gputests_1gpu.log; tail -2 gpurun_out/r02_smoke.log; cat gpurun_out/r02_traffic.log
 cut -c1-160 gpurun_out/r02_bench_1gpu.json gpurun_out/r02_bench_dp_1gpu.json
