@@ -6,8 +6,9 @@ The reference calls librosa 0.5.1 for the contact-microphone features (mr_gan.py
 available here, so the two functions are restated in numpy from librosa's published definitions
 (centered STFT, n_fft=2048, hop=512, periodic Hann window, power spectrogram, Slaney mel scale with
 area-normalised triangular filters, 10*log10 relative to the maximum, floor at -80 dB).  The MREO files are
-not distributed with the reference, so this path is covered by format / property tests only
-(tests/test_host.py) -- NOT verified against librosa output."""
+not distributed with the reference, so this path is covered by format / property tests and pinned piecewise against
+independent implementations (tests/test_host.py: the STFT against scipy.signal.stft to 1e-10, the mel scale against Slaney's
+landmarks, the filters against their definition) -- NOT verified against librosa output itself."""
 import os
 import pickle
 import sys

@@ -199,6 +199,37 @@ def test_product_never_imports_the_oracle():
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
 
 
+def test_logmel_front_end_against_scipy_stft_and_slaney_landmarks():
+    """librosa is absent, so the restated front end (mr_gan.py:45-47) is pinned piecewise: the framing / window / FFT against
+    scipy.signal.stft (an independent implementation; centred frames = reflect padding, periodic Hann, hop 512), the mel
+    scale against Slaney's published landmarks (linear 200/3 Hz per mel below 1 kHz, 27 mels per factor 6.4 above), the
+    filters against their defining properties (triangles between neighbouring centres, area-normalised), and the dB
+    conversion against its closed form."""
+    import scipy.signal as ss
+    from mr_gan_b200 import realdata
+    rng = np.random.default_rng(1)
+    y = rng.standard_normal(9600)                                         # 0.2 s at 48 kHz, processdata.py:12
+    n_fft, hop = 2048, 512
+    win = ss.get_window('hann', n_fft, fftbins=True)
+    _, _, Z = ss.stft(np.pad(y, n_fft // 2, mode='reflect'), fs=48000, window=win, nperseg=n_fft, noverlap=n_fft - hop,
+                      boundary=None, padded=False)
+    P = np.abs(Z * win.sum()) ** 2                                        # undo scipy's spectrum scaling
+    S = realdata.melspectrogram(y)
+    assert S.shape == (128, 19)
+    np.testing.assert_allclose(S, realdata.mel_filterbank() @ P, rtol=1e-10, atol=1e-12 * S.max())
+    np.testing.assert_allclose(realdata._hz_to_mel([200.0 / 3, 1000.0, 6400.0]), [1.0, 15.0, 42.0], rtol=1e-12)
+    np.testing.assert_allclose(realdata._mel_to_hz([1.0, 15.0, 42.0]), [200.0 / 3, 1000.0, 6400.0], rtol=1e-12)
+    fb = realdata.mel_filterbank()
+    edges = realdata._mel_to_hz(np.linspace(0.0, realdata._hz_to_mel(24000.0), 130))
+    hz = np.arange(1025) * 48000 / 2048.0
+    for m in (40, 90, 127):                                               # wide filters: many FFT bins per triangle
+        tri = np.interp(hz, edges[m:m + 3], [0.0, 1.0, 0.0], left=0.0, right=0.0) * 2.0 / (edges[m + 2] - edges[m])
+        np.testing.assert_allclose(fb[m], tri, atol=1e-12)
+        assert abs(fb[m].sum() * 48000 / 2048.0 - 1.0) < 0.02              # unit area in Hz
+    L = realdata.logamplitude(S)
+    np.testing.assert_allclose(L, np.maximum(10 * np.log10(np.maximum(S, 1e-10) / S.max()), -80.0), atol=1e-9)
+
+
 def test_real_data_loader_and_librosa_free_logmel(tmp_path):
     """dataset() on files in the processed-pickle format of processdata.py:91 (Python-2 protocol), and the numpy
     restatement of librosa's melspectrogram / logamplitude (shape, scale and peak-position properties)."""
