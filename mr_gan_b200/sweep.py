@@ -68,7 +68,10 @@ def assign(groups, world, cost=None):
 def chain_count(nf):
     """Parallel fold chains an epoch of a group of nf folds is captured as (mrgan_api.cu: mrgan_create, MRGAN_CHAINS)."""
     env = os.environ.get("MRGAN_CHAINS")
-    nch = int(env) if env else (4 if nf >= 32 else (2 if nf >= 8 else 1))
+    try:
+        nch = int(env) if env else (4 if nf >= 32 else (2 if nf >= 8 else 1))
+    except ValueError:
+        nch = 1                                  # the library reads it with atoi(): garbage -> 0 -> one chain
     return max(1, min(nch, 16, nf))
 
 
