@@ -185,6 +185,12 @@ def cpu_fold_per_core(D, B, warm_pairs, n_pairs, cores=None):
     return sum(n for n, _ in res) / slowest, cores, slowest
 
 
+def sweep_workload(G, D, ntr, nte, B):
+    """config.workload of the sweep bench: ONE string for both arms (the reference arm times a bounded sample of it)."""
+    return ("mr_gan.py table-1 fold group: %d folds/GPU, force+temperature D=%d, N_train=%d, N_test=%d, B=%d; "
+            "1 step = 1 epoch = %d D+G step-pairs per fold + test pass" % (G, D, ntr, nte, B, ntr // B))
+
+
 def run_reference(args, rank):
     if rank != 0:
         return 0
@@ -197,7 +203,10 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "wall_ms": 1e3 * (time.perf_counter() - t0),
-            "config": {"workload": "mr_gan table-1 folds, force+temperature D=%d, B=50, one fold per host core (CPU sample)" % D},
+            # the b200 arm's workload (table-1 split of 7200 rows: 6000 train / 1200 test); each step here is a bounded sample
+            # of it -- args.ref_pairs step pairs of one fold per host core -- described in cpu_baseline.sample
+            "config": {"workload": sweep_workload(args.folds, D, 6000, 1200, B), "folds_per_gpu": args.folds, "D": D, "batch": B,
+                       "precision": "fp32 (torch CPU)", "parallelism": "one fold per host core, %d cores" % cores},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "host_cpus": os.cpu_count(),
                              "value_one_fold_all_threads": v_one, "threads_one_fold": threads},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -518,9 +527,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": DTYPE[args.precision], "data": "synthetic",
-            "config": {"workload": "mr_gan.py table-1 fold group: %d folds/GPU, force+temperature D=%d, N_train=%d, "
-                                   "N_test=%d, B=%d; 1 step = 1 epoch = %d D+G step-pairs per fold + test pass"
-                                   % (G, D, ntr, nte, B, nb),
+            "config": {"workload": sweep_workload(G, D, ntr, nte, B),
                        "folds_per_gpu": G, "D": D, "batch": B, "precision": args.precision,
                        "l2": "state of the group (%.0f MB) exceeds L2; no flush needed" % (12e-6 * (N_D + N_G) * G),
                        "parallelism": "fold-sharded x%d, no collective" % world},
