@@ -378,7 +378,7 @@ def main():
     ap.add_argument("--dp-batch", type=int, default=8192, help="global batch of the dp workload")
     ap.add_argument("--dp-width", type=int, default=12032, help="input width of the dp workload (1 s contact mic, table 5)")
     ap.add_argument("--epochs", type=int, default=100, help="table1 workload: epochs per fold")
-    ap.add_argument("--group", type=int, default=42, help="table1 workload: folds per handle")
+    ap.add_argument("--group", type=int, default=84, help="table1 workload: largest number of folds per handle")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

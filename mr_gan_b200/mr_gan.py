@@ -189,7 +189,9 @@ def main(argv=None):
     parser.add_argument('--precision', choices=['fp32', 'tf32', 'f16'], default='f16',
                         help='arithmetic of the dense layers: f16 = fp16 operand copies, fp32 accumulation and master weights (default; per-step '
                              'losses within 1e-3 of the oracle, 43 k step-pairs/s per B200); tf32; fp32 = FFMA parity mode (1e-7, 9.8 k)')
-    parser.add_argument('--group', type=int, default=42, help='folds trained side by side per GPU launch (42 = one modality of table 1)')
+    parser.add_argument('--group', type=int, default=84,
+                        help='largest number of folds trained side by side per handle (84 = two modalities of table 1; the GPU saturates at ~74 '
+                             'folds of D=1200; results do not depend on it)')
     parser.add_argument('--data-dir', default='data_processed')
     parser.add_argument('--synthetic', action='store_true', help='synthetic data of the MREO shape instead of the processed pickles')
     parser.add_argument('--host-perm', action='store_true', help='draw the epoch permutations on the host (numpy) instead of on the device')
