@@ -199,6 +199,25 @@ def test_product_never_imports_the_oracle():
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
 
 
+def test_scheduler_mirrors_the_library_chain_rule(monkeypatch):
+    """sweep.chain_count restates how mrgan_create splits a group into concurrent fold chains; order_for_chains balances
+    exactly those ranges, so the two must not drift apart: the rule is read back from the C source."""
+    import re
+    src = open(os.path.join(ROOT, "mr_gan_b200", "csrc", "mrgan_api.cu")).read()
+    m = re.search(r"h->nf >= (\d+) \? (\d+) : \(h->nf >= (\d+) \? (\d+) : (\d+)\)", src)
+    assert m, "chain rule not found in mrgan_api.cu"
+    a, na, b, nb_, nc = map(int, m.groups())
+    kmax = int(re.search(r"constexpr int kMaxChains = (\d+);", src).group(1))
+    monkeypatch.delenv("MRGAN_CHAINS", raising=False)
+    for nf in (1, 2, b - 1, b, a - 1, a, 500):
+        want = na if nf >= a else (nb_ if nf >= b else nc)
+        assert sweep.chain_count(nf) == max(1, min(want, kmax, nf))
+    monkeypatch.setenv("MRGAN_CHAINS", "12")
+    assert sweep.chain_count(74) == 12 and sweep.chain_count(5) == 5
+    monkeypatch.setenv("MRGAN_CHAINS", "999")
+    assert sweep.chain_count(74) == kmax
+
+
 def test_logmel_front_end_against_scipy_stft_and_slaney_landmarks():
     """librosa is absent, so the restated front end (mr_gan.py:45-47) is pinned piecewise: the framing / window / FFT against
     scipy.signal.stft (an independent implementation; centred frames = reflect padding, periodic Hann, hop 512), the mel
